@@ -1,0 +1,298 @@
+/*
+ * nl_abi.h — C ABI of libnlkernels, the B200 (sm_100a) execution engine for
+ * numpyllvm's lazy thunk pipelines.
+ *
+ * This header is the drop-in boundary.  It replaces the seam where the
+ * reference hands a parsed Pipeline to LLVM and later calls the JIT'd loop
+ * (all citations are relative to the reference checkout):
+ *
+ *   reference interface                              replaced by
+ *   -----------------------------------------------  -------------------------
+ *   CompilePipeline()            compiler.cpp:309    nl_plan_compile()
+ *   CompilableOperation()        compiler.cpp:271    nl_plan_compile() rc
+ *   jit_function call            compiler.cpp:87     nl_launch_pipeline()
+ *     (typedef thread.hpp:25)
+ *   ScheduleFunction() alloc     scheduler.cpp:107   nl_malloc()/nl_memset()
+ *   ScheduleFunction() partition scheduler.cpp:133   nl_partition()
+ *   JITFunctionDECREF() gather   compiler.cpp:30-49  nl_finish_filter()
+ *   llvm_finalize_sum_data()     thunk_methods.cpp:133  nl_finish_reduce(),
+ *                                                    nl_finalize_partials()
+ *   thunk_assign_subscript()     thunk_as_mapping.cpp:80  nl_assign_fill(),
+ *     (NumPy setitem on storage)                     nl_assign_copy()
+ *   PyThunk_FromArray() copy     thunk.cpp:30        nl_memcpy_h2d()
+ *   PyThunk_AsArray()            thunk.cpp:119       nl_memcpy_d2h()
+ *   create_threads()/RunThread   scheduler.cpp:161,227  nl_init() (streams)
+ *
+ * Conventions: plain C structs and pointers, `int` return codes (0 = NL_OK,
+ * negative = error, message via nl_last_error()), no exceptions across the
+ * boundary, the caller owns every buffer.  One host thread may drive all
+ * local devices; calls are asynchronous with respect to the device unless the
+ * name says sync.  There is NO CPU fallback: every compute entry point fails
+ * with NL_ERR_NO_DEVICE when no sm_100 device was initialised.
+ */
+#ifndef NL_ABI_H
+#define NL_ABI_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NL_ABI_VERSION 1
+
+/* ---- limits of one fused pipeline (over-long chains are split by the host
+ *      plan optimiser with a materialised temporary) ------------------------ */
+#define NL_MAX_INPUTS   8
+#define NL_MAX_OUTPUTS  4
+#define NL_MAX_NODES    48
+#define NL_MAX_STEPS    64
+#define NL_MAX_TEMPS    3     /* value temporaries of the accumulator machine */
+#define NL_MAX_PTEMPS   3     /* predicate temporaries                        */
+#define NL_MAX_DEVICES  16
+#define NL_N_STREAMS    3     /* per device: 0 compute, 1 host->device, 2 device->host */
+
+/* ---- error codes ---------------------------------------------------------- */
+enum {
+  NL_OK               = 0,
+  NL_ERR_INVALID      = -1,  /* malformed argument / plan                      */
+  NL_ERR_UNSUPPORTED  = -2,  /* well-formed but outside the kernel library     */
+  NL_ERR_SPLIT        = -3,  /* expression exceeds NL_MAX_*: host must split   */
+  NL_ERR_NO_DEVICE    = -4,  /* no CUDA device initialised (no CPU fallback)   */
+  NL_ERR_CUDA         = -5,  /* a CUDA runtime call failed                     */
+  NL_ERR_NCCL         = -6,  /* NCCL missing or a collective failed            */
+  NL_ERR_NOMEM        = -7
+};
+
+/* ---- element types (subset of getLLVMType, compiler.cpp:156-182) ---------- */
+typedef enum {
+  NL_BOOL = 0,   /* NPY_BOOL, one byte, canonical 0x00/0x01 on store (Q4)      */
+  NL_I32  = 1,
+  NL_I64  = 2,
+  NL_F32  = 3,
+  NL_F64  = 4
+} nl_dtype;
+
+/* ---- operators: the per-operator "emitters" of the reference -------------- */
+typedef enum {
+  NL_OP_INPUT  = 0,  /* leaf: ObjectOperation / PipelineOperation (parser.hpp:43-58) */
+  /* T x T -> T */
+  NL_OP_MUL    = 1,  /* llvm_generate_multiply, thunk_as_number.cpp:45 (ints wrap)   */
+  NL_OP_ADD    = 2,
+  NL_OP_SUB    = 3,
+  /* T x T -> bool */
+  NL_OP_GE     = 8,  /* llvm_generate_ge, thunk_as_number.cpp:9 (signed / ordered)   */
+  NL_OP_GT     = 9,
+  NL_OP_LE     = 10,
+  NL_OP_LT     = 11,
+  NL_OP_EQ     = 12,
+  NL_OP_NE     = 13,
+  /* bool x bool -> bool, bool -> bool */
+  NL_OP_AND    = 16,
+  NL_OP_OR     = 17,
+  NL_OP_XOR    = 18,
+  NL_OP_NOT    = 19,
+  /* lhs = value (T), rhs = mask (bool) -> T; skips the element when !mask and
+   * redirects every later store to a compacted index
+   * (llvm_generate_subscript, thunk_as_mapping.cpp:9-21) */
+  NL_OP_FILTER = 24,
+  /* T -> T, cardinality 1, pipeline root only ("parallelbreaker") */
+  NL_OP_MAX    = 32, /* llvm_generate_max, thunk_methods.cpp:70 */
+  NL_OP_MIN    = 33,
+  NL_OP_SUM    = 34, /* llvm_generate_sum, thunk_methods.cpp:114 */
+  /* lhs = value (T), rhs = mask (bool): `if (mask) out[i] = value` at the loop
+   * index, root only — in-place masked assignment (thunk_as_mapping.cpp:80-86
+   * delegated this to NumPy setitem) */
+  NL_OP_WHERE_STORE = 40
+} nl_op;
+
+/* ---- one node of a pipeline's operation tree (parser.hpp:25-87).  Nodes are
+ *      stored in evaluation (post) order: children precede parents; the last
+ *      node is the pipeline root. -------------------------------------------- */
+typedef struct nl_expr_node {
+  int32_t op;       /* nl_op                                                   */
+  int32_t lhs;      /* node index of LHS (unary: the operand), -1 for a leaf   */
+  int32_t rhs;      /* node index of RHS, -1 when unary / leaf                 */
+  int32_t input;    /* NL_OP_INPUT: index into the input table, else -1        */
+  int32_t output;   /* >= 0: Operation::materialize (parser.hpp:37): the value
+                       is stored to outputs[output]; -1: stays in registers    */
+} nl_expr_node;
+
+typedef enum {
+  NL_IN_ARRAY      = 0,  /* DataSource with size > 1: streamed column          */
+  NL_IN_SCALAR_IMM = 1,  /* size-1 source baked as an immediate
+                            (getLLVMConstant, compiler.cpp:125-154)            */
+  NL_IN_SCALAR_DEV = 2   /* size-1 source left on the device (result of a child
+                            reduction pipeline; avoids the host sync that
+                            baking an immediate would need)                    */
+} nl_input_kind;
+
+typedef struct nl_input_desc {
+  int32_t  dtype;     /* nl_dtype of the source                                */
+  int32_t  kind;      /* nl_input_kind                                         */
+  uint64_t imm_bits;  /* NL_IN_SCALAR_IMM: the value, already converted to the
+                         plan dtype, as a bit pattern in the low bytes         */
+} nl_input_desc;
+
+typedef enum {
+  NL_IDX_LOOP    = 0,  /* out[i], i the loop index                              */
+  NL_IDX_COMPACT = 1,  /* out[start + k], k-th element that passed the filter   */
+  NL_IDX_SHARD   = 2,  /* out[thread_nr] — reduction partial                    */
+  NL_IDX_WHERE   = 3   /* out[i] only where the mask holds (in-place assign)    */
+} nl_index_space;
+
+typedef struct nl_output_desc {
+  int32_t dtype;       /* nl_dtype stored                                       */
+  int32_t index_space; /* nl_index_space                                        */
+} nl_output_desc;
+
+/* ---- compiled plan: program of the accumulator machine that the pipeline
+ *      kernel interprets.  Produced by nl_plan_compile(); opaque to callers
+ *      except for the descriptive fields. ------------------------------------ */
+typedef struct nl_plan {
+  int32_t        abi_version;
+  int32_t        dtype;         /* value type T of the register file           */
+  int32_t        n_inputs;
+  int32_t        n_outputs;
+  int32_t        n_steps;
+  int32_t        flags;         /* NL_PLAN_* below                              */
+  int32_t        reduce_op;     /* nl_op of the root reduction or 0             */
+  int32_t        n_temps;       /* value temporaries used                       */
+  nl_input_desc  in[NL_MAX_INPUTS];
+  nl_output_desc out[NL_MAX_OUTPUTS];
+  uint32_t       step[NL_MAX_STEPS];
+} nl_plan;
+
+enum {
+  NL_PLAN_HAS_FILTER  = 1,   /* contains NL_OP_FILTER                           */
+  NL_PLAN_HAS_COMPACT = 2,   /* some output uses NL_IDX_COMPACT (needs the scan)*/
+  NL_PLAN_HAS_REDUCE  = 4,
+  NL_PLAN_HAS_WHERE   = 8
+};
+
+/* ======================= host-only entry points ============================ */
+
+int         nl_abi_version(void);
+const char *nl_last_error(void);            /* thread-local, never NULL         */
+size_t      nl_dtype_size(int dtype);
+
+/* Lower an operation tree to a plan ("CompilePipeline", compiler.cpp:309).
+ * Pure host code; needs no device.  NL_ERR_SPLIT: too many inputs / temps /
+ * steps — split the tree at a node and materialise it.  NL_ERR_UNSUPPORTED:
+ * e.g. an array load after a filter, mixed array dtypes. */
+int nl_plan_compile(const nl_expr_node *nodes, int n_nodes,
+                    const nl_input_desc *inputs, int n_inputs,
+                    nl_plan *plan_out);
+
+/* Human-readable dump of a plan (debug_printer.cpp's role). Returns bytes
+ * written (excluding NUL) or a negative error. */
+int nl_plan_dump(const nl_plan *plan, char *buf, size_t buflen);
+
+/* The reference's range partition (scheduler.cpp:133-147): chunk j of n_chunks
+ * over [0,size); `align` (elements, power of two, 0/1 = none) rounds interior
+ * boundaries down so 128-bit accesses stay aligned.  align = 1 reproduces the
+ * reference exactly. */
+int nl_partition(int64_t size, int n_chunks, int64_t align, int chunk,
+                 int64_t *start_out, int64_t *end_out);
+
+/* ======================= runtime ========================================== */
+
+/* Create per-device streams and scratch.  device_ids == NULL: devices
+ * 0..n_devices-1.  n_devices == 0: every visible device.  Fails with
+ * NL_ERR_NO_DEVICE when there is none. */
+int nl_init(int n_devices, const int *device_ids);
+int nl_shutdown(void);
+int nl_device_count(void);                  /* local devices after nl_init, 0 before */
+int nl_device_info(int dev, char *name, size_t name_len, int *sm_count,
+                   int *cc_major, int *cc_minor, size_t *total_mem);
+
+int nl_malloc(int dev, size_t bytes, void **ptr_out);
+int nl_free(int dev, void *ptr);
+int nl_memset(int dev, int stream, void *ptr, int value, size_t bytes);
+int nl_host_alloc(size_t bytes, void **ptr_out);   /* pinned */
+int nl_host_free(void *ptr);
+int nl_memcpy_h2d(int dev, int stream, void *dst, const void *src, size_t bytes);
+int nl_memcpy_d2h(int dev, int stream, void *dst, const void *src, size_t bytes);
+int nl_memcpy_d2d(int dev, int stream, void *dst, const void *src, size_t bytes);
+/* copy between two local devices (NVLink peer copy), ordered on dst's stream */
+int nl_memcpy_peer(int dst_dev, int stream, void *dst, int src_dev, const void *src, size_t bytes);
+int nl_stream_sync(int dev, int stream);
+int nl_device_sync(int dev);
+/* make `waiter` stream wait for everything enqueued so far on `signaler` */
+int nl_stream_wait(int dev, int waiter, int signaler_dev, int signaler);
+
+/* CUDA-event timing on the launching stream */
+typedef struct nl_event_s *nl_event;
+int nl_event_create(int dev, nl_event *ev_out);
+int nl_event_destroy(nl_event ev);
+int nl_event_record(nl_event ev, int stream);
+int nl_event_sync(nl_event ev);
+int nl_event_elapsed_ms(nl_event start, nl_event stop, float *ms_out);
+
+/* ======================= the hot path ===================================== */
+
+/* Run one fused pipeline over [start,end) of its inputs on device `dev`
+ * (replaces the call of the JIT'd loop, compiler.cpp:87; argument order and
+ * meaning follow the IR prototype, compiler.cpp:340-347):
+ *   outputs[k]      device pointer of output k (caller-allocated; NL_IDX_COMPACT
+ *                   outputs need room for `end` elements — the reference
+ *                   allocates the upper bound too, thunk_as_mapping.cpp:50)
+ *   inputs[k]       device pointer of input k (NULL for NL_IN_SCALAR_IMM)
+ *   output_sizes    DEVICE pointer to n_outputs int64: final index counter of
+ *                   each output — `end`, `start + count`, or `thread_nr`-th
+ *                   slot written => 1 (compiler.cpp:491-508)
+ *   thread_nr       shard / chunk number: slot of a reduction partial
+ * Asynchronous on (dev, stream). */
+int nl_launch_pipeline(const nl_plan *plan, void *const *outputs,
+                       const void *const *inputs, int64_t start, int64_t end,
+                       int64_t *output_sizes, int thread_nr, int dev, int stream);
+
+/* Combine `n` reduction partials in order j = 0..n-1 into out[0]
+ * (llvm_finalize_sum_data, thunk_methods.cpp:133-151; same for max/min).
+ * Device-side, asynchronous. */
+int nl_finalize_partials(int dev, int stream, int reduce_op, int dtype,
+                         const void *partials, int n, void *out);
+
+/* Multi-device finish of a reduction: NCCL allreduce (max/min/sum) of ONE
+ * element of `dtype` at scalar[d] on every local device d, in place, across
+ * the whole communicator (all ranks).  Requires nl_comm_init(). */
+int nl_finish_reduce(int reduce_op, int dtype, void *const *scalar /*[n_local]*/, int stream);
+
+/* Multi-device finish of a filter: allgather the per-shard counts and take the
+ * exclusive scan (the memmove gather of compiler.cpp:36-48 turned into
+ * offsets).  count[d] is a DEVICE pointer to the shard's int64 count on local
+ * device d; offsets[d] is a DEVICE pointer to world_size+1 int64 on device d
+ * receiving the exclusive scan of all shard counts (offsets[world] = total). */
+int nl_finish_filter(const int64_t *const *count, int64_t *const *offsets, int stream);
+
+/* In-place assignment on an evaluated thunk's storage
+ * (thunk_as_mapping.cpp:80-86): dst[lo + k*step] = value for k in [0,count). */
+int nl_assign_fill(int dev, int stream, void *dst, int dtype,
+                   int64_t lo, int64_t step, int64_t count, uint64_t value_bits);
+/* dst[lo + k*step] = src[k] for k in [0,count); src on the same device. */
+int nl_assign_copy(int dev, int stream, void *dst, int dtype,
+                   int64_t lo, int64_t step, int64_t count, const void *src);
+
+/* ======================= communicator (NCCL over NVLink) ================== */
+
+#define NL_UNIQUE_ID_BYTES 128
+int nl_comm_unique_id(void *id_out /*NL_UNIQUE_ID_BYTES*/);
+/* Local device d becomes rank first_rank + d of a world_size communicator.
+ * Single process driving all GPUs: id from nl_comm_unique_id(), first_rank 0,
+ * world_size = nl_device_count().  One process per GPU: rank 0 creates the id,
+ * the host plumbing broadcasts it. */
+int nl_comm_init(const void *id, int world_size, int first_rank);
+int nl_comm_world_size(void);               /* 0 when no communicator            */
+int nl_comm_destroy(void);
+
+/* ======================= introspection ==================================== */
+/* Kernels launched by this library since load (the bench's gpu_launches). */
+uint64_t nl_launch_count(void);
+/* Name and grid of the most recent pipeline launch (for logs / tests). */
+int nl_last_launch_info(char *kernel_name, size_t name_len, int *grid, int *block, int *vec_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NL_ABI_H */
