@@ -42,6 +42,12 @@ extern "C" {
 
 #define NL_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define NL_API __attribute__((visibility("default")))
+#else
+#define NL_API
+#endif
+
 /* ---- limits of one fused pipeline (over-long chains are split by the host
  *      plan optimiser with a materialised temporary) ------------------------ */
 #define NL_MAX_INPUTS   8
@@ -173,27 +179,27 @@ enum {
 
 /* ======================= host-only entry points ============================ */
 
-int         nl_abi_version(void);
-const char *nl_last_error(void);            /* thread-local, never NULL         */
-size_t      nl_dtype_size(int dtype);
+NL_API int         nl_abi_version(void);
+NL_API const char *nl_last_error(void);            /* thread-local, never NULL         */
+NL_API size_t      nl_dtype_size(int dtype);
 
 /* Lower an operation tree to a plan ("CompilePipeline", compiler.cpp:309).
  * Pure host code; needs no device.  NL_ERR_SPLIT: too many inputs / temps /
  * steps — split the tree at a node and materialise it.  NL_ERR_UNSUPPORTED:
  * e.g. an array load after a filter, mixed array dtypes. */
-int nl_plan_compile(const nl_expr_node *nodes, int n_nodes,
+NL_API int nl_plan_compile(const nl_expr_node *nodes, int n_nodes,
                     const nl_input_desc *inputs, int n_inputs,
                     nl_plan *plan_out);
 
 /* Human-readable dump of a plan (debug_printer.cpp's role). Returns bytes
  * written (excluding NUL) or a negative error. */
-int nl_plan_dump(const nl_plan *plan, char *buf, size_t buflen);
+NL_API int nl_plan_dump(const nl_plan *plan, char *buf, size_t buflen);
 
 /* The reference's range partition (scheduler.cpp:133-147): chunk j of n_chunks
  * over [0,size); `align` (elements, power of two, 0/1 = none) rounds interior
  * boundaries down so 128-bit accesses stay aligned.  align = 1 reproduces the
  * reference exactly. */
-int nl_partition(int64_t size, int n_chunks, int64_t align, int chunk,
+NL_API int nl_partition(int64_t size, int n_chunks, int64_t align, int chunk,
                  int64_t *start_out, int64_t *end_out);
 
 /* ======================= runtime ========================================== */
@@ -201,34 +207,34 @@ int nl_partition(int64_t size, int n_chunks, int64_t align, int chunk,
 /* Create per-device streams and scratch.  device_ids == NULL: devices
  * 0..n_devices-1.  n_devices == 0: every visible device.  Fails with
  * NL_ERR_NO_DEVICE when there is none. */
-int nl_init(int n_devices, const int *device_ids);
-int nl_shutdown(void);
-int nl_device_count(void);                  /* local devices after nl_init, 0 before */
-int nl_device_info(int dev, char *name, size_t name_len, int *sm_count,
+NL_API int nl_init(int n_devices, const int *device_ids);
+NL_API int nl_shutdown(void);
+NL_API int nl_device_count(void);                  /* local devices after nl_init, 0 before */
+NL_API int nl_device_info(int dev, char *name, size_t name_len, int *sm_count,
                    int *cc_major, int *cc_minor, size_t *total_mem);
 
-int nl_malloc(int dev, size_t bytes, void **ptr_out);
-int nl_free(int dev, void *ptr);
-int nl_memset(int dev, int stream, void *ptr, int value, size_t bytes);
-int nl_host_alloc(size_t bytes, void **ptr_out);   /* pinned */
-int nl_host_free(void *ptr);
-int nl_memcpy_h2d(int dev, int stream, void *dst, const void *src, size_t bytes);
-int nl_memcpy_d2h(int dev, int stream, void *dst, const void *src, size_t bytes);
-int nl_memcpy_d2d(int dev, int stream, void *dst, const void *src, size_t bytes);
+NL_API int nl_malloc(int dev, size_t bytes, void **ptr_out);
+NL_API int nl_free(int dev, void *ptr);
+NL_API int nl_memset(int dev, int stream, void *ptr, int value, size_t bytes);
+NL_API int nl_host_alloc(size_t bytes, void **ptr_out);   /* pinned */
+NL_API int nl_host_free(void *ptr);
+NL_API int nl_memcpy_h2d(int dev, int stream, void *dst, const void *src, size_t bytes);
+NL_API int nl_memcpy_d2h(int dev, int stream, void *dst, const void *src, size_t bytes);
+NL_API int nl_memcpy_d2d(int dev, int stream, void *dst, const void *src, size_t bytes);
 /* copy between two local devices (NVLink peer copy), ordered on dst's stream */
-int nl_memcpy_peer(int dst_dev, int stream, void *dst, int src_dev, const void *src, size_t bytes);
-int nl_stream_sync(int dev, int stream);
-int nl_device_sync(int dev);
+NL_API int nl_memcpy_peer(int dst_dev, int stream, void *dst, int src_dev, const void *src, size_t bytes);
+NL_API int nl_stream_sync(int dev, int stream);
+NL_API int nl_device_sync(int dev);
 /* make `waiter` stream wait for everything enqueued so far on `signaler` */
-int nl_stream_wait(int dev, int waiter, int signaler_dev, int signaler);
+NL_API int nl_stream_wait(int dev, int waiter, int signaler_dev, int signaler);
 
 /* CUDA-event timing on the launching stream */
 typedef struct nl_event_s *nl_event;
-int nl_event_create(int dev, nl_event *ev_out);
-int nl_event_destroy(nl_event ev);
-int nl_event_record(nl_event ev, int stream);
-int nl_event_sync(nl_event ev);
-int nl_event_elapsed_ms(nl_event start, nl_event stop, float *ms_out);
+NL_API int nl_event_create(int dev, nl_event *ev_out);
+NL_API int nl_event_destroy(nl_event ev);
+NL_API int nl_event_record(nl_event ev, int stream);
+NL_API int nl_event_sync(nl_event ev);
+NL_API int nl_event_elapsed_ms(nl_event start, nl_event stop, float *ms_out);
 
 /* ======================= the hot path ===================================== */
 
@@ -244,53 +250,60 @@ int nl_event_elapsed_ms(nl_event start, nl_event stop, float *ms_out);
  *                   slot written => 1 (compiler.cpp:491-508)
  *   thread_nr       shard / chunk number: slot of a reduction partial
  * Asynchronous on (dev, stream). */
-int nl_launch_pipeline(const nl_plan *plan, void *const *outputs,
+NL_API int nl_launch_pipeline(const nl_plan *plan, void *const *outputs,
                        const void *const *inputs, int64_t start, int64_t end,
                        int64_t *output_sizes, int thread_nr, int dev, int stream);
 
 /* Combine `n` reduction partials in order j = 0..n-1 into out[0]
  * (llvm_finalize_sum_data, thunk_methods.cpp:133-151; same for max/min).
  * Device-side, asynchronous. */
-int nl_finalize_partials(int dev, int stream, int reduce_op, int dtype,
+NL_API int nl_finalize_partials(int dev, int stream, int reduce_op, int dtype,
                          const void *partials, int n, void *out);
 
 /* Multi-device finish of a reduction: NCCL allreduce (max/min/sum) of ONE
  * element of `dtype` at scalar[d] on every local device d, in place, across
  * the whole communicator (all ranks).  Requires nl_comm_init(). */
-int nl_finish_reduce(int reduce_op, int dtype, void *const *scalar /*[n_local]*/, int stream);
+NL_API int nl_finish_reduce(int reduce_op, int dtype, void *const *scalar /*[n_local]*/, int stream);
 
 /* Multi-device finish of a filter: allgather the per-shard counts and take the
  * exclusive scan (the memmove gather of compiler.cpp:36-48 turned into
  * offsets).  count[d] is a DEVICE pointer to the shard's int64 count on local
  * device d; offsets[d] is a DEVICE pointer to world_size+1 int64 on device d
  * receiving the exclusive scan of all shard counts (offsets[world] = total). */
-int nl_finish_filter(const int64_t *const *count, int64_t *const *offsets, int stream);
+NL_API int nl_finish_filter(const int64_t *const *count, int64_t *const *offsets, int stream);
 
 /* In-place assignment on an evaluated thunk's storage
  * (thunk_as_mapping.cpp:80-86): dst[lo + k*step] = value for k in [0,count). */
-int nl_assign_fill(int dev, int stream, void *dst, int dtype,
+NL_API int nl_assign_fill(int dev, int stream, void *dst, int dtype,
                    int64_t lo, int64_t step, int64_t count, uint64_t value_bits);
 /* dst[lo + k*step] = src[k] for k in [0,count); src on the same device. */
-int nl_assign_copy(int dev, int stream, void *dst, int dtype,
+NL_API int nl_assign_copy(int dev, int stream, void *dst, int dtype,
                    int64_t lo, int64_t step, int64_t count, const void *src);
+
+/* Synthetic column generator for benchmarks and tests, bit-identical to the
+ * oracle's nlo_fill: x[i] = f(splitmix64(seed ^ (first_index + i))).
+ * kind 0: ints uniform in [1,100); 1: full-range ints; 2: floats in [1,2);
+ * 3: floats in [0,1).   */
+NL_API int nl_fill(int dev, int stream, void *dst, int dtype, int64_t first_index,
+            int64_t count, uint64_t seed, int kind);
 
 /* ======================= communicator (NCCL over NVLink) ================== */
 
 #define NL_UNIQUE_ID_BYTES 128
-int nl_comm_unique_id(void *id_out /*NL_UNIQUE_ID_BYTES*/);
+NL_API int nl_comm_unique_id(void *id_out /*NL_UNIQUE_ID_BYTES*/);
 /* Local device d becomes rank first_rank + d of a world_size communicator.
  * Single process driving all GPUs: id from nl_comm_unique_id(), first_rank 0,
  * world_size = nl_device_count().  One process per GPU: rank 0 creates the id,
  * the host plumbing broadcasts it. */
-int nl_comm_init(const void *id, int world_size, int first_rank);
-int nl_comm_world_size(void);               /* 0 when no communicator            */
-int nl_comm_destroy(void);
+NL_API int nl_comm_init(const void *id, int world_size, int first_rank);
+NL_API int nl_comm_world_size(void);               /* 0 when no communicator            */
+NL_API int nl_comm_destroy(void);
 
 /* ======================= introspection ==================================== */
 /* Kernels launched by this library since load (the bench's gpu_launches). */
-uint64_t nl_launch_count(void);
+NL_API uint64_t nl_launch_count(void);
 /* Name and grid of the most recent pipeline launch (for logs / tests). */
-int nl_last_launch_info(char *kernel_name, size_t name_len, int *grid, int *block, int *vec_elems);
+NL_API int nl_last_launch_info(char *kernel_name, size_t name_len, int *grid, int *block, int *vec_elems);
 
 #ifdef __cplusplus
 }

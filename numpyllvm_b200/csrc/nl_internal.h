@@ -1,0 +1,58 @@
+// nl_internal.h — declarations shared by the translation units of libnlkernels.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#include "nl_abi.h"
+
+namespace nl {
+
+void set_error(const char *fmt, ...);
+
+// ---- kernel parameters of the pipeline kernel (passed as __grid_constant__) -------
+struct KParams {
+  const void *in[NL_MAX_INPUTS];
+  uint64_t imm[NL_MAX_INPUTS];
+  void *out[NL_MAX_OUTPUTS];
+  int64_t start, end;         // element range of this launch (indices into in[]/out[])
+  int64_t n_tiles;
+  int64_t *out_sizes;         // device, n_outputs entries
+  // scratch (per device+stream arena)
+  unsigned long long *tile_desc;  // decoupled look-back descriptors, n_tiles entries, zeroed
+  unsigned int *tile_ticket;      // dynamic tile counter, zeroed
+  unsigned long long *red_partials;  // one 8-byte partial per CTA
+  unsigned int *red_ticket;       // self-resetting
+  uint32_t step[NL_MAX_STEPS];
+  int32_t n_steps;
+  int32_t n_outputs;
+  int32_t thread_nr;
+  int32_t reduce_rop;             // ROp of the root reduction
+  int32_t reduce_out;             // its output slot
+  uint8_t in_kind[NL_MAX_INPUTS];
+  uint8_t out_space[NL_MAX_OUTPUTS];
+};
+
+// geometry of the pipeline kernel
+constexpr int kBlock = 256;       // threads per CTA (8 warps)
+constexpr int kRows = 4;          // U: vectors per thread per tile
+constexpr int kMinBlocks = 2;     // resident CTAs per SM the register allocation must allow
+
+struct LaunchInfo {
+  char kernel[96];
+  int grid, block, vec_elems;
+};
+
+// nl_kernels.cu
+int launch_pipeline_kernel(const nl_plan *plan, const KParams &kp, bool vec16, int sm_count,
+                           void *stream /*cudaStream_t*/, LaunchInfo *info);
+int launch_finalize_partials(void *stream, int rop, int dtype, const void *partials, int n, void *out);
+int launch_assign_fill(void *stream, int sm_count, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, uint64_t bits);
+int launch_assign_copy(void *stream, int sm_count, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, const void *src);
+int launch_scan_offsets(void *stream, const int64_t *counts, int n, int64_t *offsets);
+int launch_fill(void *stream, int sm_count, void *dst, int dtype, int64_t first_index, int64_t count, uint64_t seed, int kind);
+int launch_empty_range(void *stream, const nl_plan *plan, const KParams &kp);
+int pipeline_kernel_occupancy(int dtype, bool vec16, bool compact, bool reduce, int *blocks_per_sm, int *regs);
+
+void count_launch(int n = 1);
+
+}  // namespace nl

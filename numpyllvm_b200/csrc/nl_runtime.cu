@@ -1,0 +1,562 @@
+// nl_runtime.cu — device runtime behind the C-ABI: what the reference's scheduler
+// (scheduler.cpp) and worker thread (thread.cpp) become on B200.  The
+// moodycamel task queue + one pthread worker are replaced by in-order CUDA
+// streams per device; the "tasks" are kernel launches, dependencies are stream
+// order and events.  NCCL is bound lazily with dlopen so the library loads (and
+// the host-only entry points work) on a machine without GPUs or NCCL.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and enums only; symbols are resolved with dlsym
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "nl_internal.h"
+#include "nl_step.h"
+
+namespace nl {
+
+#define CUDA_TRY(expr)                                                             \
+  do {                                                                             \
+    cudaError_t e_ = (expr);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(e_));                   \
+      return NL_ERR_CUDA;                                                          \
+    }                                                                              \
+  } while (0)
+
+// scratch arena layout (per device and stream; launches on one stream are ordered)
+constexpr size_t kRedTicketOff = 0;            // u32, self-resetting
+constexpr size_t kRedPartialsOff = 256;        // 8 B x kMaxGrid
+constexpr size_t kMaxGrid = 8192;
+constexpr size_t kTileTicketOff = kRedPartialsOff + 8 * kMaxGrid;   // u32, zeroed per compact launch
+constexpr size_t kTileDescOff = kTileTicketOff + 256;               // 8 B x n_tiles, zeroed per compact launch
+constexpr size_t kGatherOff = 0;               // gather buffer lives in its own small allocation
+
+struct Scratch {
+  char *base = nullptr;
+  size_t bytes = 0;
+};
+
+struct Device {
+  int id = -1;
+  int sm_count = 0;
+  cudaStream_t stream[NL_N_STREAMS] = {nullptr, nullptr, nullptr};
+  Scratch scratch[NL_N_STREAMS];
+  int64_t *gather = nullptr;        // world_size int64 for the count allgather
+  ncclComm_t comm = nullptr;
+};
+
+static Device g_dev[NL_MAX_DEVICES];
+static int g_ndev = 0;
+static int g_world = 0, g_first_rank = 0;
+static std::atomic<uint64_t> g_launches{0};
+static LaunchInfo g_last_info = {"", 0, 0, 0};
+static std::mutex g_mu;
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int check_dev(int dev, int stream) {
+  if (g_ndev == 0) { set_error("no CUDA device initialised (call nl_init; there is no CPU fallback)"); return NL_ERR_NO_DEVICE; }
+  if (dev < 0 || dev >= g_ndev) { set_error("device index %d out of range (0..%d)", dev, g_ndev - 1); return NL_ERR_INVALID; }
+  if (stream < 0 || stream >= NL_N_STREAMS) { set_error("stream index %d out of range", stream); return NL_ERR_INVALID; }
+  return NL_OK;
+}
+
+static int ensure_scratch(Device &d, int stream, size_t need) {
+  Scratch &s = d.scratch[stream];
+  if (s.bytes >= need) return NL_OK;
+  if (s.base) {
+    CUDA_TRY(cudaStreamSynchronize(d.stream[stream]));
+    CUDA_TRY(cudaFree(s.base));
+    s.base = nullptr;
+    s.bytes = 0;
+  }
+  size_t want = need + (need >> 2) + (1u << 20);
+  CUDA_TRY(cudaMalloc((void **)&s.base, want));
+  CUDA_TRY(cudaMemsetAsync(s.base, 0, kTileDescOff, d.stream[stream]));
+  s.bytes = want;
+  return NL_OK;
+}
+
+// ------------------------------------------------------------------ NCCL binding
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.handle) return NL_OK;
+  // the bare soname resolves to an already-loaded libnccl (e.g. the one torch bundles) first
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (const char *n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) { set_error("NCCL not found: %s", dlerror()); return NL_ERR_NCCL; }
+#define BIND(field, sym)                                                     \
+  *(void **)(&g_nccl.field) = dlsym(h, sym);                                 \
+  if (!g_nccl.field) { set_error("NCCL symbol %s missing", sym); return NL_ERR_NCCL; }
+  BIND(GetUniqueId, "ncclGetUniqueId")
+  BIND(CommInitRank, "ncclCommInitRank")
+  BIND(CommDestroy, "ncclCommDestroy")
+  BIND(AllReduce, "ncclAllReduce")
+  BIND(AllGather, "ncclAllGather")
+  BIND(GroupStart, "ncclGroupStart")
+  BIND(GroupEnd, "ncclGroupEnd")
+  BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+  g_nccl.handle = h;
+  return NL_OK;
+}
+
+#define NCCL_TRY(expr)                                                             \
+  do {                                                                             \
+    ncclResult_t r_ = (expr);                                                      \
+    if (r_ != ncclSuccess) {                                                       \
+      set_error("%s failed: %s", #expr, g_nccl.GetErrorString(r_));                \
+      return NL_ERR_NCCL;                                                          \
+    }                                                                              \
+  } while (0)
+
+}  // namespace nl
+
+using namespace nl;
+
+extern "C" {
+
+// ======================================================================= runtime
+int nl_init(int n_devices, const int *device_ids) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_ndev > 0) return NL_OK;   // idempotent
+  int visible = 0;
+  cudaError_t e = cudaGetDeviceCount(&visible);
+  if (e != cudaSuccess || visible == 0) {
+    set_error("no CUDA device visible (%s); numpyllvm_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count is 0");
+    cudaGetLastError();
+    return NL_ERR_NO_DEVICE;
+  }
+  if (n_devices <= 0) n_devices = visible;
+  if (n_devices > NL_MAX_DEVICES) n_devices = NL_MAX_DEVICES;
+  if (n_devices > visible && !device_ids) { set_error("%d devices requested, %d visible", n_devices, visible); return NL_ERR_INVALID; }
+  for (int d = 0; d < n_devices; d++) {
+    Device &dv = g_dev[d];
+    dv.id = device_ids ? device_ids[d] : d;
+    CUDA_TRY(cudaSetDevice(dv.id));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dv.id));
+    if (prop.major < 10) { set_error("device %d is sm_%d%d; the kernel library is built for sm_100a only", dv.id, prop.major, prop.minor); return NL_ERR_NO_DEVICE; }
+    dv.sm_count = prop.multiProcessorCount;
+    for (int s = 0; s < NL_N_STREAMS; s++) CUDA_TRY(cudaStreamCreateWithFlags(&dv.stream[s], cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc((void **)&dv.gather, sizeof(int64_t) * 256));
+  }
+  // NVLink peer access between the local devices (shard concat, peer copies)
+  for (int a = 0; a < n_devices; a++)
+    for (int b = 0; b < n_devices; b++) {
+      if (a == b) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, g_dev[a].id, g_dev[b].id) == cudaSuccess && can) {
+        cudaSetDevice(g_dev[a].id);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(g_dev[b].id, 0);
+        if (pe != cudaSuccess) cudaGetLastError();   // already enabled is fine
+      }
+    }
+  g_ndev = n_devices;
+  return NL_OK;
+}
+
+int nl_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int d = 0; d < g_ndev; d++) {
+    Device &dv = g_dev[d];
+    cudaSetDevice(dv.id);
+    cudaDeviceSynchronize();
+    if (dv.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(dv.comm);
+    dv.comm = nullptr;
+    for (int s = 0; s < NL_N_STREAMS; s++) {
+      if (dv.scratch[s].base) cudaFree(dv.scratch[s].base);
+      dv.scratch[s] = Scratch();
+      if (dv.stream[s]) cudaStreamDestroy(dv.stream[s]);
+      dv.stream[s] = nullptr;
+    }
+    if (dv.gather) cudaFree(dv.gather);
+    dv.gather = nullptr;
+  }
+  g_ndev = 0;
+  g_world = 0;
+  return NL_OK;
+}
+
+int nl_device_count(void) { return g_ndev; }
+
+int nl_device_info(int dev, char *name, size_t name_len, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, g_dev[dev].id));
+  if (name && name_len) snprintf(name, name_len, "%s", prop.name);
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (total_mem) *total_mem = prop.totalGlobalMem;
+  return NL_OK;
+}
+
+int nl_malloc(int dev, size_t bytes, void **ptr_out) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  if (!ptr_out) { set_error("nl_malloc: null ptr_out"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  cudaError_t e = cudaMalloc(ptr_out, bytes ? bytes : 1);
+  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); set_error("out of device memory allocating %zu bytes", bytes); return NL_ERR_NOMEM; }
+  CUDA_TRY(e);
+  return NL_OK;
+}
+
+int nl_free(int dev, void *ptr) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  if (!ptr) return NL_OK;
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  CUDA_TRY(cudaFree(ptr));
+  return NL_OK;
+}
+
+int nl_memset(int dev, int stream, void *ptr, int value, size_t bytes) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  CUDA_TRY(cudaMemsetAsync(ptr, value, bytes, g_dev[dev].stream[stream]));
+  return NL_OK;
+}
+
+int nl_host_alloc(size_t bytes, void **ptr_out) {
+  if (g_ndev == 0) { set_error("nl_host_alloc: no device initialised"); return NL_ERR_NO_DEVICE; }
+  if (!ptr_out) { set_error("nl_host_alloc: null ptr_out"); return NL_ERR_INVALID; }
+  cudaError_t e = cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); set_error("out of pinned host memory allocating %zu bytes", bytes); return NL_ERR_NOMEM; }
+  CUDA_TRY(e);
+  return NL_OK;
+}
+
+int nl_host_free(void *ptr) {
+  if (!ptr) return NL_OK;
+  CUDA_TRY(cudaFreeHost(ptr));
+  return NL_OK;
+}
+
+static int copy_async(int dev, int stream, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (bytes == 0) return NL_OK;
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, kind, g_dev[dev].stream[stream]));
+  return NL_OK;
+}
+int nl_memcpy_h2d(int dev, int stream, void *dst, const void *src, size_t bytes) { return copy_async(dev, stream, dst, src, bytes, cudaMemcpyHostToDevice); }
+int nl_memcpy_d2h(int dev, int stream, void *dst, const void *src, size_t bytes) { return copy_async(dev, stream, dst, src, bytes, cudaMemcpyDeviceToHost); }
+int nl_memcpy_d2d(int dev, int stream, void *dst, const void *src, size_t bytes) { return copy_async(dev, stream, dst, src, bytes, cudaMemcpyDeviceToDevice); }
+
+int nl_memcpy_peer(int dst_dev, int stream, void *dst, int src_dev, const void *src, size_t bytes) {
+  int rc = check_dev(dst_dev, stream);
+  if (rc) return rc;
+  rc = check_dev(src_dev, 0);
+  if (rc) return rc;
+  if (bytes == 0) return NL_OK;
+  CUDA_TRY(cudaSetDevice(g_dev[dst_dev].id));
+  CUDA_TRY(cudaMemcpyPeerAsync(dst, g_dev[dst_dev].id, src, g_dev[src_dev].id, bytes, g_dev[dst_dev].stream[stream]));
+  return NL_OK;
+}
+
+int nl_stream_sync(int dev, int stream) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(g_dev[dev].stream[stream]));
+  return NL_OK;
+}
+
+int nl_device_sync(int dev) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  CUDA_TRY(cudaDeviceSynchronize());
+  return NL_OK;
+}
+
+int nl_stream_wait(int dev, int waiter, int signaler_dev, int signaler) {
+  int rc = check_dev(dev, waiter);
+  if (rc) return rc;
+  rc = check_dev(signaler_dev, signaler);
+  if (rc) return rc;
+  cudaEvent_t ev;
+  CUDA_TRY(cudaSetDevice(g_dev[signaler_dev].id));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(ev, g_dev[signaler_dev].stream[signaler]));
+  CUDA_TRY(cudaStreamWaitEvent(g_dev[dev].stream[waiter], ev, 0));
+  CUDA_TRY(cudaEventDestroy(ev));   // released once the wait has consumed it
+  return NL_OK;
+}
+
+struct nl_event_s {
+  cudaEvent_t ev;
+  int dev;
+};
+
+int nl_event_create(int dev, nl_event *ev_out) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  if (!ev_out) { set_error("nl_event_create: null"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  nl_event_s *e = new nl_event_s;
+  e->dev = dev;
+  cudaError_t ce = cudaEventCreate(&e->ev);
+  if (ce != cudaSuccess) { delete e; CUDA_TRY(ce); }
+  *ev_out = e;
+  return NL_OK;
+}
+int nl_event_destroy(nl_event ev) {
+  if (!ev) return NL_OK;
+  cudaEventDestroy(ev->ev);
+  delete ev;
+  return NL_OK;
+}
+int nl_event_record(nl_event ev, int stream) {
+  if (!ev) { set_error("null event"); return NL_ERR_INVALID; }
+  int rc = check_dev(ev->dev, stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(g_dev[ev->dev].id));
+  CUDA_TRY(cudaEventRecord(ev->ev, g_dev[ev->dev].stream[stream]));
+  return NL_OK;
+}
+int nl_event_sync(nl_event ev) {
+  if (!ev) { set_error("null event"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaEventSynchronize(ev->ev));
+  return NL_OK;
+}
+int nl_event_elapsed_ms(nl_event start, nl_event stop, float *ms_out) {
+  if (!start || !stop || !ms_out) { set_error("null event"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaEventElapsedTime(ms_out, start->ev, stop->ev));
+  return NL_OK;
+}
+
+// ======================================================================= hot path
+int nl_launch_pipeline(const nl_plan *plan, void *const *outputs, const void *const *inputs, int64_t start,
+                       int64_t end, int64_t *output_sizes, int thread_nr, int dev, int stream) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (!plan || plan->abi_version != NL_ABI_VERSION) { set_error("nl_launch_pipeline: bad plan / ABI version"); return NL_ERR_INVALID; }
+  if (plan->n_steps <= 0 || plan->n_steps > NL_MAX_STEPS || plan->n_inputs > NL_MAX_INPUTS || plan->n_outputs <= 0 ||
+      plan->n_outputs > NL_MAX_OUTPUTS) { set_error("nl_launch_pipeline: plan out of range"); return NL_ERR_INVALID; }
+  if (!outputs || (plan->n_inputs > 0 && !inputs) || !output_sizes) { set_error("nl_launch_pipeline: null argument"); return NL_ERR_INVALID; }
+  if (start < 0 || end < start || thread_nr < 0) { set_error("nl_launch_pipeline: bad range [%lld,%lld) / thread_nr", (long long)start, (long long)end); return NL_ERR_INVALID; }
+  const size_t tsize = nl_dtype_size(plan->dtype);
+  if (tsize != 4 && tsize != 8) { set_error("nl_launch_pipeline: bad plan dtype"); return NL_ERR_INVALID; }
+
+  Device &d = g_dev[dev];
+  CUDA_TRY(cudaSetDevice(d.id));
+
+  KParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const int V16 = (int)(16 / tsize);
+  bool vec16 = true;
+  for (int k = 0; k < plan->n_inputs; k++) {
+    kp.in[k] = inputs[k];
+    kp.imm[k] = plan->in[k].imm_bits;
+    kp.in_kind[k] = (uint8_t)plan->in[k].kind;
+    if (plan->in[k].kind != NL_IN_SCALAR_IMM && !inputs[k]) { set_error("input %d is a null pointer", k); return NL_ERR_INVALID; }
+    if (plan->in[k].kind == NL_IN_ARRAY) {
+      const size_t es = nl_dtype_size(plan->in[k].dtype);
+      const uintptr_t addr = (uintptr_t)inputs[k] + (uintptr_t)start * es;
+      if (addr % (es * V16)) vec16 = false;
+    }
+  }
+  for (int o = 0; o < plan->n_outputs; o++) {
+    if (!outputs[o]) { set_error("output %d is a null pointer", o); return NL_ERR_INVALID; }
+    kp.out[o] = outputs[o];
+    kp.out_space[o] = (uint8_t)plan->out[o].index_space;
+    if (plan->out[o].index_space == NL_IDX_LOOP || plan->out[o].index_space == NL_IDX_WHERE) {
+      const size_t es = nl_dtype_size(plan->out[o].dtype);
+      const uintptr_t addr = (uintptr_t)outputs[o] + (uintptr_t)start * es;
+      if (addr % (es * V16)) vec16 = false;
+    }
+  }
+  kp.start = start;
+  kp.end = end;
+  kp.out_sizes = output_sizes;
+  kp.n_steps = plan->n_steps;
+  kp.n_outputs = plan->n_outputs;
+  kp.thread_nr = thread_nr;
+  memcpy(kp.step, plan->step, sizeof(uint32_t) * (size_t)plan->n_steps);
+  for (int i = 0; i < plan->n_steps; i++)
+    if (step_op(plan->step[i]) == S_REDUCE) { kp.reduce_rop = (int32_t)step_a(plan->step[i]); kp.reduce_out = (int32_t)step_b(plan->step[i]); }
+
+  if (end == start) return launch_empty_range(d.stream[stream], plan, kp);
+
+  const int V = vec16 ? V16 : 1;
+  const int64_t tile = (int64_t)kBlock * kRows * V;
+  kp.n_tiles = (end - start + tile - 1) / tile;
+  const bool compact = (plan->flags & NL_PLAN_HAS_COMPACT) != 0;
+  const size_t need = kTileDescOff + (compact ? (size_t)kp.n_tiles * 8 : 0);
+  rc = ensure_scratch(d, stream, need);
+  if (rc) return rc;
+  char *sb = d.scratch[stream].base;
+  kp.red_ticket = (unsigned int *)(sb + kRedTicketOff);
+  kp.red_partials = (unsigned long long *)(sb + kRedPartialsOff);
+  kp.tile_ticket = (unsigned int *)(sb + kTileTicketOff);
+  kp.tile_desc = (unsigned long long *)(sb + kTileDescOff);
+  if (compact)
+    CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (size_t)kp.n_tiles * 8, d.stream[stream]));
+
+  LaunchInfo info;
+  rc = launch_pipeline_kernel(plan, kp, vec16, d.sm_count, d.stream[stream], &info);
+  if (rc == NL_OK) g_last_info = info;
+  return rc;
+}
+
+static int rop_of(int reduce_op) { return reduce_op == NL_OP_MAX ? R_MAX : reduce_op == NL_OP_MIN ? R_MIN : reduce_op == NL_OP_SUM ? R_SUM : -1; }
+
+int nl_finalize_partials(int dev, int stream, int reduce_op, int dtype, const void *partials, int n, void *out) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (rop_of(reduce_op) < 0 || !partials || !out || n < 0) { set_error("nl_finalize_partials: bad argument"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_finalize_partials(g_dev[dev].stream[stream], rop_of(reduce_op), dtype, partials, n, out);
+}
+
+int nl_assign_fill(int dev, int stream, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, uint64_t value_bits) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (!dst || lo < 0 || count < 0 || step == 0) { set_error("nl_assign_fill: bad argument"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_assign_fill(g_dev[dev].stream[stream], g_dev[dev].sm_count, dst, dtype, lo, step, count, value_bits);
+}
+
+int nl_assign_copy(int dev, int stream, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, const void *src) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (!dst || !src || lo < 0 || count < 0 || step == 0) { set_error("nl_assign_copy: bad argument"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_assign_copy(g_dev[dev].stream[stream], g_dev[dev].sm_count, dst, dtype, lo, step, count, src);
+}
+
+int nl_fill(int dev, int stream, void *dst, int dtype, int64_t first_index, int64_t count, uint64_t seed, int kind) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (!dst || count < 0) { set_error("nl_fill: bad argument"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_fill(g_dev[dev].stream[stream], g_dev[dev].sm_count, dst, dtype, first_index, count, seed, kind);
+}
+
+// ======================================================================= communicator
+int nl_comm_unique_id(void *id_out) {
+  if (!id_out) { set_error("nl_comm_unique_id: null"); return NL_ERR_INVALID; }
+  int rc = load_nccl();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == NL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  memcpy(id_out, &id, sizeof(id));
+  return NL_OK;
+}
+
+int nl_comm_init(const void *id, int world_size, int first_rank) {
+  if (g_ndev == 0) { set_error("nl_comm_init before nl_init"); return NL_ERR_NO_DEVICE; }
+  if (!id || world_size < g_ndev || first_rank < 0 || first_rank + g_ndev > world_size || world_size > 256) { set_error("nl_comm_init: bad argument"); return NL_ERR_INVALID; }
+  int rc = load_nccl();
+  if (rc) return rc;
+  if (g_world) { set_error("communicator already initialised"); return NL_ERR_INVALID; }
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int d = 0; d < g_ndev; d++) {
+    CUDA_TRY(cudaSetDevice(g_dev[d].id));
+    NCCL_TRY(g_nccl.CommInitRank(&g_dev[d].comm, world_size, uid, first_rank + d));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  g_world = world_size;
+  g_first_rank = first_rank;
+  return NL_OK;
+}
+
+int nl_comm_world_size(void) { return g_world; }
+
+int nl_comm_destroy(void) {
+  for (int d = 0; d < g_ndev; d++) {
+    if (g_dev[d].comm && g_nccl.CommDestroy) {
+      cudaSetDevice(g_dev[d].id);
+      g_nccl.CommDestroy(g_dev[d].comm);
+    }
+    g_dev[d].comm = nullptr;
+  }
+  g_world = 0;
+  return NL_OK;
+}
+
+int nl_finish_reduce(int reduce_op, int dtype, void *const *scalar, int stream) {
+  int rc = check_dev(0, stream);
+  if (rc) return rc;
+  if (rop_of(reduce_op) < 0 || !scalar) { set_error("nl_finish_reduce: bad argument"); return NL_ERR_INVALID; }
+  if (g_world <= 1 && g_ndev == 1) return NL_OK;     // a single shard: its partial is the result
+  if (!g_world) { set_error("nl_finish_reduce: %d local devices but no communicator (call nl_comm_init)", g_ndev); return NL_ERR_NCCL; }
+  ncclDataType_t t;
+  switch (dtype) {
+    case NL_I32: t = ncclInt32; break;
+    case NL_I64: t = ncclInt64; break;
+    case NL_F32: t = ncclFloat32; break;
+    case NL_F64: t = ncclFloat64; break;
+    default: set_error("nl_finish_reduce: bad dtype"); return NL_ERR_INVALID;
+  }
+  const ncclRedOp_t op = reduce_op == NL_OP_MAX ? ncclMax : reduce_op == NL_OP_MIN ? ncclMin : ncclSum;
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int d = 0; d < g_ndev; d++) {
+    if (!scalar[d]) { g_nccl.GroupEnd(); set_error("nl_finish_reduce: null scalar for device %d", d); return NL_ERR_INVALID; }
+    NCCL_TRY(g_nccl.AllReduce(scalar[d], scalar[d], 1, t, op, g_dev[d].comm, g_dev[d].stream[stream]));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  return NL_OK;
+}
+
+int nl_finish_filter(const int64_t *const *count, int64_t *const *offsets, int stream) {
+  int rc = check_dev(0, stream);
+  if (rc) return rc;
+  if (!count || !offsets) { set_error("nl_finish_filter: null"); return NL_ERR_INVALID; }
+  const int world = (g_world > 0) ? g_world : 1;
+  if (world == 1 && g_ndev > 1) { set_error("nl_finish_filter: %d local devices but no communicator", g_ndev); return NL_ERR_NCCL; }
+  if (world > 1) {
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int d = 0; d < g_ndev; d++)
+      NCCL_TRY(g_nccl.AllGather(count[d], g_dev[d].gather, 1, ncclInt64, g_dev[d].comm, g_dev[d].stream[stream]));
+    NCCL_TRY(g_nccl.GroupEnd());
+  }
+  for (int d = 0; d < g_ndev; d++) {
+    CUDA_TRY(cudaSetDevice(g_dev[d].id));
+    const int64_t *src = (world > 1) ? g_dev[d].gather : count[d];
+    rc = launch_scan_offsets(g_dev[d].stream[stream], src, world, offsets[d]);
+    if (rc) return rc;
+  }
+  return NL_OK;
+}
+
+// ======================================================================= introspection
+uint64_t nl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int nl_last_launch_info(char *kernel_name, size_t name_len, int *grid, int *block, int *vec_elems) {
+  if (kernel_name && name_len) snprintf(kernel_name, name_len, "%s", g_last_info.kernel);
+  if (grid) *grid = g_last_info.grid;
+  if (block) *block = g_last_info.block;
+  if (vec_elems) *vec_elems = g_last_info.vec_elems;
+  return NL_OK;
+}
+
+}  // extern "C"
