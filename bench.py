@@ -320,6 +320,8 @@ def run_e2e(args, rt, lib, ranks, plan, a, b, c, sizes, n, thousand):
     nchunks = (n + chunk - 1) // chunk
 
     def step():
+        # the uploads overwrite a/b: they may not start before the previous step's kernels are done
+        abi.check(lib.nl_stream_wait(0, 1, 0, 0))
         for i in range(nchunks):
             s, e_ = i * chunk, min(n, (i + 1) * chunk)
             off, nb = 4 * s, 4 * (e_ - s)

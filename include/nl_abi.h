@@ -54,7 +54,7 @@ extern "C" {
 #define NL_MAX_OUTPUTS  4
 #define NL_MAX_NODES    48
 #define NL_MAX_STEPS    64
-#define NL_MAX_TEMPS    3     /* value temporaries of the accumulator machine */
+#define NL_MAX_TEMPS    2     /* value temporaries of the accumulator machine */
 #define NL_MAX_PTEMPS   3     /* predicate temporaries                        */
 #define NL_MAX_DEVICES  16
 #define NL_N_STREAMS    3     /* per device: 0 compute, 1 host->device, 2 device->host */
@@ -302,6 +302,12 @@ NL_API int nl_comm_destroy(void);
 /* ======================= introspection ==================================== */
 /* Kernels launched by this library since load (the bench's gpu_launches). */
 NL_API uint64_t nl_launch_count(void);
+/* Kernel-template selection (the plan optimiser's last stage): name of the kernel a plan
+ * would run — a build-time instantiated shape ("static:<shape>") or the dynamic
+ * interpreter.  Host-only.  vec16: rows of 128 bits (aligned operands) or scalar rows. */
+NL_API int nl_plan_kernel(const nl_plan *plan, int vec16, char *name, size_t name_len, int *is_static);
+/* Testing hook: 0 forces every launch through the dynamic interpreter. */
+NL_API int nl_set_static_kernels(int enabled);
 /* Name and grid of the most recent pipeline launch (for logs / tests). */
 NL_API int nl_last_launch_info(char *kernel_name, size_t name_len, int *grid, int *block, int *vec_elems);
 

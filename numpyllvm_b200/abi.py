@@ -221,6 +221,8 @@ _SIGNATURES = {
     "nl_comm_init": (C.c_int, [_VP, C.c_int, C.c_int]),
     "nl_comm_world_size": (C.c_int, []),
     "nl_comm_destroy": (C.c_int, []),
+    "nl_plan_kernel": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "nl_set_static_kernels": (C.c_int, [C.c_int]),
     "nl_launch_count": (C.c_uint64, []),
     "nl_last_launch_info": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }
@@ -267,6 +269,15 @@ def dump_plan(plan: Plan) -> str:
     buf = C.create_string_buffer(8192)
     check(lib.nl_plan_dump(C.byref(plan), buf, len(buf)))
     return buf.value.decode()
+
+
+def plan_kernel(plan: Plan, vec16: bool = True):
+    """(kernel name, is_static) the library selects for this plan."""
+    lib = load_library()
+    buf = C.create_string_buffer(160)
+    st = C.c_int()
+    check(lib.nl_plan_kernel(C.byref(plan), int(vec16), buf, len(buf), C.byref(st)))
+    return buf.value.decode(), bool(st.value)
 
 
 def void_array(ptrs: Sequence[Optional[int]]):

@@ -29,7 +29,8 @@ CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", f"-I{INCLUDE}", f"-I{CSRC}"]
 
-KERNEL_SOURCES = ["nl_plan.cpp", "nl_kernels.cu", "nl_runtime.cu"]
+KERNEL_SOURCES = ["nl_plan.cpp", "nl_kernels.cu", "nl_runtime.cu",
+                  "nl_static_i32.cu", "nl_static_i64.cu", "nl_static_f32.cu", "nl_static_f64.cu"]
 JIT_SOURCES = ["jitpackage.cpp", "thunk.cpp", "operation.cpp", "thunk_as_number.cpp", "thunk_as_mapping.cpp",
                "thunk_as_sequence.cpp", "thunk_methods.cpp", "parser.cpp", "optimizer.cpp", "scheduler.cpp",
                "debug_printer.cpp"]

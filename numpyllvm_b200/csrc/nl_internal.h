@@ -51,7 +51,8 @@ int launch_assign_copy(void *stream, int sm_count, void *dst, int dtype, int64_t
 int launch_scan_offsets(void *stream, const int64_t *counts, int n, int64_t *offsets);
 int launch_fill(void *stream, int sm_count, void *dst, int dtype, int64_t first_index, int64_t count, uint64_t seed, int kind);
 int launch_empty_range(void *stream, const nl_plan *plan, const KParams &kp);
-int pipeline_kernel_occupancy(int dtype, bool vec16, bool compact, bool reduce, int *blocks_per_sm, int *regs);
+int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t name_len, int *is_static);
+void set_static_kernels_enabled(int on);
 
 void count_launch(int n = 1);
 

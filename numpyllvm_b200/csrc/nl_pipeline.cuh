@@ -1,0 +1,684 @@
+// nl_pipeline.cuh — the fused pipeline kernel template (sm_100a).
+//
+// In the reference every pipeline is ONE fused loop (compiler.cpp:362-509); here it
+// is ONE kernel template, pipeline_kernel<T, V, kCompact, kReduce, Prog>, that runs
+// the plan's accumulator-machine program (nl_step.h) over tiles of
+// kBlock * kRows * V elements.  The program driver `Prog` comes in two kinds that
+// share the same step executor (Tile::exec):
+//
+//   DynProg               reads the step words from the kernel parameters and
+//                         dispatches with warp-uniform branches — the general
+//                         engine for arbitrary thunk expressions;
+//   StaticProg<steps...>  the step words are template arguments, so dispatch,
+//                         unused temporaries and register moves fold away at build
+//                         time — the "kernel templates instantiated at build time"
+//                         for the pipeline shapes in nl_static.cuh.
+//
+// The four paths:
+//   (1) elementwise chains   128-bit coalesced streaming loads (V = 16/sizeof(T)
+//                            elements per access, kRows independent accesses in
+//                            flight per thread per operand), every intermediate in
+//                            registers, grid-stride tiles, 128-bit streaming stores
+//   (2) filter compaction    per-row popc counts, packed warp scan, single-pass
+//                            decoupled look-back across tiles (status + value in one
+//                            64-bit word), stable order, 64-bit offsets
+//   (3) max / min / sum      per-thread tree -> running accumulator -> warp shuffle
+//                            tree -> block tree -> per-CTA partial -> the last CTA
+//                            folds all partials in a fixed order (deterministic)
+//   (4) in-place assignment  masked store at the loop index (S_WHERE)
+//
+// All are HBM-bound streaming kernels: no shared-memory staging of operands (no
+// reuse) and no tensor cores (nothing is a contraction).  Integer arithmetic is done
+// in unsigned for two's-complement wrap; translation units are compiled with
+// -fmad=false so float chains round exactly like the reference's fmul/fadd sequence.
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "nl_internal.h"
+#include "nl_step.h"
+
+namespace nl {
+
+// ------------------------------------------------------------------ type traits
+template <typename T> struct TT;
+template <> struct TT<int32_t> {
+  using U = uint32_t; using Acc = long long; static constexpr bool is_float = false;
+  __device__ static int32_t lowest() { return INT32_MIN; }
+  __device__ static int32_t highest() { return INT32_MAX; }
+};
+template <> struct TT<long long> {
+  using U = unsigned long long; using Acc = long long; static constexpr bool is_float = false;
+  __device__ static long long lowest() { return LLONG_MIN; }
+  __device__ static long long highest() { return LLONG_MAX; }
+};
+template <> struct TT<float> {
+  using U = uint32_t; using Acc = double; static constexpr bool is_float = true;
+  __device__ static float lowest() { return -INFINITY; }
+  __device__ static float highest() { return INFINITY; }
+};
+template <> struct TT<double> {
+  using U = unsigned long long; using Acc = double; static constexpr bool is_float = true;
+  __device__ static double lowest() { return -INFINITY; }
+  __device__ static double highest() { return INFINITY; }
+};
+
+template <typename T> __device__ __forceinline__ T op_mul(T a, T b) {
+  if constexpr (TT<T>::is_float) return a * b; else return (T)((typename TT<T>::U)a * (typename TT<T>::U)b);
+}
+template <typename T> __device__ __forceinline__ T op_add(T a, T b) {
+  if constexpr (TT<T>::is_float) return a + b; else return (T)((typename TT<T>::U)a + (typename TT<T>::U)b);
+}
+template <typename T> __device__ __forceinline__ T op_sub(T a, T b) {
+  if constexpr (TT<T>::is_float) return a - b; else return (T)((typename TT<T>::U)a - (typename TT<T>::U)b);
+}
+// max/min with NumPy semantics: NaN is sticky
+template <typename T> __device__ __forceinline__ T op_max(T cur, T l) {
+  if constexpr (TT<T>::is_float) return (l > cur || l != l) ? l : cur; else return l > cur ? l : cur;
+}
+template <typename T> __device__ __forceinline__ T op_min(T cur, T l) {
+  if constexpr (TT<T>::is_float) return (l < cur || l != l) ? l : cur; else return l < cur ? l : cur;
+}
+__device__ __forceinline__ long long acc_add(long long a, long long b) { return (long long)((unsigned long long)a + (unsigned long long)b); }
+__device__ __forceinline__ double acc_add(double a, double b) { return a + b; }
+
+// ------------------------------------------------------------------ vector access
+template <int BYTES> struct VecOf;
+template <> struct VecOf<16> { using type = uint4; };
+template <> struct VecOf<8> { using type = uint2; };
+template <> struct VecOf<4> { using type = unsigned int; };
+template <> struct VecOf<2> { using type = unsigned short; };
+template <> struct VecOf<1> { using type = unsigned char; };
+
+// one row = V consecutive elements of one thread; streaming (evict-first) 128-bit access
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T *__restrict__ ptr, T *dst) {
+  using Vec = typename VecOf<sizeof(T) * V>::type;
+  union { Vec q; T t[V]; } u;
+  u.q = __ldcs(reinterpret_cast<const Vec *>(ptr));
+#pragma unroll
+  for (int v = 0; v < V; v++) dst[v] = u.t[v];
+}
+template <typename T, int V>
+__device__ __forceinline__ void store_vec(T *__restrict__ ptr, const T *src) {
+  using Vec = typename VecOf<sizeof(T) * V>::type;
+  union { Vec q; T t[V]; } u;
+#pragma unroll
+  for (int v = 0; v < V; v++) u.t[v] = src[v];
+  __stcs(reinterpret_cast<Vec *>(ptr), u.q);
+}
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ T from_bits(uint64_t bits) {
+  if constexpr (sizeof(T) == 8) { union { uint64_t b; T t; } u; u.b = bits; return u.t; }
+  else { union { uint32_t b; T t; } u; u.b = (uint32_t)bits; return u.t; }
+}
+template <typename T> __device__ __forceinline__ unsigned long long to_bits(T v) {
+  if constexpr (sizeof(T) == 8) { union { unsigned long long b; T t; } u; u.t = v; return u.b; }
+  else { union { uint32_t b; T t; } u; u.t = v; return u.b; }
+}
+
+constexpr unsigned long long kDescValueMask = (1ull << 62) - 1;
+constexpr unsigned long long kDescAggregate = 1ull << 62;
+constexpr unsigned long long kDescPrefix = 2ull << 62;
+
+// shared memory of one CTA (tiny: scan totals, the look-back result, the reduce tree)
+struct TileShared {
+  uint32_t wtot[kBlock / 32];          // per-warp packed row totals
+  uint32_t off[kRows * (kBlock / 32)]; // exclusive offset of (row, warp) inside the tile
+  long long prefix;                    // elements kept before this tile
+  long long tile;                      // dynamically claimed tile id
+  unsigned long long red[kBlock / 32];
+  int last;
+};
+
+// ------------------------------------------------------------------ per-tile machine state
+template <typename T, int V, bool kCompact, bool kReduce>
+struct Tile {
+  static constexpr int U = kRows;
+  static constexpr int E = U * V;
+  static constexpr int NW = kBlock / 32;
+  static constexpr int64_t TILE = (int64_t)kBlock * E;
+  static constexpr uint32_t ROWMASK = (1u << V) - 1u;
+  static constexpr uint32_t FULLMASK = (E == 32) ? 0xffffffffu : ((1u << E) - 1u);
+  static_assert(E <= 32, "one predicate bit per element");
+  static_assert(U * NW == 32, "the tile scan assumes one warp covers all (row, warp) totals");
+  static_assert(U <= 4 && V * 32 < 256, "packed 8-bit row counters");
+  using Tr = TT<T>;
+  using Acc = typename Tr::Acc;
+
+  T acc[E], t0[E], t1[E];
+  uint32_t pacc, p0, p1, p2;
+  uint32_t keep, valid;
+  int64_t cidx[U];
+  int64_t thr_base, tile;
+  bool full;
+  // running reduction state (lives across tiles)
+  Acc rsum;
+  T rext;
+
+  __device__ __forceinline__ void begin_tile(const KParams &p, int64_t tile_id, int tid) {
+    tile = tile_id;
+    const int64_t tile_base = p.start + tile_id * TILE;
+    // block-uniform: every row of every thread is in range -> straight-line vector accesses,
+    // all kRows loads of an operand are issued back to back before anything consumes them
+    full = (tile_base + TILE <= p.end);
+    thr_base = tile_base + (int64_t)tid * V;     // row u lives at thr_base + u*kBlock*V
+    keep = FULLMASK;
+    if (!full) {
+      keep = 0;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int64_t rem = p.end - (thr_base + (int64_t)u * kBlock * V);
+        const int nv = rem >= V ? V : (rem > 0 ? (int)rem : 0);
+        keep |= ((1u << nv) - 1u) << (u * V);
+      }
+    }
+    valid = keep;
+    pacc = p0 = p1 = p2 = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) { acc[e] = T(0); t0[e] = T(0); t1[e] = T(0); }
+#pragma unroll
+    for (int u = 0; u < U; u++) cidx[u] = 0;
+  }
+
+  // x <- temporary | column rows | broadcast scalar
+  __device__ __forceinline__ void fetch(const KParams &p, uint32_t src, T (&x)[E]) const {
+    if (src & SRC_TEMP) {
+      if ((src & 0x7f) == 0) {
+#pragma unroll
+        for (int e = 0; e < E; e++) x[e] = t0[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) x[e] = t1[e];
+      }
+    } else {
+      const int kind = p.in_kind[src];
+      if (kind == NL_IN_ARRAY) {
+        const T *base = reinterpret_cast<const T *>(p.in[src]) + thr_base;
+        if (full) {
+#pragma unroll
+          for (int u = 0; u < U; u++) load_vec<T, V>(base + u * kBlock * V, &x[u * V]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < E; e++) x[e] = ((valid >> e) & 1u) ? base[(e / V) * kBlock * V + (e % V)] : T(0);
+        }
+      } else {
+        const T sc = (kind == NL_IN_SCALAR_IMM) ? from_bits<T>(p.imm[src]) : *reinterpret_cast<const T *>(p.in[src]);
+#pragma unroll
+        for (int e = 0; e < E; e++) x[e] = sc;
+      }
+    }
+  }
+
+  // `if (!mask) goto for.inc` (thunk_as_mapping.cpp:11) + the order-preserving compaction index
+  __device__ __forceinline__ void filter_step(const KParams &p, TileShared &sh, int lane, int warp) {
+    keep &= pacc;
+    if constexpr (kCompact) {
+      // rank of every kept element in (row, thread, v) order == its input order
+      uint32_t packed = 0;
+#pragma unroll
+      for (int u = 0; u < U; u++) packed |= (uint32_t)__popc((keep >> (u * V)) & ROWMASK) << (8 * u);
+      uint32_t incl = packed;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += nb;
+      }
+      const uint32_t lane_excl = incl - packed;
+      if (lane == 31) sh.wtot[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        // lane l <-> (row u = l / NW, warp w = l % NW): row-major == input order
+        const int u = lane / NW, w = lane % NW;
+        const uint32_t val = (sh.wtot[w] >> (8 * u)) & 0xffu;
+        uint32_t sc = val;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t nb = __shfl_up_sync(0xffffffffu, sc, d);
+          if (lane >= d) sc += nb;
+        }
+        sh.off[lane] = sc - val;
+        const unsigned long long agg = __shfl_sync(0xffffffffu, sc, 31);
+        // decoupled look-back over the predecessors' descriptors
+        unsigned long long excl = 0;
+        if (tile == 0) {
+          if (lane == 0) st_relaxed_u64(&p.tile_desc[0], kDescPrefix | agg);
+        } else {
+          if (lane == 0) st_relaxed_u64(&p.tile_desc[tile], kDescAggregate | agg);
+          int64_t j = tile - 1;
+          while (true) {
+            const int64_t q = j - lane;
+            unsigned long long d = kDescPrefix;          // before tile 0: an empty prefix
+            if (q >= 0) {
+              d = ld_relaxed_u64(&p.tile_desc[q]);
+              while ((d >> 62) == 0) d = ld_relaxed_u64(&p.tile_desc[q]);
+            }
+            const uint32_t has_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+            const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+            unsigned long long v = (lane <= first) ? (d & kDescValueMask) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            excl += v;
+            if (has_prefix) break;
+            j -= 32;
+          }
+          if (lane == 0) st_relaxed_u64(&p.tile_desc[tile], kDescPrefix | ((excl + agg) & kDescValueMask));
+        }
+        if (lane == 0) {
+          sh.prefix = (long long)excl;
+          if (tile == p.n_tiles - 1) {
+            for (int o = 0; o < p.n_outputs; o++)
+              if (p.out_space[o] == NL_IDX_COMPACT) p.out_sizes[o] = p.start + (long long)(excl + agg);
+          }
+        }
+      }
+      __syncthreads();
+      const int64_t tile_excl = sh.prefix;
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        cidx[u] = p.start + tile_excl + (int64_t)sh.off[u * NW + warp] + (int64_t)((lane_excl >> (8 * u)) & 0xffu);
+    }
+  }
+
+  // One step of the accumulator machine.  With compile-time constant (op, a, b) — the
+  // StaticProg driver — everything but the selected case folds away.
+  __device__ __forceinline__ void exec(const KParams &p, TileShared &sh, uint32_t op, uint32_t a, uint32_t b,
+                                       int lane, int warp) {
+    switch (op) {
+      case S_LOAD:
+        fetch(p, a, acc);
+        break;
+      case S_LOADT:
+        fetch(p, SRC_TEMP | a, acc);
+        break;
+      case S_SAVE:
+        if (a == 0) {
+#pragma unroll
+          for (int e = 0; e < E; e++) t0[e] = acc[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < E; e++) t1[e] = acc[e];
+        }
+        break;
+      case S_BIN: {
+        T x[E];
+        fetch(p, b, x);
+        switch (a) {
+          case V_MUL:
+#pragma unroll
+            for (int e = 0; e < E; e++) acc[e] = op_mul<T>(acc[e], x[e]);
+            break;
+          case V_ADD:
+#pragma unroll
+            for (int e = 0; e < E; e++) acc[e] = op_add<T>(acc[e], x[e]);
+            break;
+          case V_SUB:
+#pragma unroll
+            for (int e = 0; e < E; e++) acc[e] = op_sub<T>(acc[e], x[e]);
+            break;
+          default:
+#pragma unroll
+            for (int e = 0; e < E; e++) acc[e] = op_sub<T>(x[e], acc[e]);
+            break;
+        }
+        break;
+      }
+      case S_CMP: {
+        T x[E];
+        fetch(p, b, x);
+        uint32_t m = 0;
+        switch (a) {
+          case C_GE:
+#pragma unroll
+            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] >= x[e]) << e;
+            break;
+          case C_GT:
+#pragma unroll
+            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] > x[e]) << e;
+            break;
+          case C_LE:
+#pragma unroll
+            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] <= x[e]) << e;
+            break;
+          case C_LT:
+#pragma unroll
+            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] < x[e]) << e;
+            break;
+          case C_EQ:
+#pragma unroll
+            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] == x[e]) << e;
+            break;
+          default:
+#pragma unroll
+            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] != x[e]) << e;
+            break;
+        }
+        pacc = m;
+        break;
+      }
+      case S_PLOAD: {
+        const int kind = p.in_kind[a];
+        uint32_t m = 0;
+        if (kind == NL_IN_ARRAY) {
+          const unsigned char *base = reinterpret_cast<const unsigned char *>(p.in[a]) + thr_base;
+          if (full) {
+            unsigned char bytes[E];
+#pragma unroll
+            for (int u = 0; u < U; u++) load_vec<unsigned char, V>(base + u * kBlock * V, &bytes[u * V]);
+#pragma unroll
+            for (int e = 0; e < E; e++) m |= (uint32_t)(bytes[e] != 0) << e;
+          } else {
+#pragma unroll
+            for (int e = 0; e < E; e++)
+              if ((valid >> e) & 1u) m |= (uint32_t)(base[(e / V) * kBlock * V + (e % V)] != 0) << e;
+          }
+        } else {
+          const bool on = (kind == NL_IN_SCALAR_IMM) ? ((p.imm[a] & 0xff) != 0)
+                                                     : (*reinterpret_cast<const unsigned char *>(p.in[a]) != 0);
+          m = on ? 0xffffffffu : 0u;
+        }
+        pacc = m;
+        break;
+      }
+      case S_PLOADT:
+        pacc = (a == 0) ? p0 : (a == 1) ? p1 : p2;
+        break;
+      case S_PSAVE:
+        if (a == 0) p0 = pacc; else if (a == 1) p1 = pacc; else p2 = pacc;
+        break;
+      case S_PBIN: {
+        const uint32_t q = (b == 0) ? p0 : (b == 1) ? p1 : p2;
+        pacc = (a == P_AND) ? (pacc & q) : (a == P_OR) ? (pacc | q) : (pacc ^ q);
+        break;
+      }
+      case S_PNOT:
+        pacc = ~pacc;
+        break;
+      case S_FILTER:
+        filter_step(p, sh, lane, warp);
+        break;
+      case S_STORE: {
+        if (b == NL_IDX_LOOP) {
+          T *base = reinterpret_cast<T *>(p.out[a]) + thr_base;
+          if (full) {
+#pragma unroll
+            for (int u = 0; u < U; u++) store_vec<T, V>(base + u * kBlock * V, &acc[u * V]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < E; e++)
+              if ((valid >> e) & 1u) base[(e / V) * kBlock * V + (e % V)] = acc[e];
+          }
+        } else {
+          T *base = reinterpret_cast<T *>(p.out[a]);
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            int64_t ci = cidx[u];
+#pragma unroll
+            for (int v = 0; v < V; v++)
+              if ((keep >> (u * V + v)) & 1u) base[ci++] = acc[u * V + v];
+          }
+        }
+        break;
+      }
+      case S_PSTORE: {
+        if (b == NL_IDX_LOOP) {
+          unsigned char *base = reinterpret_cast<unsigned char *>(p.out[a]) + thr_base;
+          if (full) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              unsigned char bytes[V];
+#pragma unroll
+              for (int v = 0; v < V; v++) bytes[v] = (unsigned char)((pacc >> (u * V + v)) & 1u);   // canonical 0x01 (Q4)
+              store_vec<unsigned char, V>(base + u * kBlock * V, bytes);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < E; e++)
+              if ((valid >> e) & 1u) base[(e / V) * kBlock * V + (e % V)] = (unsigned char)((pacc >> e) & 1u);
+          }
+        } else {
+          unsigned char *base = reinterpret_cast<unsigned char *>(p.out[a]);
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            int64_t ci = cidx[u];
+#pragma unroll
+            for (int v = 0; v < V; v++)
+              if ((keep >> (u * V + v)) & 1u) base[ci++] = (unsigned char)((pacc >> (u * V + v)) & 1u);
+          }
+        }
+        break;
+      }
+      case S_WHERE: {
+        T *base = reinterpret_cast<T *>(p.out[a]) + thr_base;
+        const uint32_t m = pacc & keep;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t rowbits = (m >> (u * V)) & ROWMASK;
+          if (rowbits == ROWMASK) {
+            store_vec<T, V>(base + u * kBlock * V, &acc[u * V]);
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; v++)
+              if ((rowbits >> v) & 1u) base[u * kBlock * V + v] = acc[u * V + v];
+          }
+        }
+        break;
+      }
+      case S_REDUCE:
+        if constexpr (kReduce) {
+          // fold this thread's E elements in a fixed tree first (short dependency chain),
+          // then one update of the running accumulator
+          const bool all = (keep == FULLMASK);
+          if (a == R_SUM) {
+            Acc w[E];
+            if (all) {
+#pragma unroll
+              for (int e = 0; e < E; e++) w[e] = (Acc)acc[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < E; e++) w[e] = ((keep >> e) & 1u) ? (Acc)acc[e] : Acc(0);
+            }
+#pragma unroll
+            for (int st = E / 2; st > 0; st >>= 1)
+#pragma unroll
+              for (int i = 0; i < st; i++) w[i] = acc_add(w[i], w[i + st]);
+            rsum = acc_add(rsum, w[0]);
+          } else if (a == R_MAX) {
+            T w[E];
+            if (all) {
+#pragma unroll
+              for (int e = 0; e < E; e++) w[e] = acc[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < E; e++) w[e] = ((keep >> e) & 1u) ? acc[e] : Tr::lowest();
+            }
+#pragma unroll
+            for (int st = E / 2; st > 0; st >>= 1)
+#pragma unroll
+              for (int i = 0; i < st; i++) w[i] = op_max<T>(w[i], w[i + st]);
+            rext = op_max<T>(rext, w[0]);
+          } else {
+            T w[E];
+            if (all) {
+#pragma unroll
+              for (int e = 0; e < E; e++) w[e] = acc[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < E; e++) w[e] = ((keep >> e) & 1u) ? acc[e] : Tr::highest();
+            }
+#pragma unroll
+            for (int st = E / 2; st > 0; st >>= 1)
+#pragma unroll
+              for (int i = 0; i < st; i++) w[i] = op_min<T>(w[i], w[i + st]);
+            rext = op_min<T>(rext, w[0]);
+          }
+        }
+        break;
+      default:
+        break;
+    }
+  }
+};
+
+// ------------------------------------------------------------------ program drivers
+struct DynProg {
+  static constexpr bool is_static = false;
+  template <class TileT>
+  static __device__ __forceinline__ void run(TileT &t, const KParams &p, TileShared &sh, int lane, int warp) {
+#pragma unroll 1
+    for (int pc = 0; pc < p.n_steps; pc++) {
+      const uint32_t s = p.step[pc];
+      t.exec(p, sh, step_op(s), step_a(s), step_b(s), lane, warp);
+    }
+  }
+};
+
+template <uint32_t... S>
+struct StaticProg {
+  static constexpr bool is_static = true;
+  static constexpr int n_steps = sizeof...(S);
+  template <class TileT>
+  static __device__ __forceinline__ void run(TileT &t, const KParams &p, TileShared &sh, int lane, int warp) {
+    (t.exec(p, sh, step_op(S), step_a(S), step_b(S), lane, warp), ...);
+  }
+  static bool matches(const uint32_t *steps, int n) {
+    constexpr uint32_t mine[] = {S...};
+    if (n != n_steps) return false;
+    for (int i = 0; i < n; i++)
+      if (steps[i] != mine[i]) return false;
+    return true;
+  }
+};
+
+// ------------------------------------------------------------------ the kernel
+template <typename T, int V, bool kCompact, bool kReduce, class Prog>
+__global__ void __launch_bounds__(kBlock, Prog::is_static ? 1 : kMinBlocks)
+pipeline_kernel(const __grid_constant__ KParams p) {
+  using TileT = Tile<T, V, kCompact, kReduce>;
+  using Tr = TT<T>;
+  using Acc = typename Tr::Acc;
+  constexpr int NW = kBlock / 32;
+  __shared__ TileShared sh;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // output cardinalities that do not depend on the data (compiler.cpp:491-508)
+  if (blockIdx.x == 0 && tid == 0) {
+    for (int o = 0; o < p.n_outputs; o++) {
+      if (p.out_space[o] == NL_IDX_LOOP || p.out_space[o] == NL_IDX_WHERE) p.out_sizes[o] = p.end;
+      else if (p.out_space[o] == NL_IDX_SHARD) p.out_sizes[o] = 1;
+    }
+  }
+
+  TileT t;
+  t.rsum = 0;
+  t.rext = (p.reduce_rop == R_MIN) ? Tr::highest() : Tr::lowest();
+
+  int64_t tile = blockIdx.x;
+  while (true) {
+    if constexpr (kCompact) {
+      // tiles are handed out in order so every predecessor of a tile is already owned by a
+      // running CTA: the look-back can never wait on work that has not started
+      if (tid == 0) sh.tile = (long long)atomicAdd(p.tile_ticket, 1u);
+      __syncthreads();
+      tile = sh.tile;
+    }
+    if (tile >= p.n_tiles) break;
+    t.begin_tile(p, tile, tid);
+    Prog::run(t, p, sh, lane, warp);
+    if constexpr (!kCompact) tile += gridDim.x;
+  }
+
+  if constexpr (kReduce) {
+    // block tree in a fixed order, then the last CTA to finish folds every CTA's partial
+    const int rop = p.reduce_rop;
+    auto block_reduce = [&](Acc sv, T ev) -> unsigned long long {
+      if (rop == R_SUM) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sv = acc_add(sv, __shfl_xor_sync(0xffffffffu, sv, o));
+      } else if (rop == R_MAX) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ev = op_max<T>(ev, __shfl_xor_sync(0xffffffffu, ev, o));
+      } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ev = op_min<T>(ev, __shfl_xor_sync(0xffffffffu, ev, o));
+      }
+      __syncthreads();
+      if (lane == 0) sh.red[warp] = (rop == R_SUM) ? to_bits<Acc>(sv) : to_bits<T>(ev);
+      __syncthreads();
+      unsigned long long out = 0;
+      if (warp == 0) {
+        if (rop == R_SUM) {
+          Acc v = (lane < NW) ? from_bits<Acc>(sh.red[lane]) : Acc(0);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v = acc_add(v, __shfl_xor_sync(0xffffffffu, v, o));
+          out = to_bits<Acc>(v);
+        } else {
+          T v = (lane < NW) ? from_bits<T>(sh.red[lane]) : (rop == R_MAX ? Tr::lowest() : Tr::highest());
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            v = (rop == R_MAX) ? op_max<T>(v, __shfl_xor_sync(0xffffffffu, v, o)) : op_min<T>(v, __shfl_xor_sync(0xffffffffu, v, o));
+          out = to_bits<T>(v);
+        }
+      }
+      return out;   // valid in warp 0
+    };
+
+    const unsigned long long mine = block_reduce(t.rsum, t.rext);
+    if (tid == 0) {
+      p.red_partials[blockIdx.x] = mine;
+      __threadfence();
+      const unsigned int tk = atomicAdd(p.red_ticket, 1u);
+      sh.last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (sh.last) {
+      __threadfence();
+      Acc sv = 0;
+      T ev = (rop == R_MIN) ? Tr::highest() : Tr::lowest();
+      for (unsigned int i = tid; i < gridDim.x; i += kBlock) {
+        const unsigned long long bits = ld_relaxed_u64(&p.red_partials[i]);
+        if (rop == R_SUM) sv = acc_add(sv, from_bits<Acc>(bits));
+        else if (rop == R_MAX) ev = op_max<T>(ev, from_bits<T>(bits));
+        else ev = op_min<T>(ev, from_bits<T>(bits));
+      }
+      const unsigned long long total = block_reduce(sv, ev);
+      if (tid == 0) {
+        T *out = reinterpret_cast<T *>(p.out[p.reduce_out]);
+        // the store casts the accumulator to the column type (compiler.cpp:256-260)
+        out[p.thread_nr] = (rop == R_SUM) ? (T)from_bits<Acc>(total) : from_bits<T>(total);
+        *p.red_ticket = 0u;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ static program registry
+typedef void (*pipeline_fn)(const KParams);
+
+struct StaticEntry {
+  const char *name;
+  bool (*matches)(const uint32_t *steps, int n);
+  int dtype;
+  bool vec16;
+  pipeline_fn fn;
+};
+
+// per-dtype tables, defined in nl_static_<dtype>.cu
+const StaticEntry *static_table_i32(int *n);
+const StaticEntry *static_table_i64(int *n);
+const StaticEntry *static_table_f32(int *n);
+const StaticEntry *static_table_f64(int *n);
+
+}  // namespace nl

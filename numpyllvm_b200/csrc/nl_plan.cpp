@@ -34,7 +34,8 @@ struct Lower {
   nl_plan *plan;
   int rc = NL_OK;
 
-  bool temp_used[NL_MAX_TEMPS] = {false, false, false};
+  bool temp_used[NL_MAX_TEMPS] = {false, false};
+  int cache_budget = 0;                 // temporaries that may hold re-read columns
   bool ptemp_used[NL_MAX_PTEMPS] = {false, false, false};
   int max_temps = 0;
   int input_uses[NL_MAX_INPUTS] = {0};
@@ -119,6 +120,22 @@ struct Lower {
     }
   }
 
+  // value temporaries the expression itself needs under the L-first evaluation order below
+  // (a Sethi-Ullman style count); what is left over may cache columns that are read twice
+  int temps_needed(int n) const {
+    const nl_expr_node &nd = nodes[n];
+    if (nd.op == NL_OP_INPUT) return 0;
+    if (nd.rhs < 0) return temps_needed(nd.lhs);
+    if (is_vop(nd.op) || is_cmp(nd.op)) {
+      if (simple_leaf(nd.rhs)) return temps_needed(nd.lhs);
+      if (simple_leaf(nd.lhs)) return temps_needed(nd.rhs);
+      const int l = temps_needed(nd.lhs), r = 1 + temps_needed(nd.rhs);
+      return l > r ? l : r;
+    }
+    const int l = temps_needed(nd.lhs), r = temps_needed(nd.rhs);   // filter / bool ops / where: no value held across
+    return l > r ? l : r;
+  }
+
   // ---- pass 2: code generation ----------------------------------------------------
   uint32_t src_of_leaf(int n) {
     int k = nodes[n].input;
@@ -135,10 +152,11 @@ struct Lower {
     } else {
       emit(make_step(S_LOAD, (uint32_t)k));
       // a column read more than once (a[a > t]) is kept in a temporary instead of re-read
-      if (input_uses[k] > 1 && in[k].kind == NL_IN_ARRAY) {
+      if (input_uses[k] > 1 && in[k].kind == NL_IN_ARRAY && cache_budget > 0) {
         for (int j = NL_MAX_TEMPS - 1; j >= 0; j--)
           if (!temp_used[j]) {
             temp_used[j] = true;
+            cache_budget--;
             if (j + 1 > max_temps) max_temps = j + 1;
             input_temp[k] = j;
             emit(make_step(S_SAVE, (uint32_t)j));
@@ -319,6 +337,7 @@ int nl_plan_compile(const nl_expr_node *nodes, int n_nodes, const nl_input_desc 
   lw.walk(root);
   if (lw.rc != NL_OK) return lw.rc;
   if (nodes[root].output < 0) { set_error("pipeline root is not materialised"); return NL_ERR_INVALID; }
+  lw.cache_budget = NL_MAX_TEMPS - lw.temps_needed(root);
   if (lw.is_pred(root)) lw.gen_pred(root); else lw.gen_value(root);
   if (lw.rc != NL_OK) return lw.rc;
 

@@ -549,6 +549,16 @@ int nl_finish_filter(const int64_t *const *count, int64_t *const *offsets, int s
 }
 
 // ======================================================================= introspection
+int nl_plan_kernel(const nl_plan *plan, int vec16, char *name, size_t name_len, int *is_static) {
+  if (!plan || plan->abi_version != NL_ABI_VERSION) { set_error("nl_plan_kernel: bad plan"); return NL_ERR_INVALID; }
+  return describe_pipeline_kernel(plan, vec16 != 0, name, name_len, is_static);
+}
+
+int nl_set_static_kernels(int enabled) {
+  set_static_kernels_enabled(enabled);
+  return NL_OK;
+}
+
 uint64_t nl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int nl_last_launch_info(char *kernel_name, size_t name_len, int *grid, int *block, int *vec_elems) {

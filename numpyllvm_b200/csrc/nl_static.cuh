@@ -1,0 +1,86 @@
+// nl_static.cuh — the pipeline shapes that are instantiated at build time.
+//
+// Each entry is the exact step sequence nl_plan_compile() emits for a thunk
+// expression shape (input kinds — column, immediate, device scalar — stay run-time
+// parameters, so `a * b`, `a * 2` and `res * a` with res on the device are all
+// "mul2").  A plan whose steps match an entry runs the StaticProg instantiation;
+// every other plan runs the dynamic interpreter with identical semantics
+// (tests/test_gpu_parity.py runs both drivers on the same programs).
+//
+// To add a shape: append one X(...) line; tests/test_abi_host.py checks that the
+// benchmark expressions resolve to a static kernel.
+#pragma once
+#include "nl_pipeline.cuh"
+
+namespace nl {
+namespace sp {
+constexpr uint32_t L(uint32_t k) { return make_step(S_LOAD, k); }
+constexpr uint32_t LT(uint32_t j) { return make_step(S_LOADT, j); }
+constexpr uint32_t SV(uint32_t j) { return make_step(S_SAVE, j); }
+constexpr uint32_t B(uint32_t vop, uint32_t src) { return make_step(S_BIN, vop, src); }
+constexpr uint32_t C(uint32_t cop, uint32_t src) { return make_step(S_CMP, cop, src); }
+constexpr uint32_t F() { return make_step(S_FILTER); }
+constexpr uint32_t ST(uint32_t o, uint32_t space) { return make_step(S_STORE, o, space); }
+constexpr uint32_t PST(uint32_t o, uint32_t space) { return make_step(S_PSTORE, o, space); }
+constexpr uint32_t R(uint32_t rop, uint32_t o) { return make_step(S_REDUCE, rop, o); }
+constexpr uint32_t W(uint32_t o) { return make_step(S_WHERE, o); }
+constexpr uint32_t T0 = SRC_TEMP | 0, T1 = SRC_TEMP | 1;
+constexpr uint32_t LOOP = NL_IDX_LOOP, COMPACT = NL_IDX_COMPACT;
+
+template <uint32_t... S> constexpr bool has_compact() {
+  return (((step_op(S) == S_STORE || step_op(S) == S_PSTORE) && step_b(S) == NL_IDX_COMPACT) || ...);
+}
+template <uint32_t... S> constexpr bool has_reduce() { return ((step_op(S) == S_REDUCE) || ...); }
+}  // namespace sp
+
+// X(name, steps...)
+#define NL_CMP_SHAPES(X, tag, cop)                                                                          \
+  /* a[a cmp s]            (Tests/filter.py family, C4) */                                                  \
+  X(filter_##tag, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::ST(0, sp::COMPACT))                       \
+  /* a[a cmp s].sum()/max()/min()   (Tests/max.py family) */                                                \
+  X(filter_##tag##_sum, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::R(R_SUM, 0))                        \
+  X(filter_##tag##_max, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::R(R_MAX, 0))                        \
+  X(filter_##tag##_min, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::R(R_MIN, 0))                        \
+  /* (a[a cmp s] * k).max()   (C5) */                                                                       \
+  X(filter_##tag##_mul_max, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::B(V_MUL, 2), sp::R(R_MAX, 0))   \
+  X(filter_##tag##_mul_sum, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::B(V_MUL, 2), sp::R(R_SUM, 0))   \
+  /* a cmp s  -> materialised mask */                                                                       \
+  X(mask_##tag, sp::L(0), sp::C(cop, 1), sp::PST(0, sp::LOOP))
+
+#define NL_STATIC_SHAPES(X)                                                                                 \
+  /* a * b, a * 2, res * a   (Tests/assignment.py, Tests/max.py:14, C2) */                                  \
+  X(mul2, sp::L(0), sp::B(V_MUL, 1), sp::ST(0, sp::LOOP))                                                    \
+  X(add2, sp::L(0), sp::B(V_ADD, 1), sp::ST(0, sp::LOOP))                                                    \
+  X(sub2, sp::L(0), sp::B(V_SUB, 1), sp::ST(0, sp::LOOP))                                                    \
+  /* d * e * f   (Tests/multiplication.py:26) */                                                            \
+  X(mul3, sp::L(0), sp::B(V_MUL, 1), sp::B(V_MUL, 2), sp::ST(0, sp::LOOP))                                   \
+  /* (d*e*f) * (a*b*c)   (C1) */                                                                            \
+  X(mul6, sp::L(0), sp::B(V_MUL, 1), sp::B(V_MUL, 2), sp::SV(0), sp::L(3), sp::B(V_MUL, 4), sp::B(V_MUL, 5), \
+    sp::B(V_MUL, sp::T0), sp::ST(0, sp::LOOP))                                                               \
+  /* a.max() / a.min() / a.sum()   (C3) */                                                                  \
+  X(reduce_max, sp::L(0), sp::R(R_MAX, 0))                                                                   \
+  X(reduce_min, sp::L(0), sp::R(R_MIN, 0))                                                                   \
+  X(reduce_sum, sp::L(0), sp::R(R_SUM, 0))                                                                   \
+  /* a[a * k >= s]   (Tests/filter.py:13 exactly) */                                                        \
+  X(filter_mul_ge, sp::L(0), sp::SV(1), sp::B(V_MUL, 1), sp::C(C_GE, 2), sp::F(), sp::LT(1), sp::ST(0, sp::COMPACT)) \
+  NL_CMP_SHAPES(X, ge, C_GE)                                                                                \
+  NL_CMP_SHAPES(X, gt, C_GT)                                                                                \
+  NL_CMP_SHAPES(X, le, C_LE)                                                                                \
+  NL_CMP_SHAPES(X, lt, C_LT)                                                                                \
+  NL_CMP_SHAPES(X, eq, C_EQ)                                                                                \
+  NL_CMP_SHAPES(X, ne, C_NE)
+
+// one table row per shape (128-bit rows; misaligned launches use the dynamic V = 1 kernel)
+#define NL_STATIC_ROW(name, ...)                                                                            \
+  {#name, &StaticProg<__VA_ARGS__>::matches, NL_STATIC_DTYPE, true,                                          \
+   &pipeline_kernel<NL_STATIC_T, 16 / sizeof(NL_STATIC_T), sp::has_compact<__VA_ARGS__>(),                   \
+                    sp::has_reduce<__VA_ARGS__>(), StaticProg<__VA_ARGS__>>},
+
+#define NL_DEFINE_STATIC_TABLE(fn_name)                                                                     \
+  const StaticEntry *fn_name(int *n) {                                                                      \
+    static const StaticEntry table[] = {NL_STATIC_SHAPES(NL_STATIC_ROW)};                                   \
+    *n = (int)(sizeof(table) / sizeof(table[0]));                                                           \
+    return table;                                                                                           \
+  }
+
+}  // namespace nl

@@ -7,7 +7,7 @@
 //
 // Machine state per thread, for the E = U*V elements it owns in a tile:
 //   acc[E]        value accumulator (type T)
-//   t0..t2[E]     value temporaries
+//   t0..t1[E]     value temporaries (NL_MAX_TEMPS)
 //   pacc, p0..p2  predicate accumulator / temporaries, one bit per element
 //   keep          elements still alive (in range and not filtered out)
 // All control flow is warp-uniform: the program is the same for every thread.

@@ -178,3 +178,35 @@ def test_reversed_operands_keep_non_commutative_order():
     e.materialize(e.lt(e.scalar(1.0), e.mul(x, e.scalar(2.0))))      # 1 < x*2  ==  x*2 > 1
     text = abi.dump_plan(abi.compile_plan(e))
     assert "pacc = gt(acc" in text
+
+
+def test_benchmark_shapes_resolve_to_build_time_kernels():
+    # kernel-template selection: the pipelines of BASELINE.json's configs and of the reference's
+    # tests match a shape instantiated at build time; anything else runs the interpreter
+    def kernel(e):
+        return abi.plan_kernel(abi.compile_plan(e))
+    e = Expr(np.float32); e.materialize(e.mul(e.array(), e.array()))
+    assert kernel(e) == ("pipeline_kernel<f32,V=4,static:mul2>", True)                  # C2 / Tests/assignment.py
+    e = Expr(np.float64); d, ee, f, a, b, c = (e.array() for _ in range(6))
+    e.materialize(e.mul(e.mul(e.mul(d, ee), f), e.mul(e.mul(a, b), c)))
+    assert kernel(e)[0].endswith("static:mul6>")                                        # C1
+    for dt in (np.float64, np.int64):
+        for op in ("max", "min", "sum"):
+            e = Expr(dt); e.materialize(getattr(e, op)(e.array()))
+            assert kernel(e)[0].endswith(f"static:reduce_{op}>")                        # C3
+    e = Expr(np.float64); xa = e.array(); e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(0.5))))
+    assert kernel(e)[0].endswith("static:filter_gt>")                                   # C4
+    e = Expr(np.float32); xa = e.array()
+    e.materialize(e.max(e.mul(e.filter(xa, e.ge(e.ref(xa), e.scalar(0.5))), e.scalar(3.0))))
+    assert kernel(e)[0].endswith("static:filter_ge_mul_max>")                           # C5
+    e = Expr(np.int64); xa = e.array()
+    e.materialize(e.filter(xa, e.ge(e.mul(e.ref(xa), e.scalar(2)), e.scalar(50))))
+    assert kernel(e)[0].endswith("static:filter_mul_ge>")                               # Tests/filter.py
+    e = Expr(np.int64); xa = e.array(); e.materialize(e.sum(e.filter(xa, e.ge(e.ref(xa), e.scalar(50)))))
+    assert kernel(e)[0].endswith("static:filter_ge_sum>")                               # Tests/max.py
+    e = Expr(np.int64); xa = e.array(); e.materialize(e.add(e.mul(xa, e.scalar(3)), e.scalar(1)))
+    name, is_static = kernel(e)
+    assert not is_static and "dynamic" in name
+    # scalar rows (misaligned operands) always use the interpreter
+    e = Expr(np.float32); e.materialize(e.mul(e.array(), e.array()))
+    assert abi.plan_kernel(abi.compile_plan(e), vec16=False) == ("pipeline_kernel<f32,V=1,compact=0,reduce=0,dynamic>", False)

@@ -25,6 +25,15 @@ def rt(nl):
     return Runtime.get()
 
 
+@pytest.fixture(autouse=True, params=["static", "dynamic"])
+def driver(request, nl):
+    """Every case runs twice: with the build-time instantiated shapes (nl_static.cuh) where the
+    plan matches one, and with everything forced through the dynamic interpreter."""
+    nl.nl_set_static_kernels(1 if request.param == "static" else 0)
+    yield request.param
+    nl.nl_set_static_kernels(1)
+
+
 def column(dtype, n, seed, kind=None):
     if kind is None:
         kind = 2 if np.issubdtype(dtype, np.floating) else 0
@@ -76,6 +85,15 @@ def test_ref_assignment(rt, golden):
     abi.check(rt.lib.nl_assign_fill(0, 0, C.c_void_p(da.ptr), abi.NL_I64, 0, 1, 1, abi.scalar_bits(1000, I64)))
     assert rt.download(dc).tolist() == g["c"]
     assert rt.download(da)[0] == 1000 and rt.download(da)[1:].tolist() == a[1:].tolist()
+
+
+def test_driver_selection(rt, driver):
+    e = Expr(np.float32)
+    e.materialize(e.mul(e.array(), e.array()))
+    x = column(np.float32, 5000, 1)
+    run_pipeline(rt, e, [x, x], 5000)
+    name = rt.last_launch()[0]
+    assert ("static:mul2" in name) == (driver == "static"), name
 
 
 def test_ref_filter(rt, golden):
@@ -143,7 +161,7 @@ def test_misaligned_falls_back_to_scalar_rows(rt, dtype, mis):
     assert_same(ref, got)
     name, grid, block, vec = rt.last_launch()
     if (mis * np.dtype(dtype).itemsize) % 16:
-        assert vec == 1, name
+        assert vec == 1 and "dynamic" in name, name
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
