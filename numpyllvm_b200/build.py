@@ -33,7 +33,7 @@ KERNEL_SOURCES = ["nl_plan.cpp", "nl_kernels.cu", "nl_runtime.cu",
                   "nl_static_i32.cu", "nl_static_i64.cu", "nl_static_f32.cu", "nl_static_f64.cu"]
 JIT_SOURCES = ["jitpackage.cpp", "thunk.cpp", "operation.cpp", "thunk_as_number.cpp", "thunk_as_mapping.cpp",
                "thunk_as_sequence.cpp", "thunk_methods.cpp", "parser.cpp", "optimizer.cpp", "scheduler.cpp",
-               "debug_printer.cpp"]
+               "debug_printer.cpp", "storage.cpp"]
 
 
 def _stale(target: str, deps) -> bool:

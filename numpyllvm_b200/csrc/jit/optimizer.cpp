@@ -1,0 +1,191 @@
+// optimizer.cpp — see optimizer.hpp.
+#include "optimizer.hpp"
+
+#include <cstring>
+
+static double bits_to_double(uint64_t bits, int dtype) {
+  switch (dtype) {
+    case NL_BOOL: return (double)(bits & 0xff ? 1 : 0);
+    case NL_I32: { int32_t v; memcpy(&v, &bits, 4); return (double)v; }
+    case NL_I64: { int64_t v; memcpy(&v, &bits, 8); return (double)v; }
+    case NL_F32: { float v; memcpy(&v, &bits, 4); return (double)v; }
+    default: { double v; memcpy(&v, &bits, 8); return v; }
+  }
+}
+
+static int64_t bits_to_int(uint64_t bits, int dtype) {
+  switch (dtype) {
+    case NL_BOOL: return (bits & 0xff) ? 1 : 0;
+    case NL_I32: { int32_t v; memcpy(&v, &bits, 4); return v; }
+    case NL_I64: { int64_t v; memcpy(&v, &bits, 8); return v; }
+    case NL_F32: { float v; memcpy(&v, &bits, 4); return (int64_t)v; }
+    default: { double v; memcpy(&v, &bits, 8); return (int64_t)v; }
+  }
+}
+
+// getLLVMConstant (compiler.cpp:125-154) baked a size-1 input as an immediate of the column
+// type; the conversion to the pipeline's value type happens here, on the host
+static uint64_t convert_scalar(uint64_t bits, int from, int to) {
+  if (from == to) return bits;
+  uint64_t out = 0;
+  switch (to) {
+    case NL_I32: { int32_t v = (int32_t)bits_to_int(bits, from); memcpy(&out, &v, 4); break; }
+    case NL_I64: { int64_t v = bits_to_int(bits, from); memcpy(&out, &v, 8); break; }
+    case NL_F32: { float v = (from == NL_F64 || from == NL_F32) ? (float)bits_to_double(bits, from) : (float)bits_to_int(bits, from); memcpy(&out, &v, 4); break; }
+    case NL_F64: { double v = (from == NL_F64 || from == NL_F32) ? bits_to_double(bits, from) : (double)bits_to_int(bits, from); memcpy(&out, &v, 8); break; }
+    default: out = (bits & 0xff) ? 1 : 0; break;
+  }
+  return out;
+}
+
+struct Lowering {
+  Pipeline *pipeline;
+  LoweredPipeline *out;
+  bool failed;
+  bool too_big;
+};
+
+static DataSource *find_input(Pipeline *p, Operation *op) {
+  for (DataElement &e : p->inputData->objects)
+    if (e.operation == op) return e.source;
+  return NULL;
+}
+
+static int find_output(Pipeline *p, Operation *op) {
+  int k = 0;
+  for (DataElement &e : p->outputData->objects) {
+    if (e.operation == op) return k;
+    k++;
+  }
+  return -1;
+}
+
+static int lower_op(Lowering &lw, Operation *op) {
+  LoweredPipeline *o = lw.out;
+  if (lw.failed || lw.too_big) return 0;
+  nl_expr_node nd = {NL_OP_INPUT, -1, -1, -1, -1};
+  if (op->Type() == OPTYPE_obj || op->Type() == OPTYPE_pipeline) {
+    DataSource *src = find_input(lw.pipeline, op);
+    if (!src) {
+      PyErr_SetString(PyExc_ValueError, "Column/Pipeline operation found, but not found in inputData.");   // compiler.cpp:225
+      lw.failed = true;
+      return 0;
+    }
+    // two leaves of the same thunk share one input slot (one column, read once per use)
+    int k = -1;
+    for (int i = 0; i < o->n_inputs; i++)
+      if (o->input_sources[i] == src || (src->object && o->input_sources[i]->object == src->object)) { k = i; break; }
+    if (k < 0) {
+      if (o->n_inputs >= NL_MAX_INPUTS) { lw.too_big = true; return 0; }
+      k = o->n_inputs++;
+      o->input_sources[k] = src;
+    }
+    nd.input = k;
+  } else {
+    ThunkOperation *top = GetThunkOperation(op);
+    if (!top || top->gencode.opcode < 0) {
+      PyErr_SetString(PyExc_ValueError, "operation has no kernel op-code and is not a pipeline root");
+      lw.failed = true;
+      return 0;
+    }
+    nd.op = top->gencode.opcode;
+    if (op->Type() == OPTYPE_unop) {
+      nd.lhs = lower_op(lw, ((UnaryOperation *)op)->LHS);
+    } else {
+      nd.lhs = lower_op(lw, ((BinaryOperation *)op)->LHS);
+      nd.rhs = lower_op(lw, ((BinaryOperation *)op)->RHS);
+    }
+  }
+  if (op->materialize) nd.output = find_output(lw.pipeline, op);
+  if (lw.failed || lw.too_big) return 0;
+  if (o->n_nodes >= NL_MAX_NODES) { lw.too_big = true; return 0; }
+  o->nodes[o->n_nodes] = nd;
+  return o->n_nodes++;
+}
+
+static int subtree_size(Operation *op) {
+  switch (op->Type()) {
+    case OPTYPE_unop: return 1 + subtree_size(((UnaryOperation *)op)->LHS);
+    case OPTYPE_binop: return 1 + subtree_size(((BinaryOperation *)op)->LHS) + subtree_size(((BinaryOperation *)op)->RHS);
+    default: return 1;
+  }
+}
+
+// the interior node whose subtree is closest to half of the expression: cutting there keeps
+// both halves as fused as possible
+static void pick_cut(Operation *op, Operation *root, int total, Operation **best, int *best_dist) {
+  if (op->Type() != OPTYPE_unop && op->Type() != OPTYPE_binop) return;
+  if (op != root) {
+    int d = subtree_size(op) * 2 - total;
+    if (d < 0) d = -d;
+    if (!*best || d < *best_dist) { *best = op; *best_dist = d; }
+  }
+  if (op->Type() == OPTYPE_unop) pick_cut(((UnaryOperation *)op)->LHS, root, total, best, best_dist);
+  else {
+    pick_cut(((BinaryOperation *)op)->LHS, root, total, best, best_dist);
+    pick_cut(((BinaryOperation *)op)->RHS, root, total, best, best_dist);
+  }
+}
+
+int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, PyThunkObject **cut_out) {
+  memset(out, 0, sizeof(*out));
+  Lowering lw = {pipeline, out, false, false};
+  lower_op(lw, pipeline->operation);
+  if (lw.failed) return -1;
+  out->n_outputs = (int)pipeline->outputData->objects.size();
+  if (out->n_outputs > NL_MAX_OUTPUTS) lw.too_big = true;
+
+  int rc = NL_ERR_SPLIT;
+  if (!lw.too_big) {
+    // value type of the pipeline: its (non-boolean) columns decide; scalars adopt it
+    int dtype = -1;
+    for (int k = 0; k < out->n_inputs && dtype < 0; k++) {
+      const int t = nljit_npy_to_nl(out->input_sources[k]->type);
+      if (t != NL_BOOL && out->input_sources[k]->size != 1) dtype = t;
+    }
+    for (int k = 0; k < out->n_inputs && dtype < 0; k++) {
+      const int t = nljit_npy_to_nl(out->input_sources[k]->type);
+      if (t != NL_BOOL) dtype = t;
+    }
+    if (dtype < 0) dtype = NL_I64;
+    out->dtype = dtype;
+    for (int k = 0; k < out->n_inputs; k++) {
+      DataSource *src = out->input_sources[k];
+      const int t = nljit_npy_to_nl(src->type);
+      nl_input_desc &d = out->inputs[k];
+      d.dtype = t;
+      d.imm_bits = 0;
+      if (src->size != 1) {
+        d.kind = NL_IN_ARRAY;
+      } else if (src->storage && src->storage->host_scalar) {
+        // size-1 inputs are baked as immediates (compiler.cpp:210-211)
+        d.kind = NL_IN_SCALAR_IMM;
+        if (t != NL_BOOL) { d.imm_bits = convert_scalar(src->storage->scalar_bits, t, dtype); d.dtype = dtype; }
+        else d.imm_bits = src->storage->scalar_bits & 0xff;
+      } else {
+        // the result of a child reduction stays on the device: no host round trip between pipelines
+        d.kind = NL_IN_SCALAR_DEV;
+        if (t != NL_BOOL && t != dtype) {
+          PyErr_SetString(PyExc_TypeError, "a device-resident scalar must have the dtype of the pipeline's columns");
+          return -1;
+        }
+      }
+    }
+    rc = nl_plan_compile(out->nodes, out->n_nodes, out->inputs, out->n_inputs, &out->plan);
+    if (rc == NL_OK) return 0;
+    if (rc != NL_ERR_SPLIT) {
+      nljit_raise(rc, "jit: pipeline cannot be compiled");
+      return -1;
+    }
+  }
+  // too large for one fused kernel: propose a cut
+  Operation *best = NULL;
+  int dist = 0;
+  pick_cut(pipeline->operation, pipeline->operation, subtree_size(pipeline->operation), &best, &dist);
+  if (!best || !best->thunk) {
+    nljit_raise(rc, "jit: pipeline cannot be split further");
+    return -1;
+  }
+  *cut_out = best->thunk;
+  return 1;
+}

@@ -1,0 +1,282 @@
+// scheduler.cpp — see scheduler.hpp.  What remains of scheduler.cpp:13-219 and
+// compiler.cpp:18-123 once compilation is a table lookup and execution is a kernel launch:
+//   ScheduleCompilation / CompilePipeline  -> LowerPipeline() + nl_plan_compile()
+//   ScheduleFunction   (alloc + 8 ranges)  -> output shards + one nl_launch_pipeline per device
+//   ExecuteFunction    (call the loop)     -> the launch itself
+//   JITFunctionDECREF  (gather, finalize)  -> nl_finish_reduce / shard counts, mark evaluated
+#include "scheduler.hpp"
+#include "optimizer.hpp"
+#include "debug_printer.hpp"
+
+#include <cstring>
+#include <vector>
+
+// per-device int64 scratch the kernels write output cardinalities to (compiler.cpp:491-508)
+static int64_t *g_sizes[NL_MAX_DEVICES];
+static int g_sizes_slot[NL_MAX_DEVICES];
+static const int kSizeSlots = 16;
+
+static int64_t *sizes_buffer(int dev) {
+  if (!g_sizes[dev]) {
+    void *p = NULL;
+    if (nl_malloc(dev, sizeof(int64_t) * NL_MAX_OUTPUTS * kSizeSlots, &p) != NL_OK) return NULL;
+    g_sizes[dev] = (int64_t *)p;
+  }
+  g_sizes_slot[dev] = (g_sizes_slot[dev] + 1) % kSizeSlots;
+  return g_sizes[dev] + g_sizes_slot[dev] * NL_MAX_OUTPUTS;
+}
+
+static PyThunkObject *g_pending_cut = NULL;
+
+static int sync_devices() {
+  int rc = NL_OK;
+  const int G = nljit_device_count();
+  Py_BEGIN_ALLOW_THREADS     // the reference blocks on a semaphore while holding the GIL (thunk.cpp:106)
+  for (int g = 0; g < G && rc == NL_OK; g++) rc = nl_stream_sync(g, 0);
+  Py_END_ALLOW_THREADS
+  if (rc != NL_OK) { nljit_raise(rc, "jit: device synchronisation failed"); return -1; }
+  return 0;
+}
+
+// the full pipeline breaker: materialise the child, run the NumPy base function on the host,
+// upload the result (compiler.cpp:93-122)
+static int run_base_function(Pipeline *pipeline) {
+  ThunkOperation *top = GetThunkOperation(pipeline->operation);
+  if (!top || !top->gencode.base) {
+    PyErr_SetString(PyExc_ValueError, "pipeline root has neither a kernel op-code nor a base function");
+    return -1;
+  }
+  if (pipeline->inputData->objects.size() != 1) {
+    PyErr_SetString(PyExc_ValueError, "Expected 1 parameter for a base function.");
+    return -1;
+  }
+  DataSource *in = pipeline->inputData->objects[0].source;
+  if (!in->storage) { PyErr_SetString(PyExc_ValueError, "base function input is not evaluated"); return -1; }
+  PyObject *host = storage_to_host(in->storage);
+  if (!host) return -1;
+  PyObject *result = top->gencode.base(host);
+  Py_DECREF(host);
+  if (!result) return -1;
+  PyObject *t = PyThunk_FromArray(NULL, result);     // uploads
+  Py_DECREF(result);
+  if (!t) return -1;
+  PyThunkObject *tt = (PyThunkObject *)t;
+  if (PyThunk_EnsureDevice(tt) < 0) { Py_DECREF(t); return -1; }
+  DataElement &out = pipeline->outputData->objects[0];
+  storage_incref(tt->storage);
+  out.source->storage = tt->storage;
+  storage_incref(tt->storage);
+  out.source->size = (ssize_t)tt->storage->cardinality();
+  PyThunk_MarkEvaluated(out.source->object, tt->storage);
+  Py_DECREF(t);
+  return 0;
+}
+
+static int execute_one(Pipeline *pipeline) {
+  if (nljit_ensure_runtime() < 0) return -1;
+  ThunkOperation *root_op = GetThunkOperation(pipeline->operation);
+  if (root_op && root_op->gencode.opcode < 0) return run_base_function(pipeline);
+
+  // inputs must be resident (deferred upload of host-only thunks)
+  for (DataElement &e : pipeline->inputData->objects) {
+    DataSource *src = e.source;
+    if (!src->storage && src->object) {
+      if (PyThunk_EnsureDevice(src->object) < 0) return -1;
+      src->storage = src->object->storage;
+      storage_incref(src->storage);
+    }
+    if (!src->storage) { PyErr_SetString(PyExc_ValueError, "pipeline input is not evaluated"); return -1; }
+    src->size = (ssize_t)src->storage->cardinality();
+  }
+
+  // a one-element column that is neither a host scalar nor replicated (e.g. a filter that kept one
+  // element) is broadcast like any size-1 input (compiler.cpp:210): fetch it and bake it
+  for (DataElement &e : pipeline->inputData->objects) {
+    Storage *s = e.source->storage;
+    if (e.source->size == 1 && !s->host_scalar && !s->replicated) {
+      PyObject *host = storage_to_host(s);
+      if (!host) return -1;
+      Storage *hs = storage_new(s->dtype, 1);
+      hs->host_scalar = true;
+      memcpy(&hs->scalar_bits, PyArray_DATA((PyArrayObject *)host), nl_dtype_size(s->dtype));
+      Py_DECREF(host);
+      storage_decref(s);
+      e.source->storage = hs;
+    }
+  }
+
+  LoweredPipeline lp;
+  PyThunkObject *cut = NULL;
+  int lrc = LowerPipeline(pipeline, &lp, &cut);
+  if (lrc < 0) return -1;
+  if (lrc == 1) {
+    // handled by EvaluateWithCuts: re-parse with `cut` as an extra breaker
+    g_pending_cut = cut;
+    return -2;
+  }
+  if (debug_plan_enabled()) PrintPlan(pipeline, &lp.plan);
+
+  const int G = nljit_device_count();
+  // shard geometry: every column of a pipeline shares one partition (compiler.cpp:413, 428)
+  Storage *shape = NULL;
+  for (int k = 0; k < lp.n_inputs; k++) {
+    Storage *s = lp.input_sources[k]->storage;
+    if (lp.inputs[k].kind != NL_IN_ARRAY) continue;
+    if (!shape) { shape = s; continue; }
+    bool same = s->shards.size() == shape->shards.size();
+    for (size_t g = 0; same && g < s->shards.size(); g++) same = s->shards[g].count == shape->shards[g].count;
+    if (!same) {
+      PyErr_SetString(PyExc_TypeError, "Incompatible cardinality.");
+      return -1;
+    }
+  }
+  if (!shape) {
+    PyErr_SetString(PyExc_ValueError, "a pipeline needs at least one column input");
+    return -1;
+  }
+
+  // outputs (ScheduleFunction, scheduler.cpp:107-122; no zero fill — the reference's own FIXME)
+  std::vector<Storage *> outs(lp.n_outputs, (Storage *)NULL);
+  auto fail = [&](void) { for (Storage *s : outs) if (s) storage_decref(s); return -1; };
+  for (int k = 0; k < lp.n_outputs; k++) {
+    const int space = lp.plan.out[k].index_space;
+    if (space == NL_IDX_WHERE) {
+      if (!pipeline->inplace_target || !pipeline->inplace_target->storage) {
+        PyErr_SetString(PyExc_ValueError, "masked assignment without a target"); return fail();
+      }
+      Storage *t = pipeline->inplace_target->storage;
+      bool same = t->shards.size() == shape->shards.size();
+      for (size_t g = 0; same && g < t->shards.size(); g++) same = t->shards[g].count == shape->shards[g].count;
+      if (!same) { PyErr_SetString(PyExc_IndexError, "boolean index did not match the assigned thunk's cardinality"); return fail(); }
+      storage_incref(t);
+      outs[k] = t;
+      continue;
+    }
+    Storage *s = storage_new(lp.plan.out[k].dtype, space == NL_IDX_SHARD ? 1 : shape->bound);
+    outs[k] = s;
+    s->ragged = shape->ragged || space == NL_IDX_COMPACT;
+    s->replicated = space == NL_IDX_SHARD;
+    const size_t es = nl_dtype_size(s->dtype);
+    for (int g = 0; g < G; g++) {
+      Shard sh;
+      sh.dev = g;
+      sh.start = shape->shards[g].start;
+      sh.capacity = space == NL_IDX_SHARD ? 1 : shape->shards[g].count;
+      sh.count = sh.capacity;
+      sh.ptr = NULL;
+      if (sh.capacity > 0) {
+        int rc = nl_malloc(g, (size_t)sh.capacity * es, &sh.ptr);
+        if (rc != NL_OK) { nljit_raise(rc, "jit: device allocation failed"); return fail(); }
+      }
+      s->shards.push_back(sh);
+    }
+  }
+
+  // one launch per device shard (the reference's 8 range tasks, scheduler.cpp:133-147)
+  std::vector<int64_t *> sizes(G, (int64_t *)NULL);
+  for (int g = 0; g < G; g++) {
+    void *out_ptrs[NL_MAX_OUTPUTS] = {0};
+    const void *in_ptrs[NL_MAX_INPUTS] = {0};
+    for (int k = 0; k < lp.n_outputs; k++) {
+      out_ptrs[k] = outs[k]->shards[g].ptr;
+      if (!out_ptrs[k]) out_ptrs[k] = (void *)16;     // empty shard: never dereferenced
+    }
+    for (int k = 0; k < lp.n_inputs; k++) {
+      Storage *s = lp.input_sources[k]->storage;
+      if (lp.inputs[k].kind == NL_IN_SCALAR_IMM) continue;
+      in_ptrs[k] = s->shards[g].ptr;
+      if (!in_ptrs[k]) in_ptrs[k] = (const void *)16;
+    }
+    sizes[g] = sizes_buffer(g);
+    if (!sizes[g]) { nljit_raise(NL_ERR_NOMEM, "jit: scratch allocation failed"); return fail(); }
+    int rc = nl_launch_pipeline(&lp.plan, out_ptrs, in_ptrs, 0, shape->shards[g].count, sizes[g], 0, g, 0);
+    if (rc != NL_OK) { nljit_raise(rc, "jit: pipeline launch failed"); return fail(); }
+  }
+
+  // finish (JITFunctionDECREF, compiler.cpp:30-49; llvm_finalize_sum_data, thunk_methods.cpp:133-151)
+  bool need_counts = false;
+  for (int k = 0; k < lp.n_outputs; k++) {
+    const int space = lp.plan.out[k].index_space;
+    if (space == NL_IDX_SHARD) {
+      void *ptrs[NL_MAX_DEVICES];
+      for (int g = 0; g < G; g++) ptrs[g] = outs[k]->shards[g].ptr;
+      int rc = nl_finish_reduce(lp.plan.reduce_op, outs[k]->dtype, ptrs, 0);      // NCCL allreduce over NVLink
+      if (rc != NL_OK) { nljit_raise(rc, "jit: reduction finish failed"); return fail(); }
+    } else if (space == NL_IDX_COMPACT) {
+      need_counts = true;
+    }
+  }
+  if (need_counts) {
+    // the shard counts are what the memmove gather of compiler.cpp:36-48 becomes: each shard's
+    // run starts at the exclusive scan of the counts before it
+    std::vector<int64_t> host((size_t)G * NL_MAX_OUTPUTS, 0);
+    for (int g = 0; g < G; g++) {
+      int rc = nl_memcpy_d2h(g, 0, &host[(size_t)g * NL_MAX_OUTPUTS], sizes[g], sizeof(int64_t) * (size_t)lp.n_outputs);
+      if (rc != NL_OK) { nljit_raise(rc, "jit: count read-back failed"); return fail(); }
+    }
+    if (sync_devices() < 0) return fail();
+    for (int k = 0; k < lp.n_outputs; k++)
+      if (lp.plan.out[k].index_space == NL_IDX_COMPACT)
+        for (int g = 0; g < G; g++) outs[k]->shards[g].count = host[(size_t)g * NL_MAX_OUTPUTS + k];
+  }
+
+  // mark the output thunks evaluated (compiler.cpp:51) and publish the storage to parents
+  int k = 0;
+  for (DataElement &e : pipeline->outputData->objects) {
+    if (lp.plan.out[k].index_space != NL_IDX_WHERE) {
+      storage_incref(outs[k]);
+      e.source->storage = outs[k];
+      e.source->size = (ssize_t)outs[k]->cardinality();
+      storage_incref(outs[k]);
+      PyThunk_MarkEvaluated(e.source->object, outs[k]);
+    }
+    k++;
+  }
+  for (Storage *s : outs) storage_decref(s);
+  pipeline->evaluated = true;
+  return 0;
+}
+
+static int execute_tree(Pipeline *pipeline) {
+  // children first: a parent is only scheduled once all of its children are evaluated
+  // (scheduler.cpp:13-50); stream order makes their results visible without host syncs
+  for (Pipeline *c : pipeline->children) {
+    int rc = execute_tree(c);
+    if (rc != 0) return rc;
+  }
+  return execute_one(pipeline);
+}
+
+int ScheduleExecution(Pipeline *pipeline) {
+  int rc = execute_tree(pipeline);
+  if (rc == -2) return -2;
+  if (rc < 0) return -1;
+  return sync_devices();
+}
+
+// parse -> execute, re-parsing with an extra breaker whenever the optimiser reports that an
+// expression does not fit one fused kernel
+static int EvaluateWithCuts(PyThunkObject *root, PyThunkObject *inplace_target) {
+  std::set<PyThunkObject *> cuts;
+  for (int attempt = 0; attempt < 32; attempt++) {
+    Pipeline *pipeline = ParsePipeline(root, &cuts);
+    if (!pipeline) return -1;
+    pipeline->inplace_target = inplace_target;
+    if (debug_plan_enabled()) PrintPipeline(pipeline);
+    int rc = ScheduleExecution(pipeline);
+    DestroyPipeline(pipeline);
+    if (rc == -2 && g_pending_cut && !cuts.count(g_pending_cut)) {
+      cuts.insert(g_pending_cut);
+      g_pending_cut = NULL;
+      continue;
+    }
+    if (rc == -2) break;
+    return rc;
+  }
+  PyErr_SetString(PyExc_ValueError, "expression could not be split into fused pipelines");
+  return -1;
+}
+
+int ScheduleThunk(PyThunkObject *thunk) { return EvaluateWithCuts(thunk, NULL); }
+
+int ScheduleInPlace(PyThunkObject *where, PyThunkObject *target) { return EvaluateWithCuts(where, target); }

@@ -1,0 +1,269 @@
+// thunk_as_mapping.cpp — t[mask] and t[index] = value (reference: thunk_as_mapping.cpp:9-97).
+//
+// Subscript: a boolean thunk index builds the lazy filter, exactly as in the reference; the
+// LLVM emitters (llvm_generate_subscript / llvm_initialize_subscript) are replaced by the
+// NL_OP_FILTER op-code.  Assignment keeps the reference's ordering — force every dependent of
+// the target, force the target, then update it in place (thunk_as_mapping.cpp:80-86) — but
+// the update runs on the device (the reference delegated to NumPy setitem on host storage).
+#include "thunk.hpp"
+#include "scheduler.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+static ssize_t subscript_cardinality_function(ssize_t *inputs) {
+  return inputs[1];     // upper bound: the mask's size (thunk_as_mapping.cpp:32-35)
+}
+
+static PyObject *thunk_subscript(PyObject *self_o, PyObject *other) {
+  PyThunkObject *self = (PyThunkObject *)self_o;
+  if (!PyThunk_Check(other)) {
+    PyErr_SetString(PyExc_IndexError, "FIXME: other types of array access");   // thunk_as_mapping.cpp:61
+    return NULL;
+  }
+  PyThunkObject *other_thunk = (PyThunkObject *)other;
+  if (other_thunk->type == NPY_BOOL) {
+    if (self->type == NPY_BOOL) {
+      PyErr_SetString(PyExc_IndexError, "filtering a boolean thunk is not supported");
+      return NULL;
+    }
+    if (self->cardinality > 1 && other_thunk->cardinality > 1 && self->cardinality_type == cardinality_exact &&
+        other_thunk->cardinality_type == cardinality_exact && self->cardinality != other_thunk->cardinality) {
+      PyErr_SetString(PyExc_IndexError, "boolean index did not match the indexed thunk's cardinality");
+      return NULL;
+    }
+    // boolean access: cardinality depends on the number of TRUE entries (upper bound)
+    ThunkOperation *op = ThunkOperation_FromBinary(self_o, other, optype_vectorizable, NL_OP_FILTER, "[]");
+    if (!op) return PyErr_NoMemory();
+    return PyThunk_FromOperation(op, subscript_cardinality_function, cardinality_upper_bound, self->type);
+  }
+  if (other_thunk->type == NPY_INT64 || other_thunk->type == NPY_INT32) {
+    // declared but never implemented in the reference (no emitter, thunk_as_mapping.cpp:51-55)
+    PyErr_SetString(PyExc_IndexError, "integer-array indexing (gather) is not implemented");
+    return NULL;
+  }
+  PyErr_SetString(PyExc_IndexError, "arrays used as indices must be of integer (or boolean) type");
+  return NULL;
+}
+
+// ---- in-place assignment ---------------------------------------------------------------
+
+// value -> bit pattern in the target's dtype (NumPy casting of a scalar on setitem)
+static int scalar_bits_of(PyObject *value, int npy_type, uint64_t *bits) {
+  PyArray_Descr *descr = PyArray_DescrFromType(npy_type);
+  if (!descr) return -1;
+  PyObject *arr = PyArray_FromAny(value, descr, 0, 0, NPY_ARRAY_FORCECAST, NULL);   // steals descr
+  if (!arr) return -1;
+  if (PyArray_SIZE((PyArrayObject *)arr) != 1) {
+    Py_DECREF(arr);
+    PyErr_SetString(PyExc_ValueError, "setting a thunk element with a sequence");
+    return -1;
+  }
+  *bits = 0;
+  memcpy(bits, PyArray_DATA((PyArrayObject *)arr), (size_t)PyArray_ITEMSIZE((PyArrayObject *)arr));
+  Py_DECREF(arr);
+  return 0;
+}
+
+// part of the global index run lo, lo+step, ... (count items) that falls into [s0, s1)
+static bool intersect_run(int64_t lo, int64_t step, int64_t count, int64_t s0, int64_t s1, int64_t *kmin, int64_t *kmax) {
+  if (count <= 0 || s1 <= s0) return false;
+  int64_t a, b;
+  if (step > 0) {
+    a = (s0 - lo + step - 1) / step;              // ceil
+    if (s0 <= lo) a = 0;
+    if (s1 - 1 < lo) return false;
+    b = (s1 - 1 - lo) / step;
+  } else {
+    const int64_t m = -step;
+    a = (lo - (s1 - 1) + m - 1) / m;
+    if (lo <= s1 - 1) a = 0;
+    if (lo < s0) return false;
+    b = (lo - s0) / m;
+  }
+  if (b > count - 1) b = count - 1;
+  if (a > b) return false;
+  *kmin = a;
+  *kmax = b;
+  return true;
+}
+
+static int assign_run(PyThunkObject *self, int64_t lo, int64_t step, int64_t count, PyObject *value) {
+  Storage *st = self->storage;
+  const int nl_type = st->dtype;
+  const size_t es = nl_dtype_size(nl_type);
+  if (st->host_scalar) {
+    uint64_t bits;
+    if (count != 1 || scalar_bits_of(value, self->type, &bits) < 0) {
+      if (!PyErr_Occurred()) PyErr_SetString(PyExc_IndexError, "index out of range for a size-1 thunk");
+      return -1;
+    }
+    st->scalar_bits = bits;
+    return 0;
+  }
+  if (st->ragged && st->shards.size() > 1) {
+    PyErr_SetString(PyExc_ValueError, "assignment into a filtered thunk sharded over several devices is not supported");
+    return -1;
+  }
+  // scalar or array value?
+  PyObject *varr = NULL;
+  bool scalar = true;
+  if (PyThunk_Check(value)) {
+    PyThunkObject *vt = (PyThunkObject *)value;
+    if (vt->cardinality != 1 || !vt->evaluated) {
+      varr = PyThunk_AsArray(value);           // forces it; borrowed
+      if (!varr) return -1;
+      Py_INCREF(varr);
+      scalar = PyArray_SIZE((PyArrayObject *)varr) == 1;
+    } else {
+      varr = storage_to_host(vt->storage);
+      if (!varr) return -1;
+    }
+  } else {
+    PyArray_Descr *descr = PyArray_DescrFromType(self->type);
+    varr = PyArray_FromAny(value, descr, 0, 0, NPY_ARRAY_FORCECAST | NPY_ARRAY_C_CONTIGUOUS | NPY_ARRAY_ALIGNED, NULL);
+    if (!varr) return -1;
+    scalar = PyArray_SIZE((PyArrayObject *)varr) == 1;
+  }
+  if (PyArray_TYPE((PyArrayObject *)varr) != self->type) {
+    PyObject *cast = PyArray_Cast((PyArrayObject *)varr, self->type);
+    Py_DECREF(varr);
+    if (!cast) return -1;
+    varr = cast;
+  }
+  if (!scalar && (int64_t)PyArray_SIZE((PyArrayObject *)varr) != count) {
+    PyErr_Format(PyExc_ValueError, "could not broadcast input array of size %lld into a selection of size %lld",
+                 (long long)PyArray_SIZE((PyArrayObject *)varr), (long long)count);
+    Py_DECREF(varr);
+    return -1;
+  }
+  uint64_t bits = 0;
+  if (scalar) memcpy(&bits, PyArray_DATA((PyArrayObject *)varr), es);
+  const char *vdata = (const char *)PyArray_DATA((PyArrayObject *)varr);
+
+  int rc = NL_OK;
+  int64_t gstart = 0;     // global index of the shard's first element (== sh.start unless ragged on one device)
+  for (Shard &sh : st->shards) {
+    const int64_t s0 = st->ragged ? gstart : sh.start, s1 = s0 + sh.count;
+    gstart += sh.count;
+    int64_t kmin, kmax;
+    if (!intersect_run(lo, step, count, s0, s1, &kmin, &kmax)) continue;
+    const int64_t llo = lo + kmin * step - s0, lcount = kmax - kmin + 1;
+    if (scalar) {
+      rc = nl_assign_fill(sh.dev, 0, sh.ptr, nl_type, llo, step, lcount, bits);
+    } else {
+      void *tmp = NULL;
+      rc = nl_malloc(sh.dev, (size_t)lcount * es, &tmp);
+      if (rc == NL_OK) rc = nl_memcpy_h2d(sh.dev, 0, tmp, vdata + (size_t)kmin * es, (size_t)lcount * es);
+      if (rc == NL_OK) rc = nl_assign_copy(sh.dev, 0, sh.ptr, nl_type, llo, step, lcount, tmp);
+      if (rc == NL_OK) rc = nl_stream_sync(sh.dev, 0);
+      if (tmp) nl_free(sh.dev, tmp);
+    }
+    if (rc != NL_OK) break;
+  }
+  Py_DECREF(varr);
+  if (rc != NL_OK) { nljit_raise(rc, "jit: in-place assignment failed"); return -1; }
+  return 0;
+}
+
+static int thunk_assign_subscript(PyObject *self_o, PyObject *ind, PyObject *value) {
+  PyThunkObject *self = (PyThunkObject *)self_o;
+  if (value == NULL) {
+    PyErr_SetString(PyExc_TypeError, "thunk elements cannot be deleted");
+    return -1;
+  }
+
+  // a[mask] = scalar with a mask that is a pure temporary (a[a > 5] = 0) is fused into one
+  // in-place pass; a mask someone else can still observe is forced first like any dependent
+  PyObject *where = NULL;
+  bool fused_mask = false;
+  if (PyThunk_Check(ind)) {
+    PyThunkObject *mask = (PyThunkObject *)ind;
+    if (mask->type != NPY_BOOL) {
+      PyErr_SetString(PyExc_IndexError, "only boolean thunks can be used as assignment masks");
+      return -1;
+    }
+    PyObject *vt = PyThunk_Coerce(value);
+    if (!vt) return -1;
+    if (((PyThunkObject *)vt)->cardinality != 1) {
+      Py_DECREF(vt);
+      PyErr_SetString(PyExc_ValueError, "masked assignment takes a scalar value");
+      return -1;
+    }
+    if (((PyThunkObject *)vt)->type != self->type) {
+      // cast the scalar to the target dtype (NumPy setitem casting)
+      uint64_t bits;
+      PyObject *host = PyThunk_AsArray(vt);
+      if (!host || scalar_bits_of(host, self->type, &bits) < 0) { Py_DECREF(vt); return -1; }
+      Py_DECREF(vt);
+      npy_intp one = 1;
+      PyObject *arr = PyArray_SimpleNew(1, &one, self->type);
+      if (!arr) return -1;
+      memcpy(PyArray_DATA((PyArrayObject *)arr), &bits, (size_t)PyArray_ITEMSIZE((PyArrayObject *)arr));
+      vt = PyThunk_FromArray(NULL, arr);
+      Py_DECREF(arr);
+      if (!vt) return -1;
+    }
+    fused_mask = !mask->evaluated && Py_REFCNT(ind) == 1 && mask->children->empty();
+    ThunkOperation *op = ThunkOperation_FromBinary(vt, ind, optype_parallelbreaker, NL_OP_WHERE_STORE, "[]=");
+    Py_DECREF(vt);
+    if (!op) { PyErr_NoMemory(); return -1; }
+    where = PyThunk_FromOperation(op, default_binary_cardinality_function, cardinality_exact, self->type);
+    if (!where) return -1;
+  }
+
+  // every thunk built from `self` must observe the OLD contents (thunk.cpp:81-88)
+  {
+    std::vector<PyThunkObject *> snapshot(*self->children);
+    for (PyThunkObject *c : snapshot) Py_INCREF(c);
+    for (PyThunkObject *c : snapshot) {
+      const bool skip = fused_mask && where && (PyObject *)c == ind;
+      // dependents reachable only through the fused mask are the assignment itself
+      if (!skip && !PyErr_Occurred()) {
+        PyObject *r = PyThunk_Evaluate(c);
+        Py_XDECREF(r);
+      }
+      Py_DECREF(c);
+    }
+    if (fused_mask && where) {
+      // children of the mask's own operands (e.g. `a` again) were handled above; the mask
+      // expression may hang below other columns too — they are read, not written, so nothing to force
+    }
+    if (PyErr_Occurred()) { Py_XDECREF(where); return -1; }
+  }
+  PyObject *r = PyThunk_Evaluate(self);
+  if (!r) { Py_XDECREF(where); return -1; }
+  Py_DECREF(r);
+  if (PyThunk_EnsureDevice(self) < 0) { Py_XDECREF(where); return -1; }
+
+  int rc = -1;
+  if (where) {
+    rc = ScheduleInPlace((PyThunkObject *)where, self);
+    Py_DECREF(where);
+  } else if (PySlice_Check(ind)) {
+    Py_ssize_t start, stop, step;
+    if (PySlice_Unpack(ind, &start, &stop, &step) < 0) return -1;
+    const Py_ssize_t count = PySlice_AdjustIndices((Py_ssize_t)self->cardinality, &start, &stop, step);
+    rc = assign_run(self, (int64_t)start, (int64_t)step, (int64_t)count, value);
+  } else if (PyIndex_Check(ind)) {
+    Py_ssize_t i = PyNumber_AsSsize_t(ind, PyExc_IndexError);
+    if (i == -1 && PyErr_Occurred()) return -1;
+    if (i < 0) i += (Py_ssize_t)self->cardinality;
+    if (i < 0 || i >= (Py_ssize_t)self->cardinality) {
+      PyErr_Format(PyExc_IndexError, "index %zd is out of bounds for a thunk of size %zd", i, (Py_ssize_t)self->cardinality);
+      return -1;
+    }
+    rc = assign_run(self, (int64_t)i, 1, 1, value);
+  } else {
+    PyErr_SetString(PyExc_IndexError, "thunk assignment supports integer, slice and boolean-thunk indices");
+    return -1;
+  }
+  if (rc == 0) PyThunk_InvalidateHost(self);
+  return rc;
+}
+
+PyMappingMethods thunk_as_mapping = {
+    (lenfunc)NULL,                          /* mp_length (NULL in the reference, thunk_as_mapping.cpp:89) */
+    (binaryfunc)thunk_subscript,            /* mp_subscript */
+    (objobjargproc)thunk_assign_subscript,  /* mp_ass_subscript */
+};

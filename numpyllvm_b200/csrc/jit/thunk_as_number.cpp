@@ -1,0 +1,146 @@
+// thunk_as_number.cpp — lazy arithmetic and comparisons (reference: thunk_as_number.cpp:9-128).
+// The reference implements `*` (nb_multiply) and `>=` only; `+`, `-` and the other five
+// comparisons are filled in on the same slots with the same shape.  Instead of
+// an LLVM emitter each operation records the op-code the kernel library executes.
+#include "thunk.hpp"
+
+static bool is_float_type(int t) { return t == NPY_FLOAT32 || t == NPY_FLOAT64; }
+
+// The reference types the result after the LEFT operand (thunk_as_number.cpp:78, "todo: correct
+// type") and would hand LLVM mismatched operand widths (Q3).  Here: scalars adopt the dtype of
+// the array operand (NumPy's weak-scalar rule), two arrays must agree, and a float scalar is
+// never silently truncated into an integer column.
+static int binary_value_type(PyThunkObject *l, PyThunkObject *r, int *type_out) {
+  const bool ls = l->cardinality == 1, rs = r->cardinality == 1;
+  if (l->type == NPY_BOOL || r->type == NPY_BOOL) {
+    PyErr_SetString(PyExc_TypeError, "arithmetic and comparisons on boolean thunks are not supported");
+    return -1;
+  }
+  int t;
+  if (ls && !rs) t = r->type;
+  else if (rs && !ls) t = l->type;
+  else {
+    if (l->type != r->type && !(ls && rs)) {
+      PyErr_SetString(PyExc_TypeError, "operands must have the same dtype (no implicit promotion between columns)");
+      return -1;
+    }
+    t = l->type;
+  }
+  PyThunkObject *scalar = (ls && !rs) ? l : (rs && !ls) ? r : NULL;
+  if (scalar && is_float_type(scalar->type) && !is_float_type(t)) {
+    PyErr_SetString(PyExc_TypeError, "a float scalar cannot be combined with an integer column");
+    return -1;
+  }
+  *type_out = t;
+  return 0;
+}
+
+static int check_cardinality(PyThunkObject *l, PyThunkObject *r) {
+  // thunk_as_number.cpp:60-65 meant this check but compared against the enum (Q9)
+  if (l->cardinality > 1 && r->cardinality > 1 && l->cardinality_type == cardinality_exact &&
+      r->cardinality_type == cardinality_exact && l->cardinality != r->cardinality) {
+    PyErr_SetString(PyExc_TypeError, "Incompatible cardinality.");
+    return -1;
+  }
+  return 0;
+}
+
+static PyObject *lazy_binary(PyObject *v, PyObject *w, int opcode, const char *opname) {
+  if (!PyThunk_Check(v) && !PyThunk_Check(w)) Py_RETURN_NOTIMPLEMENTED;
+  PyObject *lo = PyThunk_Coerce(v);
+  if (!lo) return NULL;
+  PyObject *ro = PyThunk_Coerce(w);
+  if (!ro) { Py_DECREF(lo); return NULL; }
+  PyThunkObject *left = (PyThunkObject *)lo, *right = (PyThunkObject *)ro;
+  int type;
+  if (binary_value_type(left, right, &type) < 0 || check_cardinality(left, right) < 0) {
+    Py_DECREF(lo); Py_DECREF(ro);
+    return NULL;
+  }
+  ThunkOperation *op = ThunkOperation_FromBinary(lo, ro, optype_vectorizable, opcode, opname);
+  Py_DECREF(lo); Py_DECREF(ro);      // the operation holds its own references
+  if (!op) return PyErr_NoMemory();
+  return PyThunk_FromOperation(op, default_binary_cardinality_function, cardinality_exact, type);
+}
+
+static PyObject *thunk_lazymultiply(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_MUL, "*"); }
+static PyObject *thunk_lazyadd(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_ADD, "+"); }
+static PyObject *thunk_lazysubtract(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_SUB, "-"); }
+
+PyObject *PyThunk_LazyRichCompare(PyObject *self, PyObject *other, int cmp_op) {
+  if (!PyThunk_Check(self)) {
+    PyErr_SetString(PyExc_ValueError, "Expected a thunk object.");
+    return NULL;
+  }
+  int opcode;
+  const char *name;
+  switch (cmp_op) {
+    case Py_GE: opcode = NL_OP_GE; name = ">="; break;   // the one the reference has (thunk_as_number.cpp:21)
+    case Py_GT: opcode = NL_OP_GT; name = ">"; break;
+    case Py_LE: opcode = NL_OP_LE; name = "<="; break;
+    case Py_LT: opcode = NL_OP_LT; name = "<"; break;
+    case Py_EQ: opcode = NL_OP_EQ; name = "=="; break;
+    default:    opcode = NL_OP_NE; name = "!="; break;
+  }
+  PyObject *ro = PyThunk_Coerce(other);
+  if (!ro) return NULL;
+  PyThunkObject *left = (PyThunkObject *)self, *right = (PyThunkObject *)ro;
+  int type;
+  if (binary_value_type(left, right, &type) < 0 || check_cardinality(left, right) < 0) {
+    Py_DECREF(ro);
+    return NULL;
+  }
+  ThunkOperation *op = ThunkOperation_FromBinary(self, ro, optype_vectorizable, opcode, name);
+  Py_DECREF(ro);
+  if (!op) return PyErr_NoMemory();
+  return PyThunk_FromOperation(op, default_binary_cardinality_function, cardinality_exact,
+                               NPY_BOOL /* returns a boolean array */);
+}
+
+// boolean thunks: & | ^ ~ combine masks inside the same fused pipeline
+static PyObject *lazy_mask_binary(PyObject *v, PyObject *w, int opcode, const char *opname) {
+  if (!PyThunk_Check(v) || !PyThunk_Check(w)) Py_RETURN_NOTIMPLEMENTED;
+  PyThunkObject *l = (PyThunkObject *)v, *r = (PyThunkObject *)w;
+  if (l->type != NPY_BOOL || r->type != NPY_BOOL) {
+    PyErr_SetString(PyExc_TypeError, "&, | and ^ are defined on boolean thunks only");
+    return NULL;
+  }
+  if (check_cardinality(l, r) < 0) return NULL;
+  ThunkOperation *op = ThunkOperation_FromBinary(v, w, optype_vectorizable, opcode, opname);
+  if (!op) return PyErr_NoMemory();
+  return PyThunk_FromOperation(op, default_binary_cardinality_function, cardinality_exact, NPY_BOOL);
+}
+static PyObject *thunk_lazyand(PyObject *v, PyObject *w) { return lazy_mask_binary(v, w, NL_OP_AND, "&"); }
+static PyObject *thunk_lazyor(PyObject *v, PyObject *w) { return lazy_mask_binary(v, w, NL_OP_OR, "|"); }
+static PyObject *thunk_lazyxor(PyObject *v, PyObject *w) { return lazy_mask_binary(v, w, NL_OP_XOR, "^"); }
+static PyObject *thunk_lazyinvert(PyObject *v) {
+  PyThunkObject *l = (PyThunkObject *)v;
+  if (l->type != NPY_BOOL) {
+    PyErr_SetString(PyExc_TypeError, "~ is defined on boolean thunks only");
+    return NULL;
+  }
+  ThunkOperation *op = ThunkOperation_FromUnary(v, optype_vectorizable, NL_OP_NOT, NULL, "~");
+  if (!op) return PyErr_NoMemory();
+  return PyThunk_FromOperation(op, default_cardinality_function, cardinality_exact, NPY_BOOL);
+}
+
+// Python 3 layout of the number protocol (the reference's table is the Python 2 one,
+// thunk_as_number.cpp:83-123); every slot not named here stays NULL as in the reference.
+PyNumberMethods thunk_as_number = {
+    (binaryfunc)thunk_lazyadd,       /* nb_add */
+    (binaryfunc)thunk_lazysubtract,  /* nb_subtract */
+    (binaryfunc)thunk_lazymultiply,  /* nb_multiply */
+    0,                               /* nb_remainder */
+    0,                               /* nb_divmod */
+    0,                               /* nb_power */
+    0,                               /* nb_negative */
+    0,                               /* nb_positive */
+    0,                               /* nb_absolute */
+    0,                               /* nb_bool */
+    (unaryfunc)thunk_lazyinvert,     /* nb_invert */
+    0,                               /* nb_lshift */
+    0,                               /* nb_rshift */
+    (binaryfunc)thunk_lazyand,       /* nb_and */
+    (binaryfunc)thunk_lazyxor,       /* nb_xor */
+    (binaryfunc)thunk_lazyor,        /* nb_or */
+};

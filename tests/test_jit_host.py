@@ -1,0 +1,153 @@
+"""CPU-only checks of the `jit` extension's host logic: the Python surface of the reference
+(jitpackage.cpp, thunk.cpp, thunk_as_*.cpp, thunk_methods.cpp), the parser's pipeline split
+(parser.cpp:81-173) and the plan optimiser.  Nothing here touches a GPU."""
+import numpy as np
+import pytest
+
+import numpyllvm_b200
+
+jit = numpyllvm_b200.install_jit_alias()
+
+
+def vec(n=100, seed=42, k=1):
+    np.random.seed(seed)
+    out = [np.random.randint(1, 100, size=(n,)) for _ in range(k)]
+    return out if k > 1 else out[0]
+
+
+def has_gpu():
+    from numpyllvm_b200 import abi
+    lib = abi.load_library()
+    return lib.nl_device_count() > 0 or lib.nl_init(0, None) == 0
+
+
+def test_module_surface_matches_the_reference():
+    import jit as alias
+    assert alias is jit                                   # `import jit` is the drop-in name
+    assert jit.__doc__ == "This module provides THUNKS."  # jitpackage.cpp:5
+    t = jit.thunk(vec())
+    assert type(t).__name__ == "thunk" and type(t) is jit.thunk_type
+    for m in ("evaluate", "isevaluated", "asnumpyarray", "sort", "max", "sum"):    # thunk_methods.cpp:186-194
+        assert callable(getattr(t, m))
+    with pytest.raises(TypeError):
+        hash(t)                                           # tp_hash = PyObject_HashNotImplemented (thunk.cpp:156)
+    assert t.isevaluated() is True
+    assert (t * t).isevaluated() is False
+
+
+def test_thunk_rejects_non_arrays_like_the_reference():
+    with pytest.raises(TypeError):
+        jit.thunk(object())
+    with pytest.raises(TypeError):
+        jit.thunk(np.array(["a", "b"]))
+    with pytest.raises(TypeError):
+        jit.thunk(np.arange(4, dtype=np.uint16))
+
+
+def test_lazy_operators_build_thunks_without_computing():
+    a, b = (jit.thunk(v) for v in vec(k=2))
+    for expr in (a * b, a * 2, 2 * a, a + b, a - 1, a >= 50, a > b, a <= 3, a < b, a == b, a != 7,
+                 a[a >= 50], a.max(), a.min(), a.sum(), a.sort(), (a >= 3) & (a < 9), ~(a >= 3)):
+        assert type(expr) is jit.thunk_type and not expr.isevaluated()
+
+
+def test_error_behaviour():
+    a = jit.thunk(vec())
+    with pytest.raises(IndexError):
+        a[3]                                              # "FIXME: other types of array access"
+    with pytest.raises(IndexError):
+        a[jit.thunk(np.arange(3.0))]                      # indices must be integer or boolean
+    with pytest.raises(IndexError):
+        a[jit.thunk(np.arange(3))]                        # integer gather: declared, not implemented
+    with pytest.raises(TypeError):
+        a * jit.thunk(np.arange(7))                       # "Incompatible cardinality." (the check Q9 broke)
+    with pytest.raises(TypeError):
+        a * jit.thunk(np.arange(100.0))                   # no implicit promotion between columns (Q3)
+    with pytest.raises(TypeError):
+        a * 2.5                                           # a float scalar is never truncated into ints
+    with pytest.raises(TypeError):
+        (a >= 3) * a
+    with pytest.raises(TypeError):
+        (a >= 3).sum()
+    with pytest.raises(TypeError):
+        a & a
+
+
+def plan_lines(t):
+    return jit.plan(t).splitlines()
+
+
+def test_parser_fuses_a_vectorizable_chain_into_one_pipeline():
+    a, b, c, d, e, f = (jit.thunk(v) for v in vec(k=6))
+    res2 = (d * e * f) * (a * b * c)
+    text = jit.plan(res2)
+    assert text.count("pipeline Pipe") == 1 and "static:mul6" in text
+    assert "inputs=6 outputs=1" in text
+
+
+def test_parser_materialises_held_intermediates():
+    # parser.cpp:63-79: an intermediate that Python still references is stored as well
+    a, b, c = (jit.thunk(v) for v in vec(k=3))
+    held = a * b
+    root = held * c
+    text = jit.plan(root)
+    assert text.count("pipeline Pipe") == 1 and "outputs=2" in text
+    del held
+    assert "outputs=1" in jit.plan(root)
+
+
+def test_parser_splits_at_breakers_like_the_reference():
+    # Tests/multiplication.py:26-27: sort is a full breaker, so res, sort(res), (a*b*c) and the
+    # final product are four pipelines (parser.cpp:99-145)
+    a, b, c, d, e, f = (jit.thunk(v) for v in vec(k=6))
+    res = d * e * f
+    res2 = res.sort() * (a * b * c)
+    lines = [l for l in plan_lines(res2) if l.startswith("pipeline")]
+    assert len(lines) == 4
+    assert sum("base function sort" in l for l in lines) == 1
+    assert sum("static:mul3" in l for l in lines) == 2
+    # Tests/max.py:13-14: the sum is a parallel breaker; its parent consumes the size-1 result
+    s = (a[a >= 50]).sum()
+    r2 = s * a
+    lines = [l for l in plan_lines(r2) if l.startswith("pipeline")]
+    assert len(lines) == 2 and "static:filter_ge_sum" in lines[0]
+
+
+def test_filter_pipeline_shape():
+    a = jit.thunk(vec())
+    text = jit.plan(a[a * 2 >= 50])
+    assert "static:filter_mul_ge" in text and "out0: i64 compact" in text
+    assert text.count("acc = in0") == 1           # the column is read once
+
+
+def test_scalars_are_baked_as_immediates_of_the_column_type():
+    x = jit.thunk(np.arange(10, dtype=np.float32))
+    text = jit.plan(x * 2)                        # Python int with a float32 column
+    assert "dtype=f32" in text and "in1: f32 imm" in text
+    y = jit.thunk(np.arange(10, dtype=np.int32))
+    assert "in1: i32 imm" in jit.plan(y >= 3)
+
+
+def test_evaluation_fails_loudly_without_a_gpu():
+    if has_gpu():
+        pytest.skip("GPU present")
+    a, b = (jit.thunk(v) for v in vec(k=2))
+    c = a * b
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c.evaluate()
+    with pytest.raises(RuntimeError):
+        str(c)
+    with pytest.raises(RuntimeError):
+        a[0] = 1000
+    assert not c.isevaluated()
+
+
+def test_children_do_not_dangle():
+    # the reference keeps raw, un-INCREF'd child pointers (thunk.cpp:68); dropping a dependent
+    # must not leave a stale entry behind
+    a, b = (jit.thunk(v) for v in vec(k=2))
+    for _ in range(100):
+        c = a * b
+        del c
+    d = a * b
+    assert "static:mul2" in jit.plan(d)
