@@ -159,6 +159,13 @@ int nl_init(int n_devices, const int *device_ids) {
     if (prop.major < 10) { set_error("device %d is sm_%d%d; the kernel library is built for sm_100a only", dv.id, prop.major, prop.minor); return NL_ERR_NO_DEVICE; }
     dv.sm_count = prop.multiProcessorCount;
     for (int s = 0; s < NL_N_STREAMS; s++) CUDA_TRY(cudaStreamCreateWithFlags(&dv.stream[s], cudaStreamNonBlocking));
+    // column buffers come from the device's stream-ordered pool and go back to it, never to the
+    // driver: thunk storage is allocated and dropped at every evaluate and cudaMalloc/cudaFree of
+    // multi-GiB blocks costs tens of milliseconds
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dv.id));
+    uint64_t keep = UINT64_MAX;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     CUDA_TRY(cudaMalloc((void **)&dv.gather, sizeof(int64_t) * 256));
   }
   // NVLink peer access between the local devices (shard concat, peer copies)
@@ -218,7 +225,17 @@ int nl_malloc(int dev, size_t bytes, void **ptr_out) {
   if (rc) return rc;
   if (!ptr_out) { set_error("nl_malloc: null ptr_out"); return NL_ERR_INVALID; }
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
-  cudaError_t e = cudaMalloc(ptr_out, bytes ? bytes : 1);
+  // stream-ordered on the compute stream: usable there at once; other streams order themselves
+  // after it with nl_stream_wait()
+  cudaError_t e = cudaMallocAsync(ptr_out, bytes ? bytes : 1, g_dev[dev].stream[0]);
+  if (e == cudaErrorMemoryAllocation) {
+    // the pool may be holding blocks of the wrong sizes: give them back and retry once
+    cudaGetLastError();
+    cudaDeviceSynchronize();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, g_dev[dev].id) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    e = cudaMallocAsync(ptr_out, bytes ? bytes : 1, g_dev[dev].stream[0]);
+  }
   if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); set_error("out of device memory allocating %zu bytes", bytes); return NL_ERR_NOMEM; }
   CUDA_TRY(e);
   return NL_OK;
@@ -229,7 +246,9 @@ int nl_free(int dev, void *ptr) {
   if (rc) return rc;
   if (!ptr) return NL_OK;
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
-  CUDA_TRY(cudaFree(ptr));
+  // freed in compute-stream order: kernels already enqueued there still see the buffer; work on
+  // the copy streams must have been ordered before this point by the caller
+  CUDA_TRY(cudaFreeAsync(ptr, g_dev[dev].stream[0]));
   return NL_OK;
 }
 
