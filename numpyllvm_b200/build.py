@@ -54,7 +54,7 @@ def _run(cmd, verbose):
 
 
 def _headers(d):
-    return [os.path.join(d, f) for f in os.listdir(d) if f.endswith((".h", ".hpp", ".inc"))]
+    return [os.path.join(d, f) for f in os.listdir(d) if f.endswith((".h", ".hpp", ".inc", ".cuh"))]
 
 
 def build_kernels(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:

@@ -35,6 +35,11 @@ struct KParams {
 // geometry of the pipeline kernel
 constexpr int kBlock = 256;       // threads per CTA (8 warps)
 constexpr int kRows = 4;          // U: vectors per thread per tile
+#ifndef NL_DESC_STRIDE
+#define NL_DESC_STRIDE 16          // 8-byte words between consecutive tile descriptors (16 = one per 128-byte line)
+#endif
+constexpr int kMinBlocksCompact = 4;  // resident CTAs per SM of the build-time compaction shapes
+constexpr int kRowsCompact = 8;   // U of the build-time compaction shapes
 constexpr int kMinBlocks = 2;     // resident CTAs per SM the register allocation must allow
 
 struct LaunchInfo {
@@ -45,6 +50,8 @@ struct LaunchInfo {
 // nl_kernels.cu
 int launch_pipeline_kernel(const nl_plan *plan, const KParams &kp, bool vec16, int sm_count,
                            void *stream /*cudaStream_t*/, LaunchInfo *info);
+// elements per tile of the kernel that nl_launch_pipeline would select for this plan
+int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16);
 int launch_finalize_partials(void *stream, int rop, int dtype, const void *partials, int n, void *out);
 int launch_assign_fill(void *stream, int sm_count, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, uint64_t bits);
 int launch_assign_copy(void *stream, int sm_count, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, const void *src);

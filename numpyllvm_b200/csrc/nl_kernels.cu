@@ -118,11 +118,11 @@ template <typename T>
 static pipeline_fn pick_T(bool vec16, bool compact, bool reduce) {
   constexpr int V16 = 16 / sizeof(T);
   if (vec16) {
-    if (compact) return reduce ? pipeline_kernel<T, V16, true, true, DynProg> : pipeline_kernel<T, V16, true, false, DynProg>;
-    return reduce ? pipeline_kernel<T, V16, false, true, DynProg> : pipeline_kernel<T, V16, false, false, DynProg>;
+    if (compact) return reduce ? pipeline_kernel<T, V16, kRows, true, true, DynProg> : pipeline_kernel<T, V16, kRows, true, false, DynProg>;
+    return reduce ? pipeline_kernel<T, V16, kRows, false, true, DynProg> : pipeline_kernel<T, V16, kRows, false, false, DynProg>;
   }
-  if (compact) return reduce ? pipeline_kernel<T, 1, true, true, DynProg> : pipeline_kernel<T, 1, true, false, DynProg>;
-  return reduce ? pipeline_kernel<T, 1, false, true, DynProg> : pipeline_kernel<T, 1, false, false, DynProg>;
+  if (compact) return reduce ? pipeline_kernel<T, 1, kRows, true, true, DynProg> : pipeline_kernel<T, 1, kRows, true, false, DynProg>;
+  return reduce ? pipeline_kernel<T, 1, kRows, false, true, DynProg> : pipeline_kernel<T, 1, kRows, false, false, DynProg>;
 }
 
 // the dynamic interpreter for (dtype, row width, mode)
@@ -178,6 +178,13 @@ static const char *dt_name(int d) {
       return NL_ERR_CUDA;                                                          \
     }                                                                              \
   } while (0)
+
+int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16) {
+  const StaticEntry *e = find_static(plan, vec16);
+  const int rows = e ? e->rows : kRows;
+  const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
+  return (int64_t)kBlock * rows * v;
+}
 
 int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t name_len, int *is_static) {
   const char *sname = nullptr;

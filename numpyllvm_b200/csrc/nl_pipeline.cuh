@@ -131,11 +131,14 @@ template <typename T> __device__ __forceinline__ unsigned long long to_bits(T v)
 constexpr unsigned long long kDescValueMask = (1ull << 62) - 1;
 constexpr unsigned long long kDescAggregate = 1ull << 62;
 constexpr unsigned long long kDescPrefix = 2ull << 62;
+// one tile descriptor per 128-byte line: neighbouring tiles are published and polled by different
+// SMs at the same time; sharing a line between them serialises in the L2 slice
+constexpr int kDescStride = NL_DESC_STRIDE;
 
 // shared memory of one CTA (tiny: scan totals, the look-back result, the reduce tree)
 struct TileShared {
-  uint32_t wtot[kBlock / 32];          // per-warp packed row totals
-  uint32_t off[kRows * (kBlock / 32)]; // exclusive offset of (row, warp) inside the tile
+  uint32_t wtot[kBlock / 32];          // elements each warp keeps in this tile
+  uint32_t off[kBlock / 32];           // exclusive offset of each warp's run inside the tile
   long long prefix;                    // elements kept before this tile
   long long tile;                      // dynamically claimed tile id
   unsigned long long red[kBlock / 32];
@@ -143,24 +146,31 @@ struct TileShared {
 };
 
 // ------------------------------------------------------------------ per-tile machine state
-template <typename T, int V, bool kCompact, bool kReduce>
+//
+// Element order inside a tile is warp-blocked: warp w owns the contiguous run
+// [w*32*E, (w+1)*32*E) of the tile and row u of lane l is the V consecutive elements at
+// w*32*E + u*32*V + l*V — every row access of a warp is one contiguous 32*V-element segment
+// (512 B for 128-bit rows), and the input order is (warp, row, lane, v).
+template <typename T, int V, int U, bool kCompact, bool kReduce>
 struct Tile {
-  static constexpr int U = kRows;
   static constexpr int E = U * V;
   static constexpr int NW = kBlock / 32;
+  static constexpr int ROWSTRIDE = 32 * V;                 // elements between consecutive rows of a lane
   static constexpr int64_t TILE = (int64_t)kBlock * E;
   static constexpr uint32_t ROWMASK = (1u << V) - 1u;
   static constexpr uint32_t FULLMASK = (E == 32) ? 0xffffffffu : ((1u << E) - 1u);
+  static constexpr int NWORDS = (U + 3) / 4;               // packed 8-bit per-row counters
+  static constexpr int LOOKBACK = 4;                       // descriptor windows (of 32) read per round trip
   static_assert(E <= 32, "one predicate bit per element");
-  static_assert(U * NW == 32, "the tile scan assumes one warp covers all (row, warp) totals");
-  static_assert(U <= 4 && V * 32 < 256, "packed 8-bit row counters");
+  static_assert(V * 32 < 256, "packed 8-bit row counters");
   using Tr = TT<T>;
   using Acc = typename Tr::Acc;
 
   T acc[E], t0[E], t1[E];
   uint32_t pacc, p0, p1, p2;
   uint32_t keep, valid;
-  int64_t cidx[U];
+  int64_t cbase;             // compacted index of this warp's run (64-bit)
+  uint32_t crow[U];          // + offset of each of this lane's rows inside the run
   int64_t thr_base, tile;
   bool full;
   // running reduction state (lives across tiles)
@@ -173,13 +183,13 @@ struct Tile {
     // block-uniform: every row of every thread is in range -> straight-line vector accesses,
     // all kRows loads of an operand are issued back to back before anything consumes them
     full = (tile_base + TILE <= p.end);
-    thr_base = tile_base + (int64_t)tid * V;     // row u lives at thr_base + u*kBlock*V
+    thr_base = tile_base + (int64_t)(tid >> 5) * (32 * E) + (int64_t)(tid & 31) * V;   // row u at thr_base + u*ROWSTRIDE
     keep = FULLMASK;
     if (!full) {
       keep = 0;
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const int64_t rem = p.end - (thr_base + (int64_t)u * kBlock * V);
+        const int64_t rem = p.end - (thr_base + (int64_t)u * ROWSTRIDE);
         const int nv = rem >= V ? V : (rem > 0 ? (int)rem : 0);
         keep |= ((1u << nv) - 1u) << (u * V);
       }
@@ -188,8 +198,9 @@ struct Tile {
     pacc = p0 = p1 = p2 = 0;
 #pragma unroll
     for (int e = 0; e < E; e++) { acc[e] = T(0); t0[e] = T(0); t1[e] = T(0); }
+    cbase = 0;
 #pragma unroll
-    for (int u = 0; u < U; u++) cidx[u] = 0;
+    for (int u = 0; u < U; u++) crow[u] = 0;
   }
 
   // x <- temporary | column rows | broadcast scalar
@@ -208,10 +219,10 @@ struct Tile {
         const T *base = reinterpret_cast<const T *>(p.in[src]) + thr_base;
         if (full) {
 #pragma unroll
-          for (int u = 0; u < U; u++) load_vec<T, V>(base + u * kBlock * V, &x[u * V]);
+          for (int u = 0; u < U; u++) load_vec<T, V>(base + u * ROWSTRIDE, &x[u * V]);
         } else {
 #pragma unroll
-          for (int e = 0; e < E; e++) x[e] = ((valid >> e) & 1u) ? base[(e / V) * kBlock * V + (e % V)] : T(0);
+          for (int e = 0; e < E; e++) x[e] = ((valid >> e) & 1u) ? base[(e / V) * ROWSTRIDE + (e % V)] : T(0);
         }
       } else {
         const T sc = (kind == NL_IN_SCALAR_IMM) ? from_bits<T>(p.imm[src]) : *reinterpret_cast<const T *>(p.in[src]);
@@ -225,55 +236,77 @@ struct Tile {
   __device__ __forceinline__ void filter_step(const KParams &p, TileShared &sh, int lane, int warp) {
     keep &= pacc;
     if constexpr (kCompact) {
-      // rank of every kept element in (row, thread, v) order == its input order
-      uint32_t packed = 0;
+      // rank of every kept element in (warp, row, lane, v) order == its input order.
+      // per-row counts travel as packed 8-bit fields, four rows per word
+      uint32_t packed[NWORDS], incl[NWORDS];
 #pragma unroll
-      for (int u = 0; u < U; u++) packed |= (uint32_t)__popc((keep >> (u * V)) & ROWMASK) << (8 * u);
-      uint32_t incl = packed;
+      for (int w = 0; w < NWORDS; w++) packed[w] = 0;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += nb;
-      }
-      const uint32_t lane_excl = incl - packed;
-      if (lane == 31) sh.wtot[warp] = incl;
-      __syncthreads();
-      if (warp == 0) {
-        // lane l <-> (row u = l / NW, warp w = l % NW): row-major == input order
-        const int u = lane / NW, w = lane % NW;
-        const uint32_t val = (sh.wtot[w] >> (8 * u)) & 0xffu;
-        uint32_t sc = val;
+      for (int u = 0; u < U; u++) packed[u / 4] |= (uint32_t)__popc((keep >> (u * V)) & ROWMASK) << (8 * (u % 4));
+#pragma unroll
+      for (int w = 0; w < NWORDS; w++) {
+        incl[w] = packed[w];
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t nb = __shfl_up_sync(0xffffffffu, incl[w], d);
+          if (lane >= d) incl[w] += nb;
+        }
+      }
+      // row bases inside the warp's run: running sum of the row totals (lane 31's inclusive counts)
+      uint32_t run = 0;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint32_t tot = (__shfl_sync(0xffffffffu, incl[u / 4], 31) >> (8 * (u % 4))) & 0xffu;
+        const uint32_t ex = ((incl[u / 4] - packed[u / 4]) >> (8 * (u % 4))) & 0xffu;
+        crow[u] = run + ex;
+        run += tot;
+      }
+      if (lane == 0) sh.wtot[warp] = run;
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t val = (lane < NW) ? sh.wtot[lane] : 0u;
+        uint32_t sc = val;
+#pragma unroll
+        for (int d = 1; d < NW; d <<= 1) {
           const uint32_t nb = __shfl_up_sync(0xffffffffu, sc, d);
           if (lane >= d) sc += nb;
         }
-        sh.off[lane] = sc - val;
-        const unsigned long long agg = __shfl_sync(0xffffffffu, sc, 31);
-        // decoupled look-back over the predecessors' descriptors
+        if (lane < NW) sh.off[lane] = sc - val;
+        const unsigned long long agg = __shfl_sync(0xffffffffu, sc, NW - 1);
+        // decoupled look-back: LOOKBACK windows of 32 predecessor descriptors are fetched per
+        // round trip (the window, not the tile, limits how fast the prefix frontier can advance)
         unsigned long long excl = 0;
         if (tile == 0) {
           if (lane == 0) st_relaxed_u64(&p.tile_desc[0], kDescPrefix | agg);
         } else {
-          if (lane == 0) st_relaxed_u64(&p.tile_desc[tile], kDescAggregate | agg);
+          if (lane == 0) st_relaxed_u64(&p.tile_desc[tile * kDescStride], kDescAggregate | agg);
           int64_t j = tile - 1;
-          while (true) {
-            const int64_t q = j - lane;
-            unsigned long long d = kDescPrefix;          // before tile 0: an empty prefix
-            if (q >= 0) {
-              d = ld_relaxed_u64(&p.tile_desc[q]);
-              while ((d >> 62) == 0) d = ld_relaxed_u64(&p.tile_desc[q]);
-            }
-            const uint32_t has_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-            const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
-            unsigned long long v = (lane <= first) ? (d & kDescValueMask) : 0ull;
+          bool done = false;
+          while (!done) {
+            unsigned long long d[LOOKBACK];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            excl += v;
-            if (has_prefix) break;
-            j -= 32;
+            for (int k = 0; k < LOOKBACK; k++) {
+              const int64_t q = j - lane - 32 * k;
+              d[k] = (q >= 0) ? ld_relaxed_u64(&p.tile_desc[q * kDescStride]) : kDescPrefix;   // before tile 0: an empty prefix
+            }
+#pragma unroll
+            for (int k = 0; k < LOOKBACK; k++) {
+              if (done) break;
+              const int64_t q = j - lane - 32 * k;
+              while ((d[k] >> 62) == 0) {
+                d[k] = ld_relaxed_u64(&p.tile_desc[q * kDescStride]);
+              }
+              const uint32_t has_prefix = __ballot_sync(0xffffffffu, (d[k] >> 62) == 2);
+              const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+              unsigned long long v = (lane <= first) ? (d[k] & kDescValueMask) : 0ull;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              excl += v;
+              if (has_prefix) done = true;
+            }
+            j -= 32 * LOOKBACK;
           }
-          if (lane == 0) st_relaxed_u64(&p.tile_desc[tile], kDescPrefix | ((excl + agg) & kDescValueMask));
+          if (lane == 0) st_relaxed_u64(&p.tile_desc[tile * kDescStride], kDescPrefix | ((excl + agg) & kDescValueMask));
         }
         if (lane == 0) {
           sh.prefix = (long long)excl;
@@ -284,10 +317,7 @@ struct Tile {
         }
       }
       __syncthreads();
-      const int64_t tile_excl = sh.prefix;
-#pragma unroll
-      for (int u = 0; u < U; u++)
-        cidx[u] = p.start + tile_excl + (int64_t)sh.off[u * NW + warp] + (int64_t)((lane_excl >> (8 * u)) & 0xffu);
+      cbase = p.start + sh.prefix + (int64_t)sh.off[warp];
     }
   }
 
@@ -375,13 +405,13 @@ struct Tile {
           if (full) {
             unsigned char bytes[E];
 #pragma unroll
-            for (int u = 0; u < U; u++) load_vec<unsigned char, V>(base + u * kBlock * V, &bytes[u * V]);
+            for (int u = 0; u < U; u++) load_vec<unsigned char, V>(base + u * ROWSTRIDE, &bytes[u * V]);
 #pragma unroll
             for (int e = 0; e < E; e++) m |= (uint32_t)(bytes[e] != 0) << e;
           } else {
 #pragma unroll
             for (int e = 0; e < E; e++)
-              if ((valid >> e) & 1u) m |= (uint32_t)(base[(e / V) * kBlock * V + (e % V)] != 0) << e;
+              if ((valid >> e) & 1u) m |= (uint32_t)(base[(e / V) * ROWSTRIDE + (e % V)] != 0) << e;
           }
         } else {
           const bool on = (kind == NL_IN_SCALAR_IMM) ? ((p.imm[a] & 0xff) != 0)
@@ -413,17 +443,17 @@ struct Tile {
           T *base = reinterpret_cast<T *>(p.out[a]) + thr_base;
           if (full) {
 #pragma unroll
-            for (int u = 0; u < U; u++) store_vec<T, V>(base + u * kBlock * V, &acc[u * V]);
+            for (int u = 0; u < U; u++) store_vec<T, V>(base + u * ROWSTRIDE, &acc[u * V]);
           } else {
 #pragma unroll
             for (int e = 0; e < E; e++)
-              if ((valid >> e) & 1u) base[(e / V) * kBlock * V + (e % V)] = acc[e];
+              if ((valid >> e) & 1u) base[(e / V) * ROWSTRIDE + (e % V)] = acc[e];
           }
         } else {
-          T *base = reinterpret_cast<T *>(p.out[a]);
+          T *base = reinterpret_cast<T *>(p.out[a]) + cbase;
 #pragma unroll
           for (int u = 0; u < U; u++) {
-            int64_t ci = cidx[u];
+            uint32_t ci = crow[u];
 #pragma unroll
             for (int v = 0; v < V; v++)
               if ((keep >> (u * V + v)) & 1u) base[ci++] = acc[u * V + v];
@@ -440,18 +470,18 @@ struct Tile {
               unsigned char bytes[V];
 #pragma unroll
               for (int v = 0; v < V; v++) bytes[v] = (unsigned char)((pacc >> (u * V + v)) & 1u);   // canonical 0x01 (Q4)
-              store_vec<unsigned char, V>(base + u * kBlock * V, bytes);
+              store_vec<unsigned char, V>(base + u * ROWSTRIDE, bytes);
             }
           } else {
 #pragma unroll
             for (int e = 0; e < E; e++)
-              if ((valid >> e) & 1u) base[(e / V) * kBlock * V + (e % V)] = (unsigned char)((pacc >> e) & 1u);
+              if ((valid >> e) & 1u) base[(e / V) * ROWSTRIDE + (e % V)] = (unsigned char)((pacc >> e) & 1u);
           }
         } else {
-          unsigned char *base = reinterpret_cast<unsigned char *>(p.out[a]);
+          unsigned char *base = reinterpret_cast<unsigned char *>(p.out[a]) + cbase;
 #pragma unroll
           for (int u = 0; u < U; u++) {
-            int64_t ci = cidx[u];
+            uint32_t ci = crow[u];
 #pragma unroll
             for (int v = 0; v < V; v++)
               if ((keep >> (u * V + v)) & 1u) base[ci++] = (unsigned char)((pacc >> (u * V + v)) & 1u);
@@ -466,11 +496,11 @@ struct Tile {
         for (int u = 0; u < U; u++) {
           const uint32_t rowbits = (m >> (u * V)) & ROWMASK;
           if (rowbits == ROWMASK) {
-            store_vec<T, V>(base + u * kBlock * V, &acc[u * V]);
+            store_vec<T, V>(base + u * ROWSTRIDE, &acc[u * V]);
           } else {
 #pragma unroll
             for (int v = 0; v < V; v++)
-              if ((rowbits >> v) & 1u) base[u * kBlock * V + v] = acc[u * V + v];
+              if ((rowbits >> v) & 1u) base[u * ROWSTRIDE + v] = acc[u * V + v];
           }
         }
         break;
@@ -562,10 +592,10 @@ struct StaticProg {
 };
 
 // ------------------------------------------------------------------ the kernel
-template <typename T, int V, bool kCompact, bool kReduce, class Prog>
-__global__ void __launch_bounds__(kBlock, Prog::is_static ? 1 : kMinBlocks)
+template <typename T, int V, int U, bool kCompact, bool kReduce, class Prog>
+__global__ void __launch_bounds__(kBlock, Prog::is_static ? (kCompact ? kMinBlocksCompact : 1) : kMinBlocks)
 pipeline_kernel(const __grid_constant__ KParams p) {
-  using TileT = Tile<T, V, kCompact, kReduce>;
+  using TileT = Tile<T, V, U, kCompact, kReduce>;
   using Tr = TT<T>;
   using Acc = typename Tr::Acc;
   constexpr int NW = kBlock / 32;
@@ -585,11 +615,14 @@ pipeline_kernel(const __grid_constant__ KParams p) {
   t.rsum = 0;
   t.rext = (p.reduce_rop == R_MIN) ? Tr::highest() : Tr::lowest();
 
+  // Plain modes stride the tiles over the grid.  Compaction hands them out with a ticket counter:
+  // tiles are claimed in order, so every predecessor of a tile is owned by a running CTA and the
+  // look-back never waits on work that has not started.  A ticket is taken only when the CTA is
+  // ready to start the tile: measured on B200, claiming one tile ahead (to prefetch it) is ~7x
+  // slower, because the parked tiles chain the CTAs' look-backs into one serial dependency.
   int64_t tile = blockIdx.x;
   while (true) {
     if constexpr (kCompact) {
-      // tiles are handed out in order so every predecessor of a tile is already owned by a
-      // running CTA: the look-back can never wait on work that has not started
       if (tid == 0) sh.tile = (long long)atomicAdd(p.tile_ticket, 1u);
       __syncthreads();
       tile = sh.tile;
@@ -672,6 +705,7 @@ struct StaticEntry {
   bool (*matches)(const uint32_t *steps, int n);
   int dtype;
   bool vec16;
+  int rows;            // U of the instantiation: rows per thread per tile
   pipeline_fn fn;
 };
 

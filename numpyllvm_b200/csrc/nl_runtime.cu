@@ -422,11 +422,10 @@ int nl_launch_pipeline(const nl_plan *plan, void *const *outputs, const void *co
 
   if (end == start) return launch_empty_range(d.stream[stream], plan, kp);
 
-  const int V = vec16 ? V16 : 1;
-  const int64_t tile = (int64_t)kBlock * kRows * V;
+  const int64_t tile = pipeline_tile_elems(plan, vec16);
   kp.n_tiles = (end - start + tile - 1) / tile;
   const bool compact = (plan->flags & NL_PLAN_HAS_COMPACT) != 0;
-  const size_t need = kTileDescOff + (compact ? (size_t)kp.n_tiles * 8 : 0);
+  const size_t need = kTileDescOff + (compact ? (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE : 0);
   rc = ensure_scratch(d, stream, need);
   if (rc) return rc;
   char *sb = d.scratch[stream].base;
@@ -435,7 +434,7 @@ int nl_launch_pipeline(const nl_plan *plan, void *const *outputs, const void *co
   kp.tile_ticket = (unsigned int *)(sb + kTileTicketOff);
   kp.tile_desc = (unsigned long long *)(sb + kTileDescOff);
   if (compact)
-    CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (size_t)kp.n_tiles * 8, d.stream[stream]));
+    CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE, d.stream[stream]));
 
   LaunchInfo info;
   rc = launch_pipeline_kernel(plan, kp, vec16, d.sm_count, d.stream[stream], &info);

@@ -31,6 +31,13 @@ template <uint32_t... S> constexpr bool has_compact() {
   return (((step_op(S) == S_STORE || step_op(S) == S_PSTORE) && step_b(S) == NL_IDX_COMPACT) || ...);
 }
 template <uint32_t... S> constexpr bool has_reduce() { return ((step_op(S) == S_REDUCE) || ...); }
+// a shape that re-reads a value temporary keeps a second register set alive: 4 rows, not 8
+template <uint32_t... S> constexpr bool reads_temp() {
+  return ((step_op(S) == S_LOADT || ((step_op(S) == S_BIN || step_op(S) == S_CMP) && (step_b(S) & SRC_TEMP))) || ...);
+}
+template <uint32_t... S> constexpr int rows_for() {
+  return (has_compact<S...>() && !reads_temp<S...>()) ? kRowsCompact : kRows;
+}
 }  // namespace sp
 
 // X(name, steps...)
@@ -71,10 +78,13 @@ template <uint32_t... S> constexpr bool has_reduce() { return ((step_op(S) == S_
   NL_CMP_SHAPES(X, ne, C_NE)
 
 // one table row per shape (128-bit rows; misaligned launches use the dynamic V = 1 kernel)
+// compaction shapes run 8 rows per thread (32 KB tiles): fewer, larger tiles keep the look-back
+// chain off the critical path; everything else 4 rows
 #define NL_STATIC_ROW(name, ...)                                                                            \
   {#name, &StaticProg<__VA_ARGS__>::matches, NL_STATIC_DTYPE, true,                                          \
-   &pipeline_kernel<NL_STATIC_T, 16 / sizeof(NL_STATIC_T), sp::has_compact<__VA_ARGS__>(),                   \
-                    sp::has_reduce<__VA_ARGS__>(), StaticProg<__VA_ARGS__>>},
+   sp::rows_for<__VA_ARGS__>(),                                                                              \
+   &pipeline_kernel<NL_STATIC_T, 16 / sizeof(NL_STATIC_T), sp::rows_for<__VA_ARGS__>(),                      \
+                    sp::has_compact<__VA_ARGS__>(), sp::has_reduce<__VA_ARGS__>(), StaticProg<__VA_ARGS__>>},
 
 #define NL_DEFINE_STATIC_TABLE(fn_name)                                                                     \
   const StaticEntry *fn_name(int *n) {                                                                      \
