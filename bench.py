@@ -104,6 +104,8 @@ def run_gpu(args):
     from numpyllvm_b200.device import Runtime
     from numpyllvm_b200.dist import Ranks
 
+    # the JSON line is the only thing this arm may print on stdout: keep NCCL's banner off it
+    os.environ["NCCL_DEBUG"] = os.environ.get("NL_NCCL_DEBUG", "WARN")
     ranks = Ranks(args.gpus)
     lib = abi.load_library()
     dev_ids = (C.c_int * 1)(ranks.local_rank)
