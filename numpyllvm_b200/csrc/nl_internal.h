@@ -30,6 +30,14 @@ struct KParams {
   int32_t reduce_out;             // its output slot
   uint8_t in_kind[NL_MAX_INPUTS];
   uint8_t out_space[NL_MAX_OUTPUTS];
+  // staged compaction pipeline (nl_compact_pipe.cuh)
+  uint8_t stage_col[NL_MAX_INPUTS];   // input k -> staged column index, 0xff: read from global
+  int32_t n_stage_cols;
+  int32_t n_inputs;
+  int32_t n_slots;                    // ring depth
+  int32_t lag;                        // tiles between the count phase and the store phase
+  int32_t batch;                      // consecutive tiles claimed per ticket
+  int32_t filter_step;                // index of the S_FILTER step
 };
 
 // geometry of the pipeline kernel
@@ -50,8 +58,9 @@ struct LaunchInfo {
 // nl_kernels.cu
 int launch_pipeline_kernel(const nl_plan *plan, const KParams &kp, bool vec16, int sm_count,
                            void *stream /*cudaStream_t*/, LaunchInfo *info);
-// elements per tile of the kernel that nl_launch_pipeline would select for this plan
-int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16);
+// elements per tile of the kernel that nl_launch_pipeline would select for this plan and size;
+// fills the staged-pipeline fields of *kp when that kernel is chosen
+int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp);
 int launch_finalize_partials(void *stream, int rop, int dtype, const void *partials, int n, void *out);
 int launch_assign_fill(void *stream, int sm_count, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, uint64_t bits);
 int launch_assign_copy(void *stream, int sm_count, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, const void *src);
@@ -60,6 +69,9 @@ int launch_fill(void *stream, int sm_count, void *dst, int dtype, int64_t first_
 int launch_empty_range(void *stream, const nl_plan *plan, const KParams &kp);
 int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t name_len, int *is_static);
 void set_static_kernels_enabled(int on);
+void set_compact_pipe_enabled(int on);
+void set_compact_pipe_batch(int b);
+void set_compact_pipe_lag(int l);
 
 void count_launch(int n = 1);
 

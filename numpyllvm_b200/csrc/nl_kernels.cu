@@ -10,7 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 
-#include "nl_pipeline.cuh"
+#include "nl_compact_pipe.cuh"
 
 namespace nl {
 
@@ -179,10 +179,71 @@ static const char *dt_name(int d) {
     }                                                                              \
   } while (0)
 
-int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16) {
+// the interpreter's staged compaction pipeline, one per dtype
+static pipeline_fn pick_dynamic_pipe(int dtype) {
+  switch (dtype) {
+    case NL_I32: return compact_pipe_kernel<int32_t, 4, DynSplit>;
+    case NL_I64: return compact_pipe_kernel<long long, 2, DynSplit>;
+    case NL_F32: return compact_pipe_kernel<float, 4, DynSplit>;
+    case NL_F64: return compact_pipe_kernel<double, 2, DynSplit>;
+  }
+  return nullptr;
+}
+
+static int g_pipe_enabled = 1;
+static int g_pipe_batch = 1;
+static int g_pipe_lag = 0;       // 0: slots - 2
+void set_compact_pipe_enabled(int on) { g_pipe_enabled = on; }
+void set_compact_pipe_batch(int b) { if (b >= 1 && b <= 4) g_pipe_batch = b; }
+void set_compact_pipe_lag(int l) { g_pipe_lag = l; }
+
+// Can this plan run on the staged compaction pipeline?  One filter, nothing stored before it,
+// at least one value column to stage, enough tiles to fill the machine.  Fills the staged fields.
+static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
+  if (!g_pipe_enabled || !vec16) return false;
+  if (!(plan->flags & NL_PLAN_HAS_COMPACT) || (plan->flags & (NL_PLAN_HAS_REDUCE | NL_PLAN_HAS_WHERE))) return false;
+  int filter = -1;
+  for (int i = 0; i < plan->n_steps; i++) {
+    const uint32_t op = step_op(plan->step[i]);
+    if (op == S_FILTER) {
+      if (filter >= 0) return false;
+      filter = i;
+    } else if ((op == S_STORE || op == S_PSTORE || op == S_WHERE) && filter < 0) {
+      return false;
+    }
+  }
+  if (filter < 0) return false;
+  const size_t es = nl_dtype_size(plan->dtype);
+  const int64_t tile = (int64_t)kPipeConsumers * kRows * (int64_t)(16 / es);
+  if (n_elems < tile * 2 * 148) return false;
+  int cols = 0;
+  uint8_t map[NL_MAX_INPUTS];
+  for (int k = 0; k < NL_MAX_INPUTS; k++) map[k] = 0xff;
+  for (int k = 0; k < plan->n_inputs; k++)
+    if (plan->in[k].kind == NL_IN_ARRAY && plan->in[k].dtype == plan->dtype) map[k] = (uint8_t)cols++;
+  if (cols == 0) return false;
+  const size_t col_bytes = (size_t)tile * es;
+  const size_t budget = (size_t)227 * 1024 - ((sizeof(PipeShared) + 127) / 128) * 128 - 1024;
+  int slots = (int)(budget / (col_bytes * (size_t)cols + (size_t)kPipeConsumers * 4));   // + the slot's keep bits
+  if (slots > kPipeMaxSlots) slots = kPipeMaxSlots;
+  if (slots < 4) return false;
+  if (kp) {
+    for (int k = 0; k < NL_MAX_INPUTS; k++) kp->stage_col[k] = map[k];
+    kp->n_stage_cols = cols;
+    kp->n_slots = slots;
+    kp->lag = (g_pipe_lag > 0 && g_pipe_lag < slots) ? g_pipe_lag : slots / 2;   // half the ring hides the look-back, half is prefetch (measured best)
+    kp->batch = g_pipe_batch;
+    kp->filter_step = filter;
+    kp->n_inputs = plan->n_inputs;
+  }
+  return true;
+}
+
+int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
+  const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
+  if (pipe_eligible(plan, vec16, n_elems, kp)) return (int64_t)kPipeConsumers * kRows * v;
   const StaticEntry *e = find_static(plan, vec16);
   const int rows = e ? e->rows : kRows;
-  const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
   return (int64_t)kBlock * rows * v;
 }
 
@@ -201,7 +262,33 @@ int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t
   return NL_OK;
 }
 
+static int launch_compact_pipe(const nl_plan *plan, const KParams &kp, int sm_count, void *stream, LaunchInfo *info) {
+  const StaticEntry *e = find_static(plan, true);
+  pipeline_fn fn = (e && e->pipe) ? e->pipe : pick_dynamic_pipe(plan->dtype);
+  if (!fn) { set_error("no compaction pipeline for dtype %d", plan->dtype); return NL_ERR_UNSUPPORTED; }
+  const size_t es = nl_dtype_size(plan->dtype);
+  const size_t col_bytes = (size_t)kPipeConsumers * kRows * 16;
+  (void)es;
+  const size_t smem = ((sizeof(PipeShared) + 127) / 128) * 128 + (size_t)kp.n_slots * ((size_t)kp.n_stage_cols * col_bytes + (size_t)kPipeConsumers * 4);
+  CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = sm_count;
+  if (grid > kp.n_tiles) grid = kp.n_tiles;
+  fn<<<(unsigned)grid, kPipeThreads, smem, (cudaStream_t)stream>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  if (info) {
+    const int v = (int)(16 / nl_dtype_size(plan->dtype));
+    snprintf(info->kernel, sizeof(info->kernel), "compact_pipe_kernel<%s,V=%d,%s%s,slots=%d,lag=%d,batch=%d>", dt_name(plan->dtype), v,
+             (e && e->pipe) ? "static:" : "dynamic", (e && e->pipe) ? e->name : "", kp.n_slots, kp.lag, kp.batch);
+    info->grid = (int)grid;
+    info->block = kPipeThreads;
+    info->vec_elems = v;
+  }
+  return NL_OK;
+}
+
 int launch_pipeline_kernel(const nl_plan *plan, const KParams &kp, bool vec16, int sm_count, void *stream, LaunchInfo *info) {
+  if (kp.n_slots > 0) return launch_compact_pipe(plan, kp, sm_count, stream, info);
   pipeline_fn fn = pick(plan, vec16, nullptr);
   if (!fn) { set_error("no pipeline kernel for dtype %d", plan->dtype); return NL_ERR_UNSUPPORTED; }
   int bps = 0;

@@ -151,16 +151,20 @@ struct TileShared {
 // [w*32*E, (w+1)*32*E) of the tile and row u of lane l is the V consecutive elements at
 // w*32*E + u*32*V + l*V — every row access of a warp is one contiguous 32*V-element segment
 // (512 B for 128-bit rows), and the input order is (warp, row, lane, v).
-template <typename T, int V, int U, bool kCompact, bool kReduce>
+//
+// BLK is the number of threads that share a tile (the CTA, or the consumer warps of the staged
+// compaction pipeline); kStaged: full tiles of column inputs are read from the shared-memory
+// slot a TMA producer filled (nl_compact_pipe.cuh) instead of from global memory.
+template <typename T, int V, int U, bool kCompact, bool kReduce, int BLK = kBlock, bool kStaged = false>
 struct Tile {
   static constexpr int E = U * V;
-  static constexpr int NW = kBlock / 32;
+  static constexpr int NW = BLK / 32;
   static constexpr int ROWSTRIDE = 32 * V;                 // elements between consecutive rows of a lane
-  static constexpr int64_t TILE = (int64_t)kBlock * E;
+  static constexpr int64_t TILE = (int64_t)BLK * E;
   static constexpr uint32_t ROWMASK = (1u << V) - 1u;
   static constexpr uint32_t FULLMASK = (E == 32) ? 0xffffffffu : ((1u << E) - 1u);
   static constexpr int NWORDS = (U + 3) / 4;               // packed 8-bit per-row counters
-  static constexpr int LOOKBACK = 4;                       // descriptor windows (of 32) read per round trip
+  static constexpr int LOOKBACK = 1;                       // descriptor windows (of 32) read per round trip
   static_assert(E <= 32, "one predicate bit per element");
   static_assert(V * 32 < 256, "packed 8-bit row counters");
   using Tr = TT<T>;
@@ -173,6 +177,8 @@ struct Tile {
   uint32_t crow[U];          // + offset of each of this lane's rows inside the run
   int64_t thr_base, tile;
   bool full;
+  const unsigned char *stage;   // kStaged: shared-memory slot of the current tile (column 0)
+  uint32_t stage_off;           // kStaged: byte offset of this lane's row 0 inside a staged column
   // running reduction state (lives across tiles)
   Acc rsum;
   T rext;
@@ -184,6 +190,7 @@ struct Tile {
     // all kRows loads of an operand are issued back to back before anything consumes them
     full = (tile_base + TILE <= p.end);
     thr_base = tile_base + (int64_t)(tid >> 5) * (32 * E) + (int64_t)(tid & 31) * V;   // row u at thr_base + u*ROWSTRIDE
+    stage_off = (uint32_t)(((tid >> 5) * (32 * E) + (tid & 31) * V) * sizeof(T));
     keep = FULLMASK;
     if (!full) {
       keep = 0;
@@ -216,6 +223,21 @@ struct Tile {
     } else {
       const int kind = p.in_kind[src];
       if (kind == NL_IN_ARRAY) {
+        if constexpr (kStaged) {
+          if (full && p.stage_col[src] != 0xff) {
+            // the tile's column sits in shared memory: 128-bit LDS per row, conflict-free
+            const T *sbase = reinterpret_cast<const T *>(stage + (size_t)p.stage_col[src] * (size_t)(TILE * sizeof(T)) + stage_off);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              using Vec = typename VecOf<sizeof(T) * V>::type;
+              union { Vec q; T t[V]; } w;
+              w.q = *reinterpret_cast<const Vec *>(sbase + u * ROWSTRIDE);
+#pragma unroll
+              for (int v = 0; v < V; v++) x[u * V + v] = w.t[v];
+            }
+            return;
+          }
+        }
         const T *base = reinterpret_cast<const T *>(p.in[src]) + thr_base;
         if (full) {
 #pragma unroll
@@ -707,6 +729,7 @@ struct StaticEntry {
   bool vec16;
   int rows;            // U of the instantiation: rows per thread per tile
   pipeline_fn fn;
+  pipeline_fn pipe;    // staged compaction pipeline (nl_compact_pipe.cuh) or nullptr
 };
 
 // per-dtype tables, defined in nl_static_<dtype>.cu

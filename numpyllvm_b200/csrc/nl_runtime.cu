@@ -422,7 +422,7 @@ int nl_launch_pipeline(const nl_plan *plan, void *const *outputs, const void *co
 
   if (end == start) return launch_empty_range(d.stream[stream], plan, kp);
 
-  const int64_t tile = pipeline_tile_elems(plan, vec16);
+  const int64_t tile = pipeline_tile_elems(plan, vec16, end - start, &kp);   // also selects the staged compaction pipeline
   kp.n_tiles = (end - start + tile - 1) / tile;
   const bool compact = (plan->flags & NL_PLAN_HAS_COMPACT) != 0;
   const size_t need = kTileDescOff + (compact ? (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE : 0);
@@ -573,7 +573,10 @@ int nl_plan_kernel(const nl_plan *plan, int vec16, char *name, size_t name_len, 
 }
 
 int nl_set_static_kernels(int enabled) {
-  set_static_kernels_enabled(enabled);
+  set_static_kernels_enabled(enabled & 1);
+  set_compact_pipe_enabled((enabled & 2) ? 0 : 1);      // bit 1 set: keep compaction on the plain kernel
+  if ((enabled >> 8) & 0xf) set_compact_pipe_batch((enabled >> 8) & 0xf);   // bits 8..11: tiles per ticket (tuning)
+  set_compact_pipe_lag((enabled >> 12) & 0xf);                              // bits 12..15: lag override (tuning)
   return NL_OK;
 }
 

@@ -10,7 +10,7 @@
 // To add a shape: append one X(...) line; tests/test_abi_host.py checks that the
 // benchmark expressions resolve to a static kernel.
 #pragma once
-#include "nl_pipeline.cuh"
+#include "nl_compact_pipe.cuh"
 
 namespace nl {
 namespace sp {
@@ -35,6 +35,11 @@ template <uint32_t... S> constexpr bool has_reduce() { return ((step_op(S) == S_
 template <uint32_t... S> constexpr bool reads_temp() {
   return ((step_op(S) == S_LOADT || ((step_op(S) == S_BIN || step_op(S) == S_CMP) && (step_b(S) & SRC_TEMP))) || ...);
 }
+// the staged compaction pipeline is instantiated for the compaction shapes only
+template <typename T, bool kOn, uint32_t... S> struct PipeFor { static constexpr pipeline_fn fn = nullptr; };
+template <typename T, uint32_t... S> struct PipeFor<T, true, S...> {
+  static constexpr pipeline_fn fn = &compact_pipe_kernel<T, 16 / sizeof(T), StaticSplit<S...>>;
+};
 template <uint32_t... S> constexpr int rows_for() {
   return (has_compact<S...>() && !reads_temp<S...>()) ? kRowsCompact : kRows;
 }
@@ -84,7 +89,8 @@ template <uint32_t... S> constexpr int rows_for() {
   {#name, &StaticProg<__VA_ARGS__>::matches, NL_STATIC_DTYPE, true,                                          \
    sp::rows_for<__VA_ARGS__>(),                                                                              \
    &pipeline_kernel<NL_STATIC_T, 16 / sizeof(NL_STATIC_T), sp::rows_for<__VA_ARGS__>(),                      \
-                    sp::has_compact<__VA_ARGS__>(), sp::has_reduce<__VA_ARGS__>(), StaticProg<__VA_ARGS__>>},
+                    sp::has_compact<__VA_ARGS__>(), sp::has_reduce<__VA_ARGS__>(), StaticProg<__VA_ARGS__>>,   \
+   sp::PipeFor<NL_STATIC_T, (sp::has_compact<__VA_ARGS__>() && !sp::has_reduce<__VA_ARGS__>()), __VA_ARGS__>::fn},
 
 #define NL_DEFINE_STATIC_TABLE(fn_name)                                                                     \
   const StaticEntry *fn_name(int *n) {                                                                      \

@@ -1,0 +1,115 @@
+"""GPU parity of the staged compaction pipeline (nl_compact_pipe.cuh: TMA producer warp, consumer
+warps, scan warps) against the oracle, and of the plain compaction kernel it replaces for large
+inputs.  Bit-exact: values, order and count."""
+import numpy as np
+import pytest
+
+import oracle
+from numpyllvm_b200 import abi
+from numpyllvm_b200.abi import Expr
+from numpyllvm_b200.device import Runtime, run_pipeline
+
+pytestmark = pytest.mark.gpu
+
+# flags of nl_set_static_kernels(): bit 0 = build-time shapes, bit 1 = keep compaction on the plain kernel
+MODES = {"pipe-static": 1, "pipe-dynamic": 0, "plain-static": 3, "plain-dynamic": 2}
+
+
+@pytest.fixture(scope="module")
+def rt(nl):
+    return Runtime.get()
+
+
+@pytest.fixture(params=list(MODES))
+def mode(request, nl):
+    nl.nl_set_static_kernels(MODES[request.param])
+    yield request.param
+    nl.nl_set_static_kernels(1)
+
+
+def tile_elems(dtype):
+    return 512 * 4 * (16 // np.dtype(dtype).itemsize)
+
+
+def check(rt, mode, e, inputs, n, expect_pipe=True):
+    ref = oracle.run(e, inputs, n, n_workers=8)
+    got = run_pipeline(rt, e, inputs, n)
+    name = rt.last_launch()[0]
+    assert ("compact_pipe_kernel" in name) == (expect_pipe and mode.startswith("pipe")), name
+    assert len(ref) == len(got)
+    for r, g in zip(ref, got):
+        assert r.shape == g.shape and np.array_equal(r.view(np.uint8), g.view(np.uint8))
+    return got
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64])
+@pytest.mark.parametrize("sel", [0.0, 0.003, 0.5, 1.0])
+def test_filter_all_dtypes(rt, mode, dtype, sel):
+    n = tile_elems(dtype) * 300 + 12345          # above the pipeline threshold, ragged last tile
+    if np.issubdtype(dtype, np.floating):
+        x, thr = oracle.fill(dtype, 0, n, 5, 3), (1.0 - sel if sel > 0 else 2.0)
+    else:
+        x, thr = oracle.fill(dtype, 0, n, 5, 0), (100 - int(99 * sel) if sel > 0 else 1000)
+    e = Expr(dtype)
+    xa = e.array()
+    e.materialize(e.filter(xa, e.ge(e.ref(xa), e.scalar(thr))))
+    (got,) = check(rt, mode, e, [x, None], n)
+    assert np.array_equal(got, x[x >= np.dtype(dtype).type(thr)])
+
+
+@pytest.mark.parametrize("extra", [0, 1, -1, 2048, 4097])
+def test_threshold_and_tile_boundaries(rt, mode, extra):
+    n = tile_elems(np.float64) * 296 + extra      # exactly at / just below the switch-over size
+    x = oracle.fill(np.float64, 0, n, 9, 3)
+    e = Expr(np.float64)
+    xa = e.array()
+    e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(0.25))))
+    check(rt, mode, e, [x, None], n, expect_pipe=(extra >= 0))
+
+
+def test_reference_filter_shape_and_two_outputs(rt, mode):
+    # Tests/filter.py's a[a*2 >= 50] (re-reads a temporary after the filter) and a pipeline that
+    # stores two compacted outputs
+    n = tile_elems(np.int64) * 300 + 7
+    x = oracle.fill(np.int64, 0, n, 42, 0)
+    e = Expr(np.int64)
+    xa = e.array()
+    e.materialize(e.filter(xa, e.ge(e.mul(e.ref(xa), e.scalar(2)), e.scalar(50))))
+    check(rt, mode, e, [x, None, None], n)
+    e = Expr(np.int64)
+    xa = e.array()
+    f = e.filter(xa, e.gt(e.ref(xa), e.scalar(30)))
+    e.materialize(f)
+    e.materialize(e.mul(f, e.scalar(3)))
+    check(rt, mode, e, [x, None, None], n)
+
+
+def test_ineligible_pipelines_stay_on_the_plain_kernel(rt, mode):
+    n = tile_elems(np.int64) * 300
+    x = oracle.fill(np.int64, 0, n, 1, 0)
+    y = oracle.fill(np.int64, 0, n, 2, 0)
+    # an intermediate stored BEFORE the filter (loop index, every element)
+    e = Expr(np.int64)
+    xa = e.array()
+    dbl = e.mul(xa, e.scalar(2))
+    e.materialize(dbl)
+    e.materialize(e.filter(e.ref(xa), e.ge(dbl, e.scalar(50))))
+    check(rt, mode, e, [x, None, None], n, expect_pipe=False)
+    # two staged columns would leave fewer than four ring slots
+    e = Expr(np.int64)
+    xa, ya = e.array(), e.array()
+    e.materialize(e.filter(xa, e.gt(ya, e.scalar(40))))
+    check(rt, mode, e, [x, y, None], n, expect_pipe=False)
+
+
+def test_repeated_launches_reuse_the_descriptors(rt, mode):
+    # the descriptor array and the ticket are reset per launch; back-to-back launches on one
+    # stream with different selectivities must not see each other's state
+    n = tile_elems(np.float32) * 300 + 99
+    x = oracle.fill(np.float32, 0, n, 3, 3)
+    for thr in (0.9, 0.1, 0.5, 0.9):
+        e = Expr(np.float32)
+        xa = e.array()
+        e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(thr))))
+        (got,) = check(rt, mode, e, [x, None], n)
+        assert len(got) == int((x > np.float32(thr)).sum())

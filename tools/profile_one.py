@@ -66,8 +66,10 @@ def main():
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--kernel-flags", type=int, default=1, help="nl_set_static_kernels() argument (tuning)")
     args = ap.parse_args()
     rt = Runtime.get(1)
+    rt.lib.nl_set_static_kernels(args.kernel_flags)
     n = args.n or (1 << args.log2n)
     plan, outs, ins, nbytes, keep = build(args.config, rt, n)
     sizes = keep[-1]
