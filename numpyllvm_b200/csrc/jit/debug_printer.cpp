@@ -25,21 +25,21 @@ bool debug_plan_enabled() {
 
 static void print_op(Operation *op, int depth) {
   for (int i = 0; i < depth; i++) fputs("  ", stderr);
-  switch (op->Type()) {
-    case OPTYPE_obj:
-      fprintf(stderr, "[%s] size=%zd\n", op->thunk && op->thunk->name ? op->thunk->name : "?", op->thunk ? op->thunk->cardinality : (ssize_t)-1);
+  switch (op->kind) {
+    case Operation::Column:
+      fprintf(stderr, "[%s] size=%zd\n", op->thunk && op->thunk->name ? op->thunk->name : "?", op->thunk ? op->thunk->card.n : (ssize_t)-1);
       break;
-    case OPTYPE_pipeline:
-      fprintf(stderr, "<%s>\n", ((PipelineOperation *)op)->pipeline->name);
+    case Operation::ChildResult:
+      fprintf(stderr, "<%s>\n", op->child->name);
       break;
-    case OPTYPE_unop:
-      fprintf(stderr, "%s%s\n", ((UnaryOperation *)op)->operation->opname, op->materialize ? "  -> stored" : "");
-      print_op(((UnaryOperation *)op)->LHS, depth + 1);
+    case Operation::Apply1:
+      fprintf(stderr, "%s%s\n", op->op->name.c_str(), op->materialize ? "  -> stored" : "");
+      print_op(op->lhs, depth + 1);
       break;
-    case OPTYPE_binop:
-      fprintf(stderr, "%s%s\n", ((BinaryOperation *)op)->operation->opname, op->materialize ? "  -> stored" : "");
-      print_op(((BinaryOperation *)op)->LHS, depth + 1);
-      print_op(((BinaryOperation *)op)->RHS, depth + 1);
+    case Operation::Apply2:
+      fprintf(stderr, "%s%s\n", op->op->name.c_str(), op->materialize ? "  -> stored" : "");
+      print_op(op->lhs, depth + 1);
+      print_op(op->rhs, depth + 1);
       break;
     default:
       fputs("?\n", stderr);
@@ -48,9 +48,9 @@ static void print_op(Operation *op, int depth) {
 
 void PrintPipeline(Pipeline *pipeline) {
   for (Pipeline *c : pipeline->children) PrintPipeline(c);
-  fprintf(stderr, "Pipeline %s (%zu inputs, %zu outputs)\n", pipeline->name, pipeline->inputData->objects.size(),
-          pipeline->outputData->objects.size());
-  print_op(pipeline->operation, 1);
+  fprintf(stderr, "Pipeline %s (%zu inputs, %zu outputs)\n", pipeline->name, pipeline->inputs.size(),
+          pipeline->outputs.size());
+  print_op(pipeline->root, 1);
 }
 
 void PrintPlan(Pipeline *pipeline, const nl_plan *plan) {
@@ -65,13 +65,13 @@ void PrintThunk(PyThunkObject *thunk) {
   if (thunk->evaluated || !thunk->operation) { fprintf(stderr, "%s", thunk->name ? thunk->name : "?"); return; }
   ThunkOperation *op = thunk->operation;
   fputc('(', stderr);
-  if (op->gencode.type == gentype_binary) {
-    PrintThunk((PyThunkObject *)op->gencode.parameter[0]);
-    fprintf(stderr, " %s ", op->opname);
-    PrintThunk((PyThunkObject *)op->gencode.parameter[1]);
+  if (op->arity == 2) {
+    PrintThunk((PyThunkObject *)op->operand[0]);
+    fprintf(stderr, " %s ", op->name.c_str());
+    PrintThunk((PyThunkObject *)op->operand[1]);
   } else {
-    fprintf(stderr, "%s ", op->opname);
-    PrintThunk((PyThunkObject *)op->gencode.parameter[0]);
+    fprintf(stderr, "%s ", op->name.c_str());
+    PrintThunk((PyThunkObject *)op->operand[0]);
   }
   fputc(')', stderr);
 }

@@ -49,16 +49,16 @@ static void describe(Pipeline *p, std::string &out) {
   for (Pipeline *c : p->children) describe(c, out);
   out += "pipeline ";
   out += p->name;
-  ThunkOperation *root = GetThunkOperation(p->operation);
-  if (root && root->gencode.opcode < 0) {
+  ThunkOperation *root = (p->root)->op;
+  if (root && root->opcode < 0) {
     out += ": base function ";
-    out += root->opname;
+    out += root->name.c_str();
     out += "\n";
     return;
   }
   bool ready = true;
-  for (DataElement &e : p->inputData->objects)
-    if (e.operation->Type() == OPTYPE_pipeline) ready = false;
+  for (Binding &e : p->inputs)
+    if (e.operation->kind == Operation::ChildResult) ready = false;
   if (!ready) { out += ": fused kernel over the results of its child pipelines\n"; return; }
   LoweredPipeline lp;
   PyThunkObject *cut = NULL;

@@ -46,14 +46,14 @@ struct Lowering {
 };
 
 static DataSource *find_input(Pipeline *p, Operation *op) {
-  for (DataElement &e : p->inputData->objects)
+  for (Binding &e : p->inputs)
     if (e.operation == op) return e.source;
   return NULL;
 }
 
 static int find_output(Pipeline *p, Operation *op) {
   int k = 0;
-  for (DataElement &e : p->outputData->objects) {
+  for (Binding &e : p->outputs) {
     if (e.operation == op) return k;
     k++;
   }
@@ -64,7 +64,7 @@ static int lower_op(Lowering &lw, Operation *op) {
   LoweredPipeline *o = lw.out;
   if (lw.failed || lw.too_big) return 0;
   nl_expr_node nd = {NL_OP_INPUT, -1, -1, -1, -1};
-  if (op->Type() == OPTYPE_obj || op->Type() == OPTYPE_pipeline) {
+  if (op->kind == Operation::Column || op->kind == Operation::ChildResult) {
     DataSource *src = find_input(lw.pipeline, op);
     if (!src) {
       PyErr_SetString(PyExc_ValueError, "Column/Pipeline operation found, but not found in inputData.");   // compiler.cpp:225
@@ -82,18 +82,18 @@ static int lower_op(Lowering &lw, Operation *op) {
     }
     nd.input = k;
   } else {
-    ThunkOperation *top = GetThunkOperation(op);
-    if (!top || top->gencode.opcode < 0) {
+    ThunkOperation *top = (op)->op;
+    if (!top || top->opcode < 0) {
       PyErr_SetString(PyExc_ValueError, "operation has no kernel op-code and is not a pipeline root");
       lw.failed = true;
       return 0;
     }
-    nd.op = top->gencode.opcode;
-    if (op->Type() == OPTYPE_unop) {
-      nd.lhs = lower_op(lw, ((UnaryOperation *)op)->LHS);
+    nd.op = top->opcode;
+    if (op->kind == Operation::Apply1) {
+      nd.lhs = lower_op(lw, op->lhs);
     } else {
-      nd.lhs = lower_op(lw, ((BinaryOperation *)op)->LHS);
-      nd.rhs = lower_op(lw, ((BinaryOperation *)op)->RHS);
+      nd.lhs = lower_op(lw, op->lhs);
+      nd.rhs = lower_op(lw, op->rhs);
     }
   }
   if (op->materialize) nd.output = find_output(lw.pipeline, op);
@@ -104,9 +104,9 @@ static int lower_op(Lowering &lw, Operation *op) {
 }
 
 static int subtree_size(Operation *op) {
-  switch (op->Type()) {
-    case OPTYPE_unop: return 1 + subtree_size(((UnaryOperation *)op)->LHS);
-    case OPTYPE_binop: return 1 + subtree_size(((BinaryOperation *)op)->LHS) + subtree_size(((BinaryOperation *)op)->RHS);
+  switch (op->kind) {
+    case Operation::Apply1: return 1 + subtree_size(op->lhs);
+    case Operation::Apply2: return 1 + subtree_size(op->lhs) + subtree_size(op->rhs);
     default: return 1;
   }
 }
@@ -114,25 +114,25 @@ static int subtree_size(Operation *op) {
 // the interior node whose subtree is closest to half of the expression: cutting there keeps
 // both halves as fused as possible
 static void pick_cut(Operation *op, Operation *root, int total, Operation **best, int *best_dist) {
-  if (op->Type() != OPTYPE_unop && op->Type() != OPTYPE_binop) return;
+  if (op->kind != Operation::Apply1 && op->kind != Operation::Apply2) return;
   if (op != root) {
     int d = subtree_size(op) * 2 - total;
     if (d < 0) d = -d;
     if (!*best || d < *best_dist) { *best = op; *best_dist = d; }
   }
-  if (op->Type() == OPTYPE_unop) pick_cut(((UnaryOperation *)op)->LHS, root, total, best, best_dist);
+  if (op->kind == Operation::Apply1) pick_cut(op->lhs, root, total, best, best_dist);
   else {
-    pick_cut(((BinaryOperation *)op)->LHS, root, total, best, best_dist);
-    pick_cut(((BinaryOperation *)op)->RHS, root, total, best, best_dist);
+    pick_cut(op->lhs, root, total, best, best_dist);
+    pick_cut(op->rhs, root, total, best, best_dist);
   }
 }
 
 int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, PyThunkObject **cut_out) {
   memset(out, 0, sizeof(*out));
   Lowering lw = {pipeline, out, false, false};
-  lower_op(lw, pipeline->operation);
+  lower_op(lw, pipeline->root);
   if (lw.failed) return -1;
-  out->n_outputs = (int)pipeline->outputData->objects.size();
+  out->n_outputs = (int)pipeline->outputs.size();
   if (out->n_outputs > NL_MAX_OUTPUTS) lw.too_big = true;
 
   int rc = NL_ERR_SPLIT;
@@ -181,7 +181,7 @@ int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, PyThunkObject **cut_
   // too large for one fused kernel: propose a cut
   Operation *best = NULL;
   int dist = 0;
-  pick_cut(pipeline->operation, pipeline->operation, subtree_size(pipeline->operation), &best, &dist);
+  pick_cut(pipeline->root, pipeline->root, subtree_size(pipeline->root), &best, &dist);
   if (!best || !best->thunk) {
     nljit_raise(rc, "jit: pipeline cannot be split further");
     return -1;

@@ -1,32 +1,40 @@
-// parser.cpp — splits the thunk DAG into pipelines at the blocking operations; everything
-// inside one pipeline is fused into a single kernel (reference: parser.cpp:6-198).  The rules
-// are the reference's:
-//   * an evaluated thunk is an input leaf (parser.cpp:84-90);
-//   * an operation is a breaker if it is a full breaker or ANY parameter's operation is a full
-//     or parallel breaker; then every unevaluated parameter becomes a child pipeline whose
-//     output is this pipeline's input (parser.cpp:116-145);
-//   * cardinality comes from the per-operation function (parser.cpp:149-151);
-//   * an operation is materialised if its thunk is referenced from outside this computation
-//     (`ob_refcnt > 1`, parser.cpp:66) or it is a pipeline root (parser.cpp:154-170).
+// parser.cpp — cuts the thunk DAG into pipelines at the blocking operations; everything inside
+// one pipeline is fused into a single kernel.  The RULES are the reference's (parser.cpp:81-173):
+//   * an evaluated thunk is an input column;
+//   * an operation "breaks" if it is a full breaker or if ANY operand is computed by a full or
+//     parallel breaker; every unevaluated operand of a breaking operation becomes a child
+//     pipeline whose output is this pipeline's input (so `sort(a*b*c) * (d*e*f)` is three
+//     pipelines, parser.cpp:99-115);
+//   * a thunk's cardinality comes from its operation's cardinality function;
+//   * a node is materialised when its thunk is referenced outside this computation
+//     (`ob_refcnt > 1`, parser.cpp:66) or it is a pipeline root.
+// The data structures are this engine's own (parser.hpp).
 #include "parser.hpp"
 #include "debug_printer.hpp"
 
 #include <cassert>
 #include <cstdlib>
 
-static Pipeline *CreatePipeline() {
-  Pipeline *pipeline = new Pipeline();
-  pipeline->operation = NULL;
-  pipeline->parent = NULL;
-  pipeline->inputData = new DataBlock();
-  pipeline->outputData = new DataBlock();
-  pipeline->name = getname("Pipe");
-  pipeline->evaluated = false;
-  pipeline->inplace_target = NULL;
-  return pipeline;
+namespace {
+
+struct Parse {
+  const std::set<PyThunkObject *> *cuts;   // extra breakers requested by the plan optimiser
+  bool failed = false;
+};
+
+Pipeline *new_pipeline() {
+  Pipeline *p = new Pipeline();
+  p->root = NULL;
+  p->parent = NULL;
+  p->evaluated = false;
+  p->inplace_target = NULL;
+  char *n = getname("Pipe");
+  p->name = n;
+  free(n);
+  return p;
 }
 
-static void source_decref(DataSource *s) {
+void release(DataSource *s) {
   if (s && --s->refs == 0) {
     Py_XDECREF((PyObject *)s->object);
     storage_decref(s->storage);
@@ -34,141 +42,103 @@ static void source_decref(DataSource *s) {
   }
 }
 
-void DestroyPipeline(Pipeline *pipeline) {
-  if (!pipeline) return;
-  for (Pipeline *c : pipeline->children) DestroyPipeline(c);
-  delete pipeline->operation;
-  for (DataElement &e : pipeline->inputData->objects) source_decref(e.source);
-  for (DataElement &e : pipeline->outputData->objects) source_decref(e.source);
-  delete pipeline->inputData;
-  delete pipeline->outputData;
-  free(pipeline->name);
-  delete pipeline;
-}
-
-static void AddChild(Pipeline *parent, Pipeline *child) {
-  assert(!child->parent);
-  child->parent = parent;
-  parent->children.push_back(child);
-}
-
-struct ParseState {
-  const std::set<PyThunkObject *> *cuts;
-  bool failed;
-};
-
-static DataSource *source_for_thunk(PyThunkObject *thunk) {
+DataSource *column_of(PyThunkObject *thunk) {
   Py_INCREF(thunk);
   if (thunk->storage) storage_incref(thunk->storage);
-  return new DataSource(thunk, thunk->storage, thunk->cardinality, thunk->type);
+  return new DataSource(thunk, thunk->storage, thunk->card.n, thunk->npy_type);
 }
 
-static Operation *OperationFromArgs(PyThunkObject *thunk, ThunkOperation *operation, Operation **operations, int op_count,
-                                    std::set<PyThunkObject *> &stored) {
-  PyThunkObject *result_object = NULL;
-  if (Py_REFCNT(thunk) > 1 && !stored.count(thunk)) {
-    /* the thunk is not only used in this calculation but elsewhere too, so we store the result */
-    result_object = thunk;
-  }
-  switch (op_count) {
-    case 1: return new UnaryOperation(result_object, thunk, operation, operations[0]);
-    case 2: return new BinaryOperation(result_object, thunk, operation, operations[0], operations[1]);
-  }
-  return NULL;
+bool computed_by_breaker(PyObject *operand) {
+  if (!PyThunk_Check(operand)) return false;
+  ThunkOperation *op = ((PyThunkObject *)operand)->operation;
+  return op != NULL && op->is_breaker();
 }
 
-static Operation *ParseOperationRecursive(PyThunkObject *thunk, Pipeline *current, DataSource *output_source,
-                                          std::set<PyThunkObject *> &stored, ParseState &ps) {
+// `sink`: when non-NULL the node is a pipeline root and its result goes to this column
+Operation *parse_node(PyThunkObject *thunk, Pipeline *current, DataSource *sink,
+                      std::set<PyThunkObject *> &stored, Parse &ps) {
   if (thunk->evaluated) {
-    // already evaluated: an endpoint
-    Operation *op = new ObjectOperation(thunk);
-    current->inputData->objects.push_back(DataElement(op, source_for_thunk(thunk)));
-    return op;
+    Operation *leaf = new Operation(Operation::Column, thunk);
+    current->inputs.push_back(Binding{leaf, column_of(thunk)});
+    return leaf;
   }
-  // not evaluated: there must be an operation that says how to compute it
-  ThunkOperation *toperation = thunk->operation;
-  if (!toperation || (int)toperation->gencode.type > 2 || (int)toperation->gencode.type < 1) {
+  ThunkOperation *top = thunk->operation;
+  if (!top || top->arity < 1 || top->arity > 2) {
     PyErr_SetString(PyExc_ValueError, "thunk has neither data nor an operation");
     ps.failed = true;
-    return new ObjectOperation(thunk);
+    return new Operation(Operation::Column, thunk);
   }
-  const int arity = (int)toperation->gencode.type;
-  Operation *operations[OPTYPE_MAX_OPERATIONS] = {NULL, NULL, NULL};
-  ssize_t child_cardinalities[OPTYPE_MAX_OPERATIONS] = {0, 0, 0};
 
-  // if any of the children is a pipeline breaker, each child becomes a separate pipeline
-  // (parser.cpp:99-129: sort(a*b*c) * (d*e*f) makes three pipelines)
-  bool breaker = toperation->type == optype_fullbreaker;
-  for (int i = 0; i < arity && !breaker; i++) {
-    PyObject *param = toperation->gencode.parameter[i];
-    if (PyThunk_Check(param) && ((PyThunkObject *)param)->operation != NULL &&
-        (((PyThunkObject *)param)->operation->type == optype_fullbreaker ||
-         ((PyThunkObject *)param)->operation->type == optype_parallelbreaker)) {
-      breaker = true;
-    }
-  }
-  for (int i = 0; i < arity; i++) {
-    PyThunkObject *thunk_child = (PyThunkObject *)toperation->gencode.parameter[i];
-    const bool cut = ps.cuts && ps.cuts->count(thunk_child);
-    if ((breaker || cut) && !thunk_child->evaluated) {
-      Pipeline *child = CreatePipeline();
-      DataSource *source = new DataSource(NULL, NULL, 0, 0);
+  bool breaks = top->klass == OpClass::FullBreaker;
+  for (int i = 0; i < top->arity && !breaks; i++) breaks = computed_by_breaker(top->operand[i]);
+
+  Operation *node = new Operation(top->arity == 1 ? Operation::Apply1 : Operation::Apply2, thunk);
+  node->op = top;
+  ssize_t sizes[2] = {0, 0};
+  for (int i = 0; i < top->arity; i++) {
+    PyThunkObject *operand = (PyThunkObject *)top->operand[i];
+    Operation *sub;
+    const bool cut = ps.cuts && ps.cuts->count(operand);
+    if ((breaks || cut) && !operand->evaluated) {
+      // the operand gets a pipeline of its own; here it is read back as a column
+      Pipeline *child = new_pipeline();
+      DataSource *col = new DataSource(NULL, NULL, 0, 0);
       std::set<PyThunkObject *> child_stored;
-      // we materialise after a breaking operation
-      child->operation = ParseOperationRecursive(thunk_child, child, source, child_stored, ps);
-      // placeholder that receives the child pipeline's result as input
-      operations[i] = new PipelineOperation(child, thunk_child);
-      source->refs++;
-      current->inputData->objects.push_back(DataElement(operations[i], source));
-      source_decref(source);   // the parse-time reference; output list + input list hold theirs
-      AddChild(current, child);
+      child->root = parse_node(operand, child, col, child_stored, ps);
+      child->parent = current;
+      current->children.push_back(child);
+      sub = new Operation(Operation::ChildResult, operand);
+      sub->child = child;
+      col->refs++;
+      current->inputs.push_back(Binding{sub, col});
+      release(col);              // drop the construction reference; both lists hold their own
     } else {
-      operations[i] = ParseOperationRecursive(thunk_child, current, NULL, stored, ps);
+      sub = parse_node(operand, current, NULL, stored, ps);
     }
-    child_cardinalities[i] = thunk_child->cardinality;
+    (i == 0 ? node->lhs : node->rhs) = sub;
+    sizes[i] = operand->card.n;
   }
-  thunk->cardinality = thunk->cardinality_func(child_cardinalities);
-  if (thunk->cardinality < 0 && !ps.failed) {
+  thunk->card.n = thunk->card.fn(sizes);
+  if (thunk->card.n < 0 && !ps.failed) {
     PyErr_SetString(PyExc_TypeError, "Incompatible cardinality.");
     ps.failed = true;
   }
 
-  Operation *op = OperationFromArgs(thunk, toperation, operations, arity, stored);
-  if (op->result_object || output_source) {
-    op->materialize = true;
+  // somebody besides this computation holds the thunk: keep its value
+  if (Py_REFCNT(thunk) > 1 && !stored.count(thunk)) node->result_object = thunk;
+  if (node->result_object || sink) {
+    node->materialize = true;
     stored.insert(thunk);
-    if (output_source) {
-      output_source->object = thunk;
-      output_source->storage = NULL;
-      output_source->size = thunk->cardinality;
-      output_source->type = thunk->type;
-      output_source->refs++;
-      Py_INCREF(thunk);
-    } else {
-      output_source = new DataSource(thunk, NULL, thunk->cardinality, thunk->type);
-      Py_INCREF(thunk);
-    }
-    current->outputData->objects.push_back(DataElement(op, output_source));
+    DataSource *out = sink ? sink : new DataSource(NULL, NULL, 0, 0);
+    out->object = thunk;
+    out->size = thunk->card.n;
+    out->type = thunk->npy_type;
+    Py_INCREF(thunk);
+    if (sink) out->refs++;
+    current->outputs.push_back(Binding{node, out});
   }
-  return op;
+  return node;
 }
 
-ThunkOperation *GetThunkOperation(Operation *op) {
-  switch (op->Type()) {
-    case OPTYPE_unop: return ((UnaryOperation *)op)->operation;
-    case OPTYPE_binop: return ((BinaryOperation *)op)->operation;
-    default: return NULL;
-  }
+}  // namespace
+
+void DestroyPipeline(Pipeline *pipeline) {
+  if (!pipeline) return;
+  for (Pipeline *c : pipeline->children) DestroyPipeline(c);
+  delete pipeline->root;
+  for (Binding &b : pipeline->inputs) release(b.source);
+  for (Binding &b : pipeline->outputs) release(b.source);
+  delete pipeline;
 }
 
 Pipeline *ParsePipeline(PyThunkObject *thunk, const std::set<PyThunkObject *> *cuts) {
-  Pipeline *pipeline = CreatePipeline();
-  ParseState ps = {cuts, false};
+  Pipeline *pipeline = new_pipeline();
+  Parse ps;
+  ps.cuts = cuts;
   std::set<PyThunkObject *> stored;
-  // the root is always materialised (parser.cpp:154: a pipeline root has an output source)
-  DataSource *root = new DataSource(NULL, NULL, 0, 0);
-  pipeline->operation = ParseOperationRecursive(thunk, pipeline, root, stored, ps);
-  source_decref(root);
+  DataSource *result = new DataSource(NULL, NULL, 0, 0);    // the root is always materialised
+  pipeline->root = parse_node(thunk, pipeline, result, stored, ps);
+  release(result);
   if (ps.failed) {
     DestroyPipeline(pipeline);
     return NULL;

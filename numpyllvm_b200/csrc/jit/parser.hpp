@@ -1,78 +1,48 @@
-// parser.hpp — DAG of thunks -> tree of fused pipelines (reference: parser.hpp:14-141).
+// parser.hpp — the thunk DAG cut into a tree of fused pipelines.
+//
+// Same job as the reference's parser (parser.hpp:14-141): an operation tree per pipeline with
+// its input and output columns.  The reference models nodes as a class hierarchy
+// (Object/Pipeline/Nullary/Unary/BinaryOperation) and columns as DataBlock/DataElement; here a
+// node is one tagged struct and a pipeline simply owns two binding lists.
 #ifndef NLJIT_PARSER_H
 #define NLJIT_PARSER_H
 
-#include "gencode.hpp"
 #include "thunk.hpp"
 #include <set>
+#include <string>
 #include <vector>
 
-class Pipeline;
+struct Pipeline;
 
-enum operation_type {
-  OPTYPE_nullop = 0,
-  OPTYPE_unop = 1,
-  OPTYPE_binop = 2,
-  OPTYPE_pipeline = 100,
-  OPTYPE_obj = 101,
-  OPTYPE_unknown = 255
+// one node of a pipeline's operation tree
+struct Operation {
+  enum Kind {
+    Column,        // an evaluated thunk read as an input column
+    ChildResult,   // the output of a child pipeline read as an input column
+    Apply1,        // unary operator
+    Apply2         // binary operator
+  };
+  Kind kind;
+  PyThunkObject *thunk;          // the thunk this node computes / reads
+  PyThunkObject *result_object;  // non-NULL: the value is also wanted outside this computation
+  bool materialize;              // the node's value is stored to an output column
+  ThunkOperation *op;            // Apply1/Apply2: the operator record
+  Operation *lhs, *rhs;          // owned
+  Pipeline *child;               // ChildResult: the pipeline that produces it
+
+  Operation(Kind k, PyThunkObject *t)
+      : kind(k), thunk(t), result_object(NULL), materialize(false), op(NULL), lhs(NULL), rhs(NULL), child(NULL) {}
+  ~Operation() {
+    delete lhs;
+    delete rhs;
+  }
+  bool is_leaf() const { return kind == Column || kind == ChildResult; }
 };
 
-#define OPTYPE_MAX_OPERATIONS 3
-
-class Operation {
-public:
-  /* Where the result of this operation is stored; NULL for an unnecessary intermediate
-   * (parser.hpp:27-36).  `thunk` is the node the operation computes, materialised or not. */
-  PyThunkObject *result_object;
-  PyThunkObject *thunk;
-  bool materialize;
-  Operation(PyThunkObject *result, PyThunkObject *thunk) : result_object(result), thunk(thunk), materialize(false) {}
-  virtual ~Operation() {}
-  virtual operation_type Type() { return OPTYPE_unknown; }
-};
-
-/* input data from an evaluated thunk */
-class ObjectOperation : public Operation {
-public:
-  ObjectOperation(PyThunkObject *thunk) : Operation(NULL, thunk) {}
-  virtual operation_type Type() { return OPTYPE_obj; }
-};
-
-/* input data that is the result of a child pipeline */
-class PipelineOperation : public Operation {
-public:
-  Pipeline *pipeline;
-  PipelineOperation(Pipeline *pipeline, PyThunkObject *thunk) : Operation(NULL, thunk), pipeline(pipeline) {}
-  virtual operation_type Type() { return OPTYPE_pipeline; }
-};
-
-class UnaryOperation : public Operation {
-public:
-  ThunkOperation *operation;
-  Operation *LHS;
-  UnaryOperation(PyThunkObject *result_object, PyThunkObject *thunk, ThunkOperation *operation, Operation *LHS)
-      : Operation(result_object, thunk), operation(operation), LHS(LHS) {}
-  virtual ~UnaryOperation() { delete LHS; }
-  virtual operation_type Type() { return OPTYPE_unop; }
-};
-
-class BinaryOperation : public Operation {
-public:
-  ThunkOperation *operation;
-  Operation *LHS, *RHS;
-  BinaryOperation(PyThunkObject *result_object, PyThunkObject *thunk, ThunkOperation *operation, Operation *LHS, Operation *RHS)
-      : Operation(result_object, thunk), operation(operation), LHS(LHS), RHS(RHS) {}
-  virtual ~BinaryOperation() { delete LHS; delete RHS; }
-  virtual operation_type Type() { return OPTYPE_binop; }
-};
-
-ThunkOperation *GetThunkOperation(Operation *op);
-
-/* A column a pipeline reads or writes (parser.hpp:94-103): the owning thunk, its storage once
- * it exists, its size (the upper bound for filter results) and dtype. */
-class DataSource {
-public:
+// a column a pipeline reads or writes: the owning thunk, its storage once it exists, its size
+// (the upper bound for filter results) and NumPy type.  Shared between a child's output list
+// and its parent's input list.
+struct DataSource {
   PyThunkObject *object;
   Storage *storage;
   ssize_t size;
@@ -82,28 +52,20 @@ public:
       : object(object), storage(storage), size(size), type(type), refs(1) {}
 };
 
-class DataElement {
-public:
+struct Binding {
   Operation *operation;
   DataSource *source;
-  DataElement(Operation *op, DataSource *source) : operation(op), source(source) {}
 };
 
-class DataBlock {
-public:
-  std::vector<DataElement> objects;
-};
-
-class Pipeline {
-public:
-  Operation *operation;
+struct Pipeline {
+  Operation *root;
   Pipeline *parent;
   std::vector<Pipeline *> children;
-  DataBlock *inputData;
-  DataBlock *outputData;
-  char *name;
+  std::vector<Binding> inputs;    // columns read (evaluated thunks and child results)
+  std::vector<Binding> outputs;   // columns written (materialised nodes)
+  std::string name;
   bool evaluated;
-  PyThunkObject *inplace_target;   /* masked assignment: the root's output aliases this thunk's storage */
+  PyThunkObject *inplace_target;  // masked assignment: the root's output aliases this thunk's storage
 };
 
 /* `cuts`: thunks the plan optimiser wants materialised by their own pipeline (an expression too

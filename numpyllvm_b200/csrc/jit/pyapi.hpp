@@ -1,7 +1,7 @@
-// config.hpp — common includes of the `jit` extension (reference: config.hpp:1-12, ported to
-// CPython 3.12 and the NumPy 2 C-API).
-#ifndef NLJIT_CONFIG_H
-#define NLJIT_CONFIG_H
+// pyapi.hpp — the CPython 3.12 / NumPy 2 C-API as every translation unit of the `jit` extension
+// sees it (one PY_ARRAY_UNIQUE_SYMBOL, imported in jitpackage.cpp), plus the engine's C ABI.
+#ifndef NLJIT_PYAPI_H
+#define NLJIT_PYAPI_H
 
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>

@@ -41,20 +41,20 @@ static int sync_devices() {
 // the full pipeline breaker: materialise the child, run the NumPy base function on the host,
 // upload the result (compiler.cpp:93-122)
 static int run_base_function(Pipeline *pipeline) {
-  ThunkOperation *top = GetThunkOperation(pipeline->operation);
-  if (!top || !top->gencode.base) {
+  ThunkOperation *top = (pipeline->root)->op;
+  if (!top || !top->base) {
     PyErr_SetString(PyExc_ValueError, "pipeline root has neither a kernel op-code nor a base function");
     return -1;
   }
-  if (pipeline->inputData->objects.size() != 1) {
+  if (pipeline->inputs.size() != 1) {
     PyErr_SetString(PyExc_ValueError, "Expected 1 parameter for a base function.");
     return -1;
   }
-  DataSource *in = pipeline->inputData->objects[0].source;
+  DataSource *in = pipeline->inputs[0].source;
   if (!in->storage) { PyErr_SetString(PyExc_ValueError, "base function input is not evaluated"); return -1; }
   PyObject *host = storage_to_host(in->storage);
   if (!host) return -1;
-  PyObject *result = top->gencode.base(host);
+  PyObject *result = top->base(host);
   Py_DECREF(host);
   if (!result) return -1;
   PyObject *t = PyThunk_FromArray(NULL, result);     // uploads
@@ -62,7 +62,7 @@ static int run_base_function(Pipeline *pipeline) {
   if (!t) return -1;
   PyThunkObject *tt = (PyThunkObject *)t;
   if (PyThunk_EnsureDevice(tt) < 0) { Py_DECREF(t); return -1; }
-  DataElement &out = pipeline->outputData->objects[0];
+  Binding &out = pipeline->outputs[0];
   storage_incref(tt->storage);
   out.source->storage = tt->storage;
   storage_incref(tt->storage);
@@ -74,11 +74,11 @@ static int run_base_function(Pipeline *pipeline) {
 
 static int execute_one(Pipeline *pipeline) {
   if (nljit_ensure_runtime() < 0) return -1;
-  ThunkOperation *root_op = GetThunkOperation(pipeline->operation);
-  if (root_op && root_op->gencode.opcode < 0) return run_base_function(pipeline);
+  ThunkOperation *root_op = (pipeline->root)->op;
+  if (root_op && root_op->opcode < 0) return run_base_function(pipeline);
 
   // inputs must be resident (deferred upload of host-only thunks)
-  for (DataElement &e : pipeline->inputData->objects) {
+  for (Binding &e : pipeline->inputs) {
     DataSource *src = e.source;
     if (!src->storage && src->object) {
       if (PyThunk_EnsureDevice(src->object) < 0) return -1;
@@ -91,7 +91,7 @@ static int execute_one(Pipeline *pipeline) {
 
   // a one-element column that is neither a host scalar nor replicated (e.g. a filter that kept one
   // element) is broadcast like any size-1 input (compiler.cpp:210): fetch it and bake it
-  for (DataElement &e : pipeline->inputData->objects) {
+  for (Binding &e : pipeline->inputs) {
     Storage *s = e.source->storage;
     if (e.source->size == 1 && !s->host_scalar && !s->replicated) {
       PyObject *host = storage_to_host(s);
@@ -222,7 +222,7 @@ static int execute_one(Pipeline *pipeline) {
 
   // mark the output thunks evaluated (compiler.cpp:51) and publish the storage to parents
   int k = 0;
-  for (DataElement &e : pipeline->outputData->objects) {
+  for (Binding &e : pipeline->outputs) {
     if (lp.plan.out[k].index_space != NL_IDX_WHERE) {
       storage_incref(outs[k]);
       e.source->storage = outs[k];

@@ -5,7 +5,7 @@
 #ifndef NLJIT_STORAGE_H
 #define NLJIT_STORAGE_H
 
-#include "config.hpp"
+#include "pyapi.hpp"
 #include <vector>
 
 struct Shard {

@@ -15,9 +15,9 @@
 #include <cstring>
 #include <string>
 
-ssize_t default_cardinality_function(ssize_t *inputs) { return inputs[0]; }
+ssize_t cardinality_same_as_operand(ssize_t *inputs) { return inputs[0]; }
 
-ssize_t default_binary_cardinality_function(ssize_t *inputs) {
+ssize_t cardinality_broadcast(ssize_t *inputs) {
   // if one input is a constant the other size is used (thunk.cpp:14-23)
   if (inputs[0] == 1) return inputs[1];
   if (inputs[1] == 1) return inputs[0];
@@ -32,12 +32,12 @@ static PyThunkObject *thunk_alloc() {
   thunk->host = NULL;
   thunk->evaluated = false;
   thunk->operation = NULL;
-  thunk->cardinality = -1;
-  thunk->cardinality_type = cardinality_unknown;
-  thunk->cardinality_func = NULL;
-  thunk->type = NPY_NOTYPE;
+  thunk->card.n = -1;
+  thunk->card.kind = CardinalityKind::Unknown;
+  thunk->card.fn = NULL;
+  thunk->npy_type = NPY_NOTYPE;
   thunk->name = NULL;
-  thunk->children = new std::vector<PyThunkObject *>();
+  thunk->dependents = new std::vector<PyThunkObject *>();
   return thunk;
 }
 
@@ -61,11 +61,11 @@ PyObject *PyThunk_FromArray(PyObject *unused, PyObject *input) {
   PyThunkObject *thunk = thunk_alloc();
   if (!thunk) { Py_DECREF(arr); return NULL; }
   thunk->evaluated = true;
-  thunk->cardinality = (ssize_t)PyArray_SIZE(a);
-  thunk->cardinality_type = cardinality_exact;
-  thunk->type = PyArray_TYPE(a);
+  thunk->card.n = (ssize_t)PyArray_SIZE(a);
+  thunk->card.kind = CardinalityKind::Exact;
+  thunk->npy_type = PyArray_TYPE(a);
   thunk->name = getname("A");
-  if (thunk->cardinality == 1) {
+  if (thunk->card.n == 1) {
     // scalars become size-1 thunks (thunk_as_number.cpp:52-59) and never need the device
     Storage *s = storage_new(nl_type, 1);
     s->host_scalar = true;
@@ -102,20 +102,20 @@ PyObject *PyThunk_Coerce(PyObject *obj) {
   return t;
 }
 
-PyObject *PyThunk_FromOperation(ThunkOperation *operation, cardinality_function cardinality_func,
-                                cardinality_type_t cardinality_tpe, int type) {
+PyObject *PyThunk_FromOperation(ThunkOperation *operation, CardinalityFn cardinality_func,
+                                CardinalityKind cardinality_tpe, int type) {
   PyThunkObject *thunk = thunk_alloc();
   if (!thunk) return NULL;
   thunk->operation = operation;
-  thunk->cardinality_type = cardinality_tpe;
-  thunk->cardinality_func = cardinality_func;
-  thunk->type = type;
+  thunk->card.kind = cardinality_tpe;
+  thunk->card.fn = cardinality_func;
+  thunk->npy_type = type;
   thunk->name = getname("operation");
   // register as a dependent of each parameter (thunk.cpp:65-70): assignment to a parameter
   // must evaluate us first
-  for (int i = 0; i < (int)operation->gencode.type; i++) {
-    PyObject *parameter = operation->gencode.parameter[i];
-    if (PyThunk_Check(parameter)) ((PyThunkObject *)parameter)->children->push_back(thunk);
+  for (int i = 0; i < (int)operation->arity; i++) {
+    PyObject *parameter = operation->operand[i];
+    if (PyThunk_Check(parameter)) ((PyThunkObject *)parameter)->dependents->push_back(thunk);
   }
   return (PyObject *)thunk;
 }
@@ -123,20 +123,20 @@ PyObject *PyThunk_FromOperation(ThunkOperation *operation, cardinality_function 
 static void release_operation(PyThunkObject *thunk) {
   ThunkOperation *op = thunk->operation;
   if (!op) return;
-  for (int i = 0; i < (int)op->gencode.type; i++) {
-    PyObject *parameter = op->gencode.parameter[i];
+  for (int i = 0; i < (int)op->arity; i++) {
+    PyObject *parameter = op->operand[i];
     if (parameter && PyThunk_Check(parameter)) {
-      std::vector<PyThunkObject *> *ch = ((PyThunkObject *)parameter)->children;
+      std::vector<PyThunkObject *> *ch = ((PyThunkObject *)parameter)->dependents;
       ch->erase(std::remove(ch->begin(), ch->end(), thunk), ch->end());
     }
   }
   thunk->operation = NULL;
-  ThunkOperation_Destroy(op);
+  DestroyOperation(op);
 }
 
 void PyThunk_EvaluateChildren(PyThunkObject *thunk) {
   // evaluating a child unregisters it, so walk a snapshot (thunk.cpp:81-88)
-  std::vector<PyThunkObject *> snapshot(*thunk->children);
+  std::vector<PyThunkObject *> snapshot(*thunk->dependents);
   for (PyThunkObject *c : snapshot) Py_INCREF(c);
   for (PyThunkObject *c : snapshot) {
     if (!PyErr_Occurred()) PyThunk_Evaluate(c);
@@ -161,8 +161,8 @@ void PyThunk_MarkEvaluated(PyThunkObject *thunk, Storage *storage) {
   if (thunk->storage) storage_decref(thunk->storage);
   thunk->storage = storage;
   thunk->evaluated = true;
-  thunk->cardinality = (ssize_t)storage->cardinality();
-  thunk->cardinality_type = cardinality_exact;
+  thunk->card.n = (ssize_t)storage->cardinality();
+  thunk->card.kind = CardinalityKind::Exact;
   Py_CLEAR(thunk->host);
   release_operation(thunk);
 }
@@ -204,8 +204,8 @@ static void PyThunk_dealloc(PyThunkObject *self) {
   release_operation(self);
   // anything still registered as our dependent holds a reference to us through its operation,
   // so the list is empty here; clear defensively
-  delete self->children;
-  self->children = NULL;
+  delete self->dependents;
+  self->dependents = NULL;
   storage_decref(self->storage);
   Py_XDECREF(self->host);
   free(self->name);

@@ -1,4 +1,9 @@
-// thunk.hpp — the lazy array object (reference: thunk.hpp:23-66).
+// thunk.hpp — the lazy array object of module `jit`.
+//
+// Plays the part of the reference's PyThunkObject (thunk.hpp:23-43): an evaluated thunk owns
+// data, an unevaluated one owns the operation that will compute it.  The data is device-resident
+// shard storage (storage.hpp) with a host ndarray cached on demand; dependents are tracked so an
+// in-place assignment can force them first (thunk.cpp:81-88).
 #ifndef NLJIT_THUNK_H
 #define NLJIT_THUNK_H
 
@@ -6,51 +11,47 @@
 #include "storage.hpp"
 #include <vector>
 
-typedef ssize_t (*cardinality_function)(ssize_t *inputs);
+typedef ssize_t (*CardinalityFn)(ssize_t *operand_sizes);
 
-ssize_t default_cardinality_function(ssize_t *inputs);
-ssize_t default_binary_cardinality_function(ssize_t *inputs);
+enum class CardinalityKind : int { Unknown, Exact, UpperBound };
 
-typedef enum {
-  cardinality_unknown = 255,
-  cardinality_exact = 1,
-  cardinality_upper_bound = 2
-} cardinality_type_t;
+// how many elements a thunk has / will have
+struct Cardinality {
+  ssize_t n;             // -1 until known
+  CardinalityKind kind;  // a filter only knows an upper bound before it runs
+  CardinalityFn fn;      // result size from the operand sizes (unevaluated thunks)
+};
+
+ssize_t cardinality_same_as_operand(ssize_t *sizes);
+ssize_t cardinality_broadcast(ssize_t *sizes);   // size-1 operands broadcast; -1 on mismatch
 
 struct PyThunkObject {
   PyObject_HEAD
-  Storage *storage;          /* device shards (or a host scalar); NULL until evaluated / uploaded */
-  PyObject *host;            /* host ndarray: the wrapped copy when no device is present, else a
-                                cache filled by asnumpyarray()/str() */
   bool evaluated;
-  ThunkOperation *operation; /* how to compute this thunk; released once evaluated */
-  ssize_t cardinality;
-  cardinality_type_t cardinality_type;
-  cardinality_function cardinality_func;
-  int type;                  /* NumPy type number */
+  int npy_type;                               // NumPy type number of the elements
+  Cardinality card;
+  ThunkOperation *operation;                  // how to compute this thunk; released once evaluated
+  Storage *storage;                           // device shards or a host scalar; NULL until evaluated / uploaded
+  PyObject *host;                             // host ndarray: the wrapped copy when no device exists,
+                                              // otherwise a cache filled by asnumpyarray() / str()
+  std::vector<PyThunkObject *> *dependents;   // thunks computed from this one (borrowed; each removes
+                                              // itself when it is evaluated or destroyed)
   char *name;
-  std::vector<PyThunkObject *> *children;  /* thunks computed from this one (borrowed; each child
-                                              removes itself on dealloc) */
 };
 
 extern PyTypeObject PyThunk_Type;
 
-#define PyThunk_CheckExact(op) (Py_TYPE(op) == &PyThunk_Type)
 #define PyThunk_Check(op) PyObject_TypeCheck((PyObject *)(op), &PyThunk_Type)
 
 PyObject *PyThunk_FromArray(PyObject *unused, PyObject *input);
-PyObject *PyThunk_FromOperation(ThunkOperation *operation, cardinality_function cardinality_func,
-                                cardinality_type_t cardinality_tpe, int type);
-/* coerce an operand (thunk, ndarray, Python scalar) to a thunk; new reference */
-PyObject *PyThunk_Coerce(PyObject *obj);
+PyObject *PyThunk_FromOperation(ThunkOperation *operation, CardinalityFn fn, CardinalityKind kind, int npy_type);
+PyObject *PyThunk_Coerce(PyObject *obj);           /* thunk, ndarray or Python scalar -> new reference to a thunk */
 
 int PyThunk_Init(void);
-void PyThunk_EvaluateChildren(PyThunkObject *thunk);
 PyObject *PyThunk_Evaluate(PyThunkObject *thunk);
 bool PyThunk_IsEvaluated(PyThunkObject *thunk);
 PyObject *PyThunk_AsArray(PyObject *thunk);        /* borrowed reference to the host ndarray */
-/* make sure an evaluated thunk's data is on the device (deferred upload); 0 / -1 */
-int PyThunk_EnsureDevice(PyThunkObject *thunk);
+int PyThunk_EnsureDevice(PyThunkObject *thunk);    /* deferred upload of a host-only thunk; 0 / -1 */
 void PyThunk_InvalidateHost(PyThunkObject *thunk);
 
 extern PyObject *PyThunk_LazyRichCompare(PyObject *self, PyObject *other, int cmp_op);

@@ -22,22 +22,22 @@ static PyObject *thunk_subscript(PyObject *self_o, PyObject *other) {
     return NULL;
   }
   PyThunkObject *other_thunk = (PyThunkObject *)other;
-  if (other_thunk->type == NPY_BOOL) {
-    if (self->type == NPY_BOOL) {
+  if (other_thunk->npy_type == NPY_BOOL) {
+    if (self->npy_type == NPY_BOOL) {
       PyErr_SetString(PyExc_IndexError, "filtering a boolean thunk is not supported");
       return NULL;
     }
-    if (self->cardinality > 1 && other_thunk->cardinality > 1 && self->cardinality_type == cardinality_exact &&
-        other_thunk->cardinality_type == cardinality_exact && self->cardinality != other_thunk->cardinality) {
+    if (self->card.n > 1 && other_thunk->card.n > 1 && self->card.kind == CardinalityKind::Exact &&
+        other_thunk->card.kind == CardinalityKind::Exact && self->card.n != other_thunk->card.n) {
       PyErr_SetString(PyExc_IndexError, "boolean index did not match the indexed thunk's cardinality");
       return NULL;
     }
     // boolean access: cardinality depends on the number of TRUE entries (upper bound)
-    ThunkOperation *op = ThunkOperation_FromBinary(self_o, other, optype_vectorizable, NL_OP_FILTER, "[]");
+    ThunkOperation *op = NewBinaryOperation(self_o, other, OpClass::Vectorizable, NL_OP_FILTER, "[]");
     if (!op) return PyErr_NoMemory();
-    return PyThunk_FromOperation(op, subscript_cardinality_function, cardinality_upper_bound, self->type);
+    return PyThunk_FromOperation(op, subscript_cardinality_function, CardinalityKind::UpperBound, self->npy_type);
   }
-  if (other_thunk->type == NPY_INT64 || other_thunk->type == NPY_INT32) {
+  if (other_thunk->npy_type == NPY_INT64 || other_thunk->npy_type == NPY_INT32) {
     // declared but never implemented in the reference (no emitter, thunk_as_mapping.cpp:51-55)
     PyErr_SetString(PyExc_IndexError, "integer-array indexing (gather) is not implemented");
     return NULL;
@@ -94,7 +94,7 @@ static int assign_run(PyThunkObject *self, int64_t lo, int64_t step, int64_t cou
   const size_t es = nl_dtype_size(nl_type);
   if (st->host_scalar) {
     uint64_t bits;
-    if (count != 1 || scalar_bits_of(value, self->type, &bits) < 0) {
+    if (count != 1 || scalar_bits_of(value, self->npy_type, &bits) < 0) {
       if (!PyErr_Occurred()) PyErr_SetString(PyExc_IndexError, "index out of range for a size-1 thunk");
       return -1;
     }
@@ -110,7 +110,7 @@ static int assign_run(PyThunkObject *self, int64_t lo, int64_t step, int64_t cou
   bool scalar = true;
   if (PyThunk_Check(value)) {
     PyThunkObject *vt = (PyThunkObject *)value;
-    if (vt->cardinality != 1 || !vt->evaluated) {
+    if (vt->card.n != 1 || !vt->evaluated) {
       varr = PyThunk_AsArray(value);           // forces it; borrowed
       if (!varr) return -1;
       Py_INCREF(varr);
@@ -120,13 +120,13 @@ static int assign_run(PyThunkObject *self, int64_t lo, int64_t step, int64_t cou
       if (!varr) return -1;
     }
   } else {
-    PyArray_Descr *descr = PyArray_DescrFromType(self->type);
+    PyArray_Descr *descr = PyArray_DescrFromType(self->npy_type);
     varr = PyArray_FromAny(value, descr, 0, 0, NPY_ARRAY_FORCECAST | NPY_ARRAY_C_CONTIGUOUS | NPY_ARRAY_ALIGNED, NULL);
     if (!varr) return -1;
     scalar = PyArray_SIZE((PyArrayObject *)varr) == 1;
   }
-  if (PyArray_TYPE((PyArrayObject *)varr) != self->type) {
-    PyObject *cast = PyArray_Cast((PyArrayObject *)varr, self->type);
+  if (PyArray_TYPE((PyArrayObject *)varr) != self->npy_type) {
+    PyObject *cast = PyArray_Cast((PyArrayObject *)varr, self->npy_type);
     Py_DECREF(varr);
     if (!cast) return -1;
     varr = cast;
@@ -179,42 +179,42 @@ static int thunk_assign_subscript(PyObject *self_o, PyObject *ind, PyObject *val
   bool fused_mask = false;
   if (PyThunk_Check(ind)) {
     PyThunkObject *mask = (PyThunkObject *)ind;
-    if (mask->type != NPY_BOOL) {
+    if (mask->npy_type != NPY_BOOL) {
       PyErr_SetString(PyExc_IndexError, "only boolean thunks can be used as assignment masks");
       return -1;
     }
     PyObject *vt = PyThunk_Coerce(value);
     if (!vt) return -1;
-    if (((PyThunkObject *)vt)->cardinality != 1) {
+    if (((PyThunkObject *)vt)->card.n != 1) {
       Py_DECREF(vt);
       PyErr_SetString(PyExc_ValueError, "masked assignment takes a scalar value");
       return -1;
     }
-    if (((PyThunkObject *)vt)->type != self->type) {
+    if (((PyThunkObject *)vt)->npy_type != self->npy_type) {
       // cast the scalar to the target dtype (NumPy setitem casting)
       uint64_t bits;
       PyObject *host = PyThunk_AsArray(vt);
-      if (!host || scalar_bits_of(host, self->type, &bits) < 0) { Py_DECREF(vt); return -1; }
+      if (!host || scalar_bits_of(host, self->npy_type, &bits) < 0) { Py_DECREF(vt); return -1; }
       Py_DECREF(vt);
       npy_intp one = 1;
-      PyObject *arr = PyArray_SimpleNew(1, &one, self->type);
+      PyObject *arr = PyArray_SimpleNew(1, &one, self->npy_type);
       if (!arr) return -1;
       memcpy(PyArray_DATA((PyArrayObject *)arr), &bits, (size_t)PyArray_ITEMSIZE((PyArrayObject *)arr));
       vt = PyThunk_FromArray(NULL, arr);
       Py_DECREF(arr);
       if (!vt) return -1;
     }
-    fused_mask = !mask->evaluated && Py_REFCNT(ind) == 1 && mask->children->empty();
-    ThunkOperation *op = ThunkOperation_FromBinary(vt, ind, optype_parallelbreaker, NL_OP_WHERE_STORE, "[]=");
+    fused_mask = !mask->evaluated && Py_REFCNT(ind) == 1 && mask->dependents->empty();
+    ThunkOperation *op = NewBinaryOperation(vt, ind, OpClass::ParallelBreaker, NL_OP_WHERE_STORE, "[]=");
     Py_DECREF(vt);
     if (!op) { PyErr_NoMemory(); return -1; }
-    where = PyThunk_FromOperation(op, default_binary_cardinality_function, cardinality_exact, self->type);
+    where = PyThunk_FromOperation(op, cardinality_broadcast, CardinalityKind::Exact, self->npy_type);
     if (!where) return -1;
   }
 
   // every thunk built from `self` must observe the OLD contents (thunk.cpp:81-88)
   {
-    std::vector<PyThunkObject *> snapshot(*self->children);
+    std::vector<PyThunkObject *> snapshot(*self->dependents);
     for (PyThunkObject *c : snapshot) Py_INCREF(c);
     for (PyThunkObject *c : snapshot) {
       const bool skip = fused_mask && where && (PyObject *)c == ind;
@@ -243,14 +243,14 @@ static int thunk_assign_subscript(PyObject *self_o, PyObject *ind, PyObject *val
   } else if (PySlice_Check(ind)) {
     Py_ssize_t start, stop, step;
     if (PySlice_Unpack(ind, &start, &stop, &step) < 0) return -1;
-    const Py_ssize_t count = PySlice_AdjustIndices((Py_ssize_t)self->cardinality, &start, &stop, step);
+    const Py_ssize_t count = PySlice_AdjustIndices((Py_ssize_t)self->card.n, &start, &stop, step);
     rc = assign_run(self, (int64_t)start, (int64_t)step, (int64_t)count, value);
   } else if (PyIndex_Check(ind)) {
     Py_ssize_t i = PyNumber_AsSsize_t(ind, PyExc_IndexError);
     if (i == -1 && PyErr_Occurred()) return -1;
-    if (i < 0) i += (Py_ssize_t)self->cardinality;
-    if (i < 0 || i >= (Py_ssize_t)self->cardinality) {
-      PyErr_Format(PyExc_IndexError, "index %zd is out of bounds for a thunk of size %zd", i, (Py_ssize_t)self->cardinality);
+    if (i < 0) i += (Py_ssize_t)self->card.n;
+    if (i < 0 || i >= (Py_ssize_t)self->card.n) {
+      PyErr_Format(PyExc_IndexError, "index %zd is out of bounds for a thunk of size %zd", i, (Py_ssize_t)self->card.n);
       return -1;
     }
     rc = assign_run(self, (int64_t)i, 1, 1, value);

@@ -11,23 +11,23 @@ static bool is_float_type(int t) { return t == NPY_FLOAT32 || t == NPY_FLOAT64; 
 // the array operand (NumPy's weak-scalar rule), two arrays must agree, and a float scalar is
 // never silently truncated into an integer column.
 static int binary_value_type(PyThunkObject *l, PyThunkObject *r, int *type_out) {
-  const bool ls = l->cardinality == 1, rs = r->cardinality == 1;
-  if (l->type == NPY_BOOL || r->type == NPY_BOOL) {
+  const bool ls = l->card.n == 1, rs = r->card.n == 1;
+  if (l->npy_type == NPY_BOOL || r->npy_type == NPY_BOOL) {
     PyErr_SetString(PyExc_TypeError, "arithmetic and comparisons on boolean thunks are not supported");
     return -1;
   }
   int t;
-  if (ls && !rs) t = r->type;
-  else if (rs && !ls) t = l->type;
+  if (ls && !rs) t = r->npy_type;
+  else if (rs && !ls) t = l->npy_type;
   else {
-    if (l->type != r->type && !(ls && rs)) {
+    if (l->npy_type != r->npy_type && !(ls && rs)) {
       PyErr_SetString(PyExc_TypeError, "operands must have the same dtype (no implicit promotion between columns)");
       return -1;
     }
-    t = l->type;
+    t = l->npy_type;
   }
   PyThunkObject *scalar = (ls && !rs) ? l : (rs && !ls) ? r : NULL;
-  if (scalar && is_float_type(scalar->type) && !is_float_type(t)) {
+  if (scalar && is_float_type(scalar->npy_type) && !is_float_type(t)) {
     PyErr_SetString(PyExc_TypeError, "a float scalar cannot be combined with an integer column");
     return -1;
   }
@@ -37,8 +37,8 @@ static int binary_value_type(PyThunkObject *l, PyThunkObject *r, int *type_out) 
 
 static int check_cardinality(PyThunkObject *l, PyThunkObject *r) {
   // thunk_as_number.cpp:60-65 meant this check but compared against the enum (Q9)
-  if (l->cardinality > 1 && r->cardinality > 1 && l->cardinality_type == cardinality_exact &&
-      r->cardinality_type == cardinality_exact && l->cardinality != r->cardinality) {
+  if (l->card.n > 1 && r->card.n > 1 && l->card.kind == CardinalityKind::Exact &&
+      r->card.kind == CardinalityKind::Exact && l->card.n != r->card.n) {
     PyErr_SetString(PyExc_TypeError, "Incompatible cardinality.");
     return -1;
   }
@@ -57,10 +57,10 @@ static PyObject *lazy_binary(PyObject *v, PyObject *w, int opcode, const char *o
     Py_DECREF(lo); Py_DECREF(ro);
     return NULL;
   }
-  ThunkOperation *op = ThunkOperation_FromBinary(lo, ro, optype_vectorizable, opcode, opname);
+  ThunkOperation *op = NewBinaryOperation(lo, ro, OpClass::Vectorizable, opcode, opname);
   Py_DECREF(lo); Py_DECREF(ro);      // the operation holds its own references
   if (!op) return PyErr_NoMemory();
-  return PyThunk_FromOperation(op, default_binary_cardinality_function, cardinality_exact, type);
+  return PyThunk_FromOperation(op, cardinality_broadcast, CardinalityKind::Exact, type);
 }
 
 static PyObject *thunk_lazymultiply(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_MUL, "*"); }
@@ -90,10 +90,10 @@ PyObject *PyThunk_LazyRichCompare(PyObject *self, PyObject *other, int cmp_op) {
     Py_DECREF(ro);
     return NULL;
   }
-  ThunkOperation *op = ThunkOperation_FromBinary(self, ro, optype_vectorizable, opcode, name);
+  ThunkOperation *op = NewBinaryOperation(self, ro, OpClass::Vectorizable, opcode, name);
   Py_DECREF(ro);
   if (!op) return PyErr_NoMemory();
-  return PyThunk_FromOperation(op, default_binary_cardinality_function, cardinality_exact,
+  return PyThunk_FromOperation(op, cardinality_broadcast, CardinalityKind::Exact,
                                NPY_BOOL /* returns a boolean array */);
 }
 
@@ -101,27 +101,27 @@ PyObject *PyThunk_LazyRichCompare(PyObject *self, PyObject *other, int cmp_op) {
 static PyObject *lazy_mask_binary(PyObject *v, PyObject *w, int opcode, const char *opname) {
   if (!PyThunk_Check(v) || !PyThunk_Check(w)) Py_RETURN_NOTIMPLEMENTED;
   PyThunkObject *l = (PyThunkObject *)v, *r = (PyThunkObject *)w;
-  if (l->type != NPY_BOOL || r->type != NPY_BOOL) {
+  if (l->npy_type != NPY_BOOL || r->npy_type != NPY_BOOL) {
     PyErr_SetString(PyExc_TypeError, "&, | and ^ are defined on boolean thunks only");
     return NULL;
   }
   if (check_cardinality(l, r) < 0) return NULL;
-  ThunkOperation *op = ThunkOperation_FromBinary(v, w, optype_vectorizable, opcode, opname);
+  ThunkOperation *op = NewBinaryOperation(v, w, OpClass::Vectorizable, opcode, opname);
   if (!op) return PyErr_NoMemory();
-  return PyThunk_FromOperation(op, default_binary_cardinality_function, cardinality_exact, NPY_BOOL);
+  return PyThunk_FromOperation(op, cardinality_broadcast, CardinalityKind::Exact, NPY_BOOL);
 }
 static PyObject *thunk_lazyand(PyObject *v, PyObject *w) { return lazy_mask_binary(v, w, NL_OP_AND, "&"); }
 static PyObject *thunk_lazyor(PyObject *v, PyObject *w) { return lazy_mask_binary(v, w, NL_OP_OR, "|"); }
 static PyObject *thunk_lazyxor(PyObject *v, PyObject *w) { return lazy_mask_binary(v, w, NL_OP_XOR, "^"); }
 static PyObject *thunk_lazyinvert(PyObject *v) {
   PyThunkObject *l = (PyThunkObject *)v;
-  if (l->type != NPY_BOOL) {
+  if (l->npy_type != NPY_BOOL) {
     PyErr_SetString(PyExc_TypeError, "~ is defined on boolean thunks only");
     return NULL;
   }
-  ThunkOperation *op = ThunkOperation_FromUnary(v, optype_vectorizable, NL_OP_NOT, NULL, "~");
+  ThunkOperation *op = NewUnaryOperation(v, OpClass::Vectorizable, NL_OP_NOT, NULL, "~");
   if (!op) return PyErr_NoMemory();
-  return PyThunk_FromOperation(op, default_cardinality_function, cardinality_exact, NPY_BOOL);
+  return PyThunk_FromOperation(op, cardinality_same_as_operand, CardinalityKind::Exact, NPY_BOOL);
 }
 
 // Python 3 layout of the number protocol (the reference's table is the Python 2 one,

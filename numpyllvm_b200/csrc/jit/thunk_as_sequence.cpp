@@ -10,7 +10,7 @@ static Py_ssize_t thunk_length(PyObject *self) {
     if (!r) return -1;
     Py_DECREF(r);
   }
-  return (Py_ssize_t)t->cardinality;
+  return (Py_ssize_t)t->card.n;
 }
 
 PySequenceMethods thunk_as_sequence = {

@@ -41,10 +41,10 @@ static PyObject *_thunk_sort(PyThunkObject *self, PyObject *unused) {
     PyErr_SetString(PyExc_TypeError, "Expected a thunk object as parameter.");
     return NULL;
   }
-  ThunkOperation *op = ThunkOperation_FromUnary((PyObject *)self, optype_fullbreaker, -1,
-                                                (base_function_unary)_thunk_inline_sort, "sort");
+  ThunkOperation *op = NewUnaryOperation((PyObject *)self, OpClass::FullBreaker, -1,
+                                                (HostFunction)_thunk_inline_sort, "sort");
   if (!op) return PyErr_NoMemory();
-  return PyThunk_FromOperation(op, default_cardinality_function, cardinality_exact, self->type);
+  return PyThunk_FromOperation(op, cardinality_same_as_operand, CardinalityKind::Exact, self->npy_type);
 }
 
 static ssize_t aggregate_cardinality_function(ssize_t *inputs) {
@@ -57,13 +57,13 @@ static PyObject *lazy_reduce(PyThunkObject *self, int opcode, const char *name) 
     PyErr_SetString(PyExc_TypeError, "Expected a thunk object as parameter.");
     return NULL;
   }
-  if (self->type == NPY_BOOL) {
+  if (self->npy_type == NPY_BOOL) {
     PyErr_SetString(PyExc_TypeError, "reductions of boolean thunks are not supported");
     return NULL;
   }
-  ThunkOperation *op = ThunkOperation_FromUnary((PyObject *)self, optype_parallelbreaker, opcode, NULL, name);
+  ThunkOperation *op = NewUnaryOperation((PyObject *)self, OpClass::ParallelBreaker, opcode, NULL, name);
   if (!op) return PyErr_NoMemory();
-  return PyThunk_FromOperation(op, aggregate_cardinality_function, cardinality_exact, self->type);
+  return PyThunk_FromOperation(op, aggregate_cardinality_function, CardinalityKind::Exact, self->npy_type);
 }
 
 static PyObject *_thunk_max(PyThunkObject *self, PyObject *unused) { (void)unused; return lazy_reduce(self, NL_OP_MAX, "max"); }
