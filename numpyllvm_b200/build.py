@@ -28,6 +28,7 @@ CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", f"-I{INCLUDE}", f"-I{CSRC}"]
+NVCC_FLAGS += os.environ.get("NL_EXTRA_NVCC_FLAGS", "").split()   # tuning experiments (-DNL_PIPE_ROWS=8 ...); use with --force
 
 KERNEL_SOURCES = ["nl_plan.cpp", "nl_kernels.cu", "nl_runtime.cu",
                   "nl_static_i32.cu", "nl_static_i64.cu", "nl_static_f32.cu", "nl_static_f64.cu"]

@@ -36,8 +36,8 @@ struct KParams {
   int32_t n_inputs;
   int32_t n_slots;                    // ring depth
   int32_t lag;                        // tiles between the count phase and the store phase
-  int32_t batch;                      // consecutive tiles claimed per ticket
   int32_t filter_step;                // index of the S_FILTER step
+  int32_t side_cap;                   // survivors per warp and tile that may wait in the side buffer (0: none)
 };
 
 // geometry of the pipeline kernel
@@ -70,7 +70,7 @@ int launch_empty_range(void *stream, const nl_plan *plan, const KParams &kp);
 int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t name_len, int *is_static);
 void set_static_kernels_enabled(int on);
 void set_compact_pipe_enabled(int on);
-void set_compact_pipe_batch(int b);
+void set_compact_pipe_side(int on);
 void set_compact_pipe_lag(int l);
 
 void count_launch(int n = 1);

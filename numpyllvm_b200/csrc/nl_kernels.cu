@@ -191,14 +191,22 @@ static pipeline_fn pick_dynamic_pipe(int dtype) {
 }
 
 static int g_pipe_enabled = 1;
-static int g_pipe_batch = 1;
+static int g_pipe_no_side = 0;
 static int g_pipe_lag = 0;       // 0: slots - 2
 void set_compact_pipe_enabled(int on) { g_pipe_enabled = on; }
-void set_compact_pipe_batch(int b) { if (b >= 1 && b <= 4) g_pipe_batch = b; }
+void set_compact_pipe_side(int on) { g_pipe_no_side = !on; }
 void set_compact_pipe_lag(int l) { g_pipe_lag = l; }
 
 // Can this plan run on the staged compaction pipeline?  One filter, nothing stored before it,
 // at least one value column to stage, enough tiles to fill the machine.  Fills the staged fields.
+// dynamic shared memory of compact_pipe_kernel (must mirror the carve-up at the top of the kernel)
+static size_t pipe_smem_bytes(int slots, int lag, int cols, bool side, size_t es) {
+  const size_t col_bytes = (size_t)kPipeConsumers * kPipeRows * 16;
+  const size_t entries = (size_t)lag + 1;
+  return ((sizeof(PipeShared) + 127) / 128) * 128 + entries * kPipeConsumers * ((kPipeRows * 16 / es <= 16) ? 2 : 4) +
+         (side ? entries * kPipeConsumerWarps * kPipeSideBytes : 0) + (size_t)slots * cols * col_bytes;
+}
+
 static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
   if (!g_pipe_enabled || !vec16) return false;
   if (!(plan->flags & NL_PLAN_HAS_COMPACT) || (plan->flags & (NL_PLAN_HAS_REDUCE | NL_PLAN_HAS_WHERE))) return false;
@@ -210,11 +218,13 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
       filter = i;
     } else if ((op == S_STORE || op == S_PSTORE || op == S_WHERE) && filter < 0) {
       return false;
+    } else if ((op == S_PLOADT || op == S_PBIN || op == S_PSTORE) && filter >= 0) {
+      return false;   // phase B skips the predicate steps before the filter: nothing after it may read them
     }
   }
   if (filter < 0) return false;
   const size_t es = nl_dtype_size(plan->dtype);
-  const int64_t tile = (int64_t)kPipeConsumers * kRows * (int64_t)(16 / es);
+  const int64_t tile = (int64_t)kPipeConsumers * kPipeRows * (int64_t)(16 / es);
   if (n_elems < tile * 2 * 148) return false;
   int cols = 0;
   uint8_t map[NL_MAX_INPUTS];
@@ -223,25 +233,45 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
     if (plan->in[k].kind == NL_IN_ARRAY && plan->in[k].dtype == plan->dtype) map[k] = (uint8_t)cols++;
   if (cols == 0) return false;
   const size_t col_bytes = (size_t)tile * es;
-  const size_t budget = (size_t)227 * 1024 - ((sizeof(PipeShared) + 127) / 128) * 128 - 1024;
-  int slots = (int)(budget / (col_bytes * (size_t)cols + (size_t)kPipeConsumers * 4));   // + the slot's keep bits
-  if (slots > kPipeMaxSlots) slots = kPipeMaxSlots;
-  if (slots < 4) return false;
+  // the side buffer can take a survivor only if everything after the filter works on a bare
+  // value: scalar operands and compacted stores
+  bool sparse_ok = true;
+  for (int i = filter + 1; i < plan->n_steps; i++) {
+    const uint32_t st = plan->step[i], op = step_op(st);
+    if (op == S_BIN) {
+      const uint32_t src = step_b(st);
+      if ((src & SRC_TEMP) || plan->in[src].kind == NL_IN_ARRAY) sparse_ok = false;
+    } else if (op == S_STORE) {
+      if (step_b(st) == NL_IDX_LOOP) sparse_ok = false;
+    } else {
+      sparse_ok = false;
+    }
+  }
+  if (g_pipe_no_side) sparse_ok = false;   // tuning switch
+  // deepest ring that fits: [PipeShared | keep bits and side buffers per lag entry | slots]
+  int slots = 0, lag = 0;
+  for (int s_try = kPipeMaxSlots; s_try >= 4; s_try--) {
+    int d = (g_pipe_lag > 0) ? g_pipe_lag : s_try / 2;   // half the ring hides the look-back, half is prefetch (measured best)
+    if (d > s_try - 2) d = s_try - 2;                    // a parked tile must be stored before the producer needs its slot
+    if (s_try + d + 1 > kPipeMeta) continue;
+    if (pipe_smem_bytes(s_try, d, cols, sparse_ok, es) <= (size_t)227 * 1024 - 1024) { slots = s_try; lag = d; break; }
+  }
+  if (slots == 0) return false;
   if (kp) {
     for (int k = 0; k < NL_MAX_INPUTS; k++) kp->stage_col[k] = map[k];
     kp->n_stage_cols = cols;
     kp->n_slots = slots;
-    kp->lag = (g_pipe_lag > 0 && g_pipe_lag < slots) ? g_pipe_lag : slots / 2;   // half the ring hides the look-back, half is prefetch (measured best)
-    kp->batch = g_pipe_batch;
+    kp->lag = lag;
     kp->filter_step = filter;
     kp->n_inputs = plan->n_inputs;
+    kp->side_cap = sparse_ok ? (int32_t)(kPipeSideBytes / es) : 0;
   }
   return true;
 }
 
 int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
   const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
-  if (pipe_eligible(plan, vec16, n_elems, kp)) return (int64_t)kPipeConsumers * kRows * v;
+  if (pipe_eligible(plan, vec16, n_elems, kp)) return (int64_t)kPipeConsumers * kPipeRows * v;
   const StaticEntry *e = find_static(plan, vec16);
   const int rows = e ? e->rows : kRows;
   return (int64_t)kBlock * rows * v;
@@ -266,10 +296,7 @@ static int launch_compact_pipe(const nl_plan *plan, const KParams &kp, int sm_co
   const StaticEntry *e = find_static(plan, true);
   pipeline_fn fn = (e && e->pipe) ? e->pipe : pick_dynamic_pipe(plan->dtype);
   if (!fn) { set_error("no compaction pipeline for dtype %d", plan->dtype); return NL_ERR_UNSUPPORTED; }
-  const size_t es = nl_dtype_size(plan->dtype);
-  const size_t col_bytes = (size_t)kPipeConsumers * kRows * 16;
-  (void)es;
-  const size_t smem = ((sizeof(PipeShared) + 127) / 128) * 128 + (size_t)kp.n_slots * ((size_t)kp.n_stage_cols * col_bytes + (size_t)kPipeConsumers * 4);
+  const size_t smem = pipe_smem_bytes(kp.n_slots, kp.lag, kp.n_stage_cols, kp.side_cap != 0, nl_dtype_size(plan->dtype));
   CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = sm_count;
   if (grid > kp.n_tiles) grid = kp.n_tiles;
@@ -278,8 +305,8 @@ static int launch_compact_pipe(const nl_plan *plan, const KParams &kp, int sm_co
   count_launch();
   if (info) {
     const int v = (int)(16 / nl_dtype_size(plan->dtype));
-    snprintf(info->kernel, sizeof(info->kernel), "compact_pipe_kernel<%s,V=%d,%s%s,slots=%d,lag=%d,batch=%d>", dt_name(plan->dtype), v,
-             (e && e->pipe) ? "static:" : "dynamic", (e && e->pipe) ? e->name : "", kp.n_slots, kp.lag, kp.batch);
+    snprintf(info->kernel, sizeof(info->kernel), "compact_pipe_kernel<%s,V=%d,%s%s,slots=%d,lag=%d,side=%d>", dt_name(plan->dtype), v,
+             (e && e->pipe) ? "static:" : "dynamic", (e && e->pipe) ? e->name : "", kp.n_slots, kp.lag, kp.side_cap);
     info->grid = (int)grid;
     info->block = kPipeThreads;
     info->vec_elems = v;

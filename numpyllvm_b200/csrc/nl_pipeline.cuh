@@ -254,35 +254,42 @@ struct Tile {
     }
   }
 
+  // crow[u] <- rank of this thread's first kept element of row u inside the warp's run (rows in
+  // order, lanes in order inside a row); returns the warp's total.  Per-row counts travel as
+  // packed 8-bit fields, four rows per word, so one shuffle scan serves four rows.
+  __device__ __forceinline__ uint32_t rank_rows(int lane) {
+    uint32_t packed[NWORDS], incl[NWORDS];
+#pragma unroll
+    for (int w = 0; w < NWORDS; w++) packed[w] = 0;
+#pragma unroll
+    for (int u = 0; u < U; u++) packed[u / 4] |= (uint32_t)__popc((keep >> (u * V)) & ROWMASK) << (8 * (u % 4));
+#pragma unroll
+    for (int w = 0; w < NWORDS; w++) {
+      incl[w] = packed[w];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t nb = __shfl_up_sync(0xffffffffu, incl[w], d);
+        if (lane >= d) incl[w] += nb;
+      }
+    }
+    // row bases inside the warp's run: running sum of the row totals (lane 31's inclusive counts)
+    uint32_t run = 0;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint32_t tot = (__shfl_sync(0xffffffffu, incl[u / 4], 31) >> (8 * (u % 4))) & 0xffu;
+      const uint32_t ex = ((incl[u / 4] - packed[u / 4]) >> (8 * (u % 4))) & 0xffu;
+      crow[u] = run + ex;
+      run += tot;
+    }
+    return run;
+  }
+
   // `if (!mask) goto for.inc` (thunk_as_mapping.cpp:11) + the order-preserving compaction index
   __device__ __forceinline__ void filter_step(const KParams &p, TileShared &sh, int lane, int warp) {
     keep &= pacc;
     if constexpr (kCompact) {
-      // rank of every kept element in (warp, row, lane, v) order == its input order.
-      // per-row counts travel as packed 8-bit fields, four rows per word
-      uint32_t packed[NWORDS], incl[NWORDS];
-#pragma unroll
-      for (int w = 0; w < NWORDS; w++) packed[w] = 0;
-#pragma unroll
-      for (int u = 0; u < U; u++) packed[u / 4] |= (uint32_t)__popc((keep >> (u * V)) & ROWMASK) << (8 * (u % 4));
-#pragma unroll
-      for (int w = 0; w < NWORDS; w++) {
-        incl[w] = packed[w];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t nb = __shfl_up_sync(0xffffffffu, incl[w], d);
-          if (lane >= d) incl[w] += nb;
-        }
-      }
-      // row bases inside the warp's run: running sum of the row totals (lane 31's inclusive counts)
-      uint32_t run = 0;
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        const uint32_t tot = (__shfl_sync(0xffffffffu, incl[u / 4], 31) >> (8 * (u % 4))) & 0xffu;
-        const uint32_t ex = ((incl[u / 4] - packed[u / 4]) >> (8 * (u % 4))) & 0xffu;
-        crow[u] = run + ex;
-        run += tot;
-      }
+      // rank of every kept element in (warp, row, lane, v) order == its input order
+      const uint32_t run = rank_rows(lane);
       if (lane == 0) sh.wtot[warp] = run;
       __syncthreads();
       if (warp == 0) {
@@ -343,13 +350,81 @@ struct Tile {
     }
   }
 
+  __device__ __forceinline__ bool is_scalar(const KParams &p, uint32_t src) const {
+    return !(src & SRC_TEMP) && p.in_kind[src] != NL_IN_ARRAY;
+  }
+  __device__ __forceinline__ T scalar_of(const KParams &p, uint32_t src) const {
+    return (p.in_kind[src] == NL_IN_SCALAR_IMM) ? from_bits<T>(p.imm[src]) : *reinterpret_cast<const T *>(p.in[src]);
+  }
+  template <class X>
+  __device__ __forceinline__ void bin_apply(uint32_t vop, X x) {
+    switch (vop) {
+      case V_MUL:
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e] = op_mul<T>(acc[e], x(e));
+        break;
+      case V_ADD:
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e] = op_add<T>(acc[e], x(e));
+        break;
+      case V_SUB:
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e] = op_sub<T>(acc[e], x(e));
+        break;
+      default:
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e] = op_sub<T>(x(e), acc[e]);
+        break;
+    }
+  }
+  template <class X>
+  __device__ __forceinline__ uint32_t cmp_apply(uint32_t cop, X x) const {
+    uint32_t m = 0;
+    switch (cop) {
+      case C_GE:
+#pragma unroll
+        for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] >= x(e)) << e;
+        break;
+      case C_GT:
+#pragma unroll
+        for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] > x(e)) << e;
+        break;
+      case C_LE:
+#pragma unroll
+        for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] <= x(e)) << e;
+        break;
+      case C_LT:
+#pragma unroll
+        for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] < x(e)) << e;
+        break;
+      case C_EQ:
+#pragma unroll
+        for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] == x(e)) << e;
+        break;
+      default:
+#pragma unroll
+        for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] != x(e)) << e;
+        break;
+    }
+    return m;
+  }
+
   // One step of the accumulator machine.  With compile-time constant (op, a, b) — the
   // StaticProg driver — everything but the selected case folds away.
+  // kValuesOnly (phase B of the staged compaction pipeline): the keep mask is already known, so
+  // steps that only produce predicates are skipped.
+  template <bool kValuesOnly = false>
   __device__ __forceinline__ void exec(const KParams &p, TileShared &sh, uint32_t op, uint32_t a, uint32_t b,
                                        int lane, int warp) {
     switch (op) {
       case S_LOAD:
-        fetch(p, a, acc);
+        if (is_scalar(p, a)) {
+          const T sc = scalar_of(p, a);
+#pragma unroll
+          for (int e = 0; e < E; e++) acc[e] = sc;
+        } else {
+          fetch(p, a, acc);
+        }
         break;
       case S_LOADT:
         fetch(p, SRC_TEMP | a, acc);
@@ -363,63 +438,32 @@ struct Tile {
           for (int e = 0; e < E; e++) t1[e] = acc[e];
         }
         break;
-      case S_BIN: {
-        T x[E];
-        fetch(p, b, x);
-        switch (a) {
-          case V_MUL:
-#pragma unroll
-            for (int e = 0; e < E; e++) acc[e] = op_mul<T>(acc[e], x[e]);
-            break;
-          case V_ADD:
-#pragma unroll
-            for (int e = 0; e < E; e++) acc[e] = op_add<T>(acc[e], x[e]);
-            break;
-          case V_SUB:
-#pragma unroll
-            for (int e = 0; e < E; e++) acc[e] = op_sub<T>(acc[e], x[e]);
-            break;
-          default:
-#pragma unroll
-            for (int e = 0; e < E; e++) acc[e] = op_sub<T>(x[e], acc[e]);
-            break;
+      case S_BIN:
+        // a scalar operand is used straight from its (uniform) register: broadcasting it into E
+        // registers first cost 16 moves per step
+        if (is_scalar(p, b)) {
+          const T sc = scalar_of(p, b);
+          bin_apply(a, [&](int) { return sc; });
+        } else {
+          T x[E];
+          fetch(p, b, x);
+          bin_apply(a, [&](int e) { return x[e]; });
         }
         break;
-      }
-      case S_CMP: {
-        T x[E];
-        fetch(p, b, x);
-        uint32_t m = 0;
-        switch (a) {
-          case C_GE:
-#pragma unroll
-            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] >= x[e]) << e;
-            break;
-          case C_GT:
-#pragma unroll
-            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] > x[e]) << e;
-            break;
-          case C_LE:
-#pragma unroll
-            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] <= x[e]) << e;
-            break;
-          case C_LT:
-#pragma unroll
-            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] < x[e]) << e;
-            break;
-          case C_EQ:
-#pragma unroll
-            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] == x[e]) << e;
-            break;
-          default:
-#pragma unroll
-            for (int e = 0; e < E; e++) m |= (uint32_t)(acc[e] != x[e]) << e;
-            break;
+      case S_CMP:
+        if constexpr (!kValuesOnly) {
+          if (is_scalar(p, b)) {
+            const T sc = scalar_of(p, b);
+            pacc = cmp_apply(a, [&](int) { return sc; });
+          } else {
+            T x[E];
+            fetch(p, b, x);
+            pacc = cmp_apply(a, [&](int e) { return x[e]; });
+          }
         }
-        pacc = m;
         break;
-      }
       case S_PLOAD: {
+        if constexpr (kValuesOnly) break;
         const int kind = p.in_kind[a];
         uint32_t m = 0;
         if (kind == NL_IN_ARRAY) {
