@@ -258,28 +258,53 @@ struct Tile {
   // order, lanes in order inside a row); returns the warp's total.  Per-row counts travel as
   // packed 8-bit fields, four rows per word, so one shuffle scan serves four rows.
   __device__ __forceinline__ uint32_t rank_rows(int lane) {
+    (void)lane;
     uint32_t packed[NWORDS], incl[NWORDS];
 #pragma unroll
-    for (int w = 0; w < NWORDS; w++) packed[w] = 0;
+    for (int w = 0; w < NWORDS; w++) {
+      // per-row popcounts of four rows at once, then spread into 8-bit fields
+      const int rows = (U - 4 * w >= 4) ? 4 : (U - 4 * w);
+      const uint32_t x = (keep >> (4 * w * V)) & ((rows * V >= 32) ? 0xffffffffu : ((1u << (rows * V)) - 1u));
+      if constexpr (V == 1) {
+        packed[w] = (x | (x << 7) | (x << 14) | (x << 21)) & 0x01010101u;
+      } else if constexpr (V == 2) {
+        const uint32_t c = x - ((x >> 1) & 0x55u);
+        packed[w] = (c | (c << 6) | (c << 12) | (c << 18)) & 0x03030303u;
+      } else if constexpr (V == 4) {
+        uint32_t c = x - ((x >> 1) & 0x5555u);
+        c = (c & 0x3333u) + ((c >> 2) & 0x3333u);
+        packed[w] = (c & 0x0000000fu) | ((c << 4) & 0x00000f00u) | ((c << 8) & 0x000f0000u) | ((c << 12) & 0x0f000000u);
+      } else {
+        packed[w] = 0;
 #pragma unroll
-    for (int u = 0; u < U; u++) packed[u / 4] |= (uint32_t)__popc((keep >> (u * V)) & ROWMASK) << (8 * (u % 4));
+        for (int r = 0; r < 4; r++)
+          if (4 * w + r < U) packed[w] |= (uint32_t)__popc((keep >> ((4 * w + r) * V)) & ROWMASK) << (8 * r);
+      }
+    }
 #pragma unroll
     for (int w = 0; w < NWORDS; w++) {
       incl[w] = packed[w];
+      // inclusive scan over the lanes; the shuffle's own predicate (source lane in range) guards
+      // the add, so no lane compare is needed
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t nb = __shfl_up_sync(0xffffffffu, incl[w], d);
-        if (lane >= d) incl[w] += nb;
-      }
+      for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{\n\t.reg .u32 r;\n\t.reg .pred p;\n\tshfl.sync.up.b32 r|p, %0, %1, 0x0, 0xffffffff;\n\t@p add.u32 %0, %0, r;\n\t}"
+                     : "+r"(incl[w])
+                     : "r"(d));
     }
     // row bases inside the warp's run: running sum of the row totals (lane 31's inclusive counts)
     uint32_t run = 0;
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint32_t tot = (__shfl_sync(0xffffffffu, incl[u / 4], 31) >> (8 * (u % 4))) & 0xffu;
-      const uint32_t ex = ((incl[u / 4] - packed[u / 4]) >> (8 * (u % 4))) & 0xffu;
-      crow[u] = run + ex;
-      run += tot;
+    for (int w = 0; w < NWORDS; w++) {
+      const uint32_t totw = __shfl_sync(0xffffffffu, incl[w], 31);
+      const uint32_t exw = incl[w] - packed[w];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (4 * w + r < U) {
+          crow[4 * w + r] = run + ((exw >> (8 * r)) & 0xffu);
+          run += (totw >> (8 * r)) & 0xffu;
+        }
+      }
     }
     return run;
   }
