@@ -14,8 +14,10 @@
  *     (typedef thread.hpp:25)
  *   ScheduleFunction() alloc     scheduler.cpp:107   nl_malloc()/nl_memset()
  *   ScheduleFunction() partition scheduler.cpp:133   nl_partition()
- *   JITFunctionDECREF() gather   compiler.cpp:30-49  nl_finish_filter()
- *   llvm_finalize_sum_data()     thunk_methods.cpp:133  nl_finish_reduce(),
+ *   JITFunctionDECREF() gather   compiler.cpp:30-49  nl_launch_pipeline_allgather(),
+ *                                                    nl_finish_filter()
+ *   llvm_finalize_sum_data()     thunk_methods.cpp:133  nl_launch_pipeline_allreduce(),
+ *                                                    nl_finish_reduce(),
  *                                                    nl_finalize_partials()
  *   thunk_assign_subscript()     thunk_as_mapping.cpp:80  nl_assign_fill(),
  *     (NumPy setitem on storage)                     nl_assign_copy()
@@ -254,6 +256,28 @@ NL_API int nl_launch_pipeline(const nl_plan *plan, void *const *outputs,
                        const void *const *inputs, int64_t start, int64_t end,
                        int64_t *output_sizes, int thread_nr, int dev, int stream);
 
+/* The same launch for a plan that ends in a reduction, with the multi-GPU
+ * finish FUSED into the kernel: the CTA that folds this device's partials
+ * writes the result into a mailbox on every peer GPU (stores over NVLink
+ * peer / IPC mappings), waits for the peers' slots and folds them in rank
+ * order, so out[0] on every rank holds the global result when the kernel
+ * ends — no collective launch follows (replaces llvm_finalize_sum_data,
+ * thunk_methods.cpp:133-151, across devices).  Every rank must issue the same
+ * sequence of these calls (like a collective); stream 0, slot 0.  Requires
+ * nl_comm_peer_ready(). */
+NL_API int nl_launch_pipeline_allreduce(const nl_plan *plan, void *const *outputs,
+                                 const void *const *inputs, int64_t start, int64_t end,
+                                 int64_t *output_sizes, int dev);
+
+/* The filter's twin: a compaction pipeline whose kernel also posts the shard's
+ * count to every peer and leaves in `offsets` (DEVICE, world_size + 1 int64)
+ * the exclusive scan of all ranks' counts — where each shard's run starts in
+ * the concatenated result, and the total (the memmove gather of
+ * compiler.cpp:36-48 without moving data).  Same calling rules as above. */
+NL_API int nl_launch_pipeline_allgather(const nl_plan *plan, void *const *outputs,
+                                 const void *const *inputs, int64_t start, int64_t end,
+                                 int64_t *output_sizes, int64_t *offsets, int dev);
+
 /* Combine `n` reduction partials in order j = 0..n-1 into out[0]
  * (llvm_finalize_sum_data, thunk_methods.cpp:133-151; same for max/min).
  * Device-side, asynchronous. */
@@ -298,6 +322,16 @@ NL_API int nl_comm_unique_id(void *id_out /*NL_UNIQUE_ID_BYTES*/);
 NL_API int nl_comm_init(const void *id, int world_size, int first_rank);
 NL_API int nl_comm_world_size(void);               /* 0 when no communicator            */
 NL_API int nl_comm_destroy(void);
+
+/* NVLink mailboxes: the peer memory behind nl_launch_pipeline_allreduce().
+ * A process that drives every rank itself gets them from nl_comm_init() (CUDA
+ * peer access).  With one process per GPU each rank exports the IPC handle of
+ * its mailbox, the host plumbing all-gathers the handles (rank order,
+ * NL_MAILBOX_HANDLE_BYTES each) and every rank imports the lot. */
+#define NL_MAILBOX_HANDLE_BYTES 64
+NL_API int nl_comm_mailbox_export(int dev, void *handle_out /*NL_MAILBOX_HANDLE_BYTES*/);
+NL_API int nl_comm_mailbox_import(const void *handles /*world_size x NL_MAILBOX_HANDLE_BYTES*/);
+NL_API int nl_comm_peer_ready(void);               /* 1 when the fused finish can be used */
 
 /* ======================= introspection ==================================== */
 /* Kernels launched by this library since load (the bench's gpu_launches). */

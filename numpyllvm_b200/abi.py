@@ -20,6 +20,7 @@ NL_MAX_OUTPUTS = 4
 NL_MAX_NODES = 48
 NL_MAX_STEPS = 64
 NL_UNIQUE_ID_BYTES = 128
+NL_MAILBOX_HANDLE_BYTES = 64
 
 # error codes
 NL_OK, NL_ERR_INVALID, NL_ERR_UNSUPPORTED, NL_ERR_SPLIT = 0, -1, -2, -3
@@ -211,6 +212,10 @@ _SIGNATURES = {
     "nl_event_elapsed_ms": (C.c_int, [_VP, _VP, C.POINTER(C.c_float)]),
     "nl_launch_pipeline": (C.c_int, [C.POINTER(Plan), C.POINTER(_VP), C.POINTER(_VP), C.c_int64, C.c_int64,
                                      _VP, C.c_int, C.c_int, C.c_int]),
+    "nl_launch_pipeline_allreduce": (C.c_int, [C.POINTER(Plan), C.POINTER(_VP), C.POINTER(_VP), C.c_int64, C.c_int64,
+                                               _VP, C.c_int]),
+    "nl_launch_pipeline_allgather": (C.c_int, [C.POINTER(Plan), C.POINTER(_VP), C.POINTER(_VP), C.c_int64, C.c_int64,
+                                               _VP, _VP, C.c_int]),
     "nl_finalize_partials": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP]),
     "nl_finish_reduce": (C.c_int, [C.c_int, C.c_int, C.POINTER(_VP), C.c_int]),
     "nl_finish_filter": (C.c_int, [C.POINTER(_VP), C.POINTER(_VP), C.c_int]),
@@ -221,6 +226,9 @@ _SIGNATURES = {
     "nl_comm_init": (C.c_int, [_VP, C.c_int, C.c_int]),
     "nl_comm_world_size": (C.c_int, []),
     "nl_comm_destroy": (C.c_int, []),
+    "nl_comm_mailbox_export": (C.c_int, [C.c_int, _VP]),
+    "nl_comm_mailbox_import": (C.c_int, [_VP]),
+    "nl_comm_peer_ready": (C.c_int, []),
     "nl_plan_kernel": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]),
     "nl_set_static_kernels": (C.c_int, [C.c_int]),
     "nl_launch_count": (C.c_uint64, []),

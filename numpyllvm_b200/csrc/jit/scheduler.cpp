@@ -173,6 +173,7 @@ static int execute_one(Pipeline *pipeline) {
   }
 
   // one launch per device shard (the reference's 8 range tasks, scheduler.cpp:133-147)
+  const bool fused_finish = G > 1 && (lp.plan.flags & NL_PLAN_HAS_REDUCE) && nl_comm_peer_ready();
   std::vector<int64_t *> sizes(G, (int64_t *)NULL);
   for (int g = 0; g < G; g++) {
     void *out_ptrs[NL_MAX_OUTPUTS] = {0};
@@ -189,7 +190,11 @@ static int execute_one(Pipeline *pipeline) {
     }
     sizes[g] = sizes_buffer(g);
     if (!sizes[g]) { nljit_raise(NL_ERR_NOMEM, "jit: scratch allocation failed"); return fail(); }
-    int rc = nl_launch_pipeline(&lp.plan, out_ptrs, in_ptrs, 0, shape->shards[g].count, sizes[g], 0, g, 0);
+    // a reduction over several GPUs finishes inside its kernel: the partials travel through the
+    // peers' NVLink mailboxes, no collective launch follows
+    int rc = fused_finish
+                 ? nl_launch_pipeline_allreduce(&lp.plan, out_ptrs, in_ptrs, 0, shape->shards[g].count, sizes[g], g)
+                 : nl_launch_pipeline(&lp.plan, out_ptrs, in_ptrs, 0, shape->shards[g].count, sizes[g], 0, g, 0);
     if (rc != NL_OK) { nljit_raise(rc, "jit: pipeline launch failed"); return fail(); }
   }
 
@@ -200,6 +205,7 @@ static int execute_one(Pipeline *pipeline) {
     if (space == NL_IDX_SHARD) {
       void *ptrs[NL_MAX_DEVICES];
       for (int g = 0; g < G; g++) ptrs[g] = outs[k]->shards[g].ptr;
+      if (fused_finish) continue;
       int rc = nl_finish_reduce(lp.plan.reduce_op, outs[k]->dtype, ptrs, 0);      // NCCL allreduce over NVLink
       if (rc != NL_OK) { nljit_raise(rc, "jit: reduction finish failed"); return fail(); }
     } else if (space == NL_IDX_COMPACT) {

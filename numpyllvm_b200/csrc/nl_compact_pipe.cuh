@@ -371,6 +371,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) compact_pipe_kernel(const __g
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ps.ranked[me]);    // release: prefix and off[] are visible to phase B
+      // multi-GPU: the shard's count goes to the peers from inside the kernel
+      if (tile == p.n_tiles - 1 && p.peer_offsets != nullptr) peer_scan_counts(p, excl + agg, lane);
       PSTAT_ADD(st_look, c1);
       PSTAT_INC(st_n, 1);
     }

@@ -38,6 +38,11 @@ struct KParams {
   int32_t lag;                        // tiles between the count phase and the store phase
   int32_t filter_step;                // index of the S_FILTER step
   int32_t side_cap;                   // survivors per warp and tile that may wait in the side buffer (0: none)
+  // fused multi-GPU finish of a reduction over peer memory (NVLink mailboxes, nl_pipeline.cuh)
+  unsigned long long *const *peer_box;   // device array: mailbox of every rank, mapped here (NULL: no fused finish)
+  int32_t peer_world, peer_rank;
+  unsigned long long peer_epoch;      // > 0, the same on every rank for one reduction
+  long long *peer_offsets;            // filters: exclusive scan of every rank's count, peer_world + 1 entries (or NULL)
 };
 
 // geometry of the pipeline kernel

@@ -18,18 +18,25 @@ namespace nl {
 // reduction identity (llvm_initialize_max / _sum with zero iterations).
 template <typename T>
 __global__ void empty_range_kernel(const __grid_constant__ KParams p) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   for (int o = 0; o < p.n_outputs; o++) {
     if (p.out_space[o] == NL_IDX_SHARD) {
-      p.out_sizes[o] = 1;
-      T *out = reinterpret_cast<T *>(p.out[o]);
-      out[p.thread_nr] = (p.reduce_rop == R_SUM) ? T(0) : (p.reduce_rop == R_MAX ? TT<T>::lowest() : TT<T>::highest());
-    } else if (p.out_space[o] == NL_IDX_COMPACT) {
-      p.out_sizes[o] = p.start;
-    } else {
-      p.out_sizes[o] = p.end;
+      using Acc = typename TT<T>::Acc;
+      // identity of the reduction; with a fused multi-GPU finish the empty shard still takes part
+      unsigned long long bits = (p.reduce_rop == R_SUM) ? to_bits<Acc>(Acc(0))
+                                                        : to_bits<T>(p.reduce_rop == R_MAX ? TT<T>::lowest() : TT<T>::highest());
+      if (p.peer_box != nullptr) bits = peer_allreduce<T>(p, bits, p.reduce_rop, lane);
+      if (lane == 0) {
+        p.out_sizes[o] = 1;
+        T *out = reinterpret_cast<T *>(p.out[o]);
+        out[p.thread_nr] = (p.reduce_rop == R_SUM) ? (T)from_bits<Acc>(bits) : from_bits<T>(bits);
+      }
+    } else if (lane == 0) {
+      p.out_sizes[o] = (p.out_space[o] == NL_IDX_COMPACT) ? p.start : p.end;
     }
   }
+  if (p.peer_offsets != nullptr) peer_scan_counts(p, 0ull, lane);   // an empty shard keeps nothing but still posts its slot
 }
 
 // ------------------------------------------------------------------ small kernels

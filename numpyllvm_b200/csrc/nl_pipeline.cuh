@@ -135,6 +135,90 @@ constexpr unsigned long long kDescPrefix = 2ull << 62;
 // SMs at the same time; sharing a line between them serialises in the L2 slice
 constexpr int kDescStride = NL_DESC_STRIDE;
 
+// ------------------------------------------------------------------ NVLink mailbox all-reduce
+// Fused multi-GPU finish of a reduction: the CTA that folded this GPU's partials writes the
+// result straight into a mailbox slot on EVERY peer GPU (plain stores over NVLink P2P / IPC
+// mappings, released with a system-scope flag), then waits until its own mailbox holds the
+// slot of every rank for this epoch and folds them in rank order — the same order on every
+// GPU, so all ranks end up with bit-identical results and no NCCL launch follows the kernel.
+//
+// Mailbox of one rank: [2 parities][world][value u64, epoch u64].  Two parities suffice: a rank
+// can start epoch e + 2 only after it finished e + 1, which needed every peer's e + 1 slot,
+// which a peer writes only after it finished reading epoch e.
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Called by ONE warp (all 32 lanes); `mine` = this GPU's result as accumulator bits (Acc for
+// sums, T for max/min).  Returns the global result bits in every lane.
+template <typename T>
+__device__ __forceinline__ unsigned long long peer_allreduce(const KParams &p, unsigned long long mine, int rop, int lane) {
+  using Acc = typename TT<T>::Acc;
+  using Tr = TT<T>;
+  const int W = p.peer_world, r = p.peer_rank;
+  const unsigned long long epoch = p.peer_epoch;
+  const size_t par_off = (size_t)(epoch & 1ull) * (size_t)W * 2;
+  for (int dst = lane; dst < W; dst += 32) {
+    unsigned long long *slot = p.peer_box[dst] + par_off + (size_t)r * 2;
+    st_relaxed_sys_u64(slot, mine);
+    st_release_sys_u64(slot + 1, epoch);
+  }
+  const unsigned long long *own = p.peer_box[r] + par_off;
+  Acc sv = 0;
+  T ev = (rop == R_MIN) ? Tr::highest() : Tr::lowest();
+  for (int src = 0; src < W; src++) {                     // rank order: deterministic, identical everywhere
+    unsigned long long bits = 0;
+    if (lane == 0) {
+      while (ld_acquire_sys_u64(own + (size_t)src * 2 + 1) != epoch) {
+      }
+      bits = ld_relaxed_sys_u64(own + (size_t)src * 2);
+    }
+    bits = __shfl_sync(0xffffffffu, bits, 0);
+    if (rop == R_SUM) sv = acc_add(sv, from_bits<Acc>(bits));
+    else if (rop == R_MAX) ev = op_max<T>(ev, from_bits<T>(bits));
+    else ev = op_min<T>(ev, from_bits<T>(bits));
+  }
+  return (rop == R_SUM) ? to_bits<Acc>(sv) : to_bits<T>(ev);
+}
+
+// The filter's finish over the same mailboxes: every rank posts how many elements its shard
+// kept; offsets[r] = where rank r's run starts in the concatenated result, offsets[world] =
+// total (what the memmove gather of compiler.cpp:36-48 computes).  Called by one warp.
+__device__ __forceinline__ void peer_scan_counts(const KParams &p, unsigned long long count, int lane) {
+  const int W = p.peer_world, r = p.peer_rank;
+  const unsigned long long epoch = p.peer_epoch;
+  const size_t par_off = (size_t)(epoch & 1ull) * (size_t)W * 2;
+  for (int dst = lane; dst < W; dst += 32) {
+    unsigned long long *slot = p.peer_box[dst] + par_off + (size_t)r * 2;
+    st_relaxed_sys_u64(slot, count);
+    st_release_sys_u64(slot + 1, epoch);
+  }
+  if (lane == 0) {
+    const unsigned long long *own = p.peer_box[r] + par_off;
+    long long run = 0;
+    for (int src = 0; src < W; src++) {
+      while (ld_acquire_sys_u64(own + (size_t)src * 2 + 1) != epoch) {
+      }
+      p.peer_offsets[src] = run;
+      run += (long long)ld_relaxed_sys_u64(own + (size_t)src * 2);
+    }
+    p.peer_offsets[W] = run;
+  }
+}
+
 // shared memory of one CTA (tiny: scan totals, the look-back result, the reduce tree)
 struct TileShared {
   uint32_t wtot[kBlock / 32];          // elements each warp keeps in this tile
@@ -369,6 +453,8 @@ struct Tile {
               if (p.out_space[o] == NL_IDX_COMPACT) p.out_sizes[o] = p.start + (long long)(excl + agg);
           }
         }
+        // multi-GPU: the shard's count goes to the peers from inside the kernel
+        if (tile == p.n_tiles - 1 && p.peer_offsets != nullptr) peer_scan_counts(p, excl + agg, lane);
       }
       __syncthreads();
       cbase = p.start + sh.prefix + (int64_t)sh.off[warp];
@@ -777,7 +863,9 @@ pipeline_kernel(const __grid_constant__ KParams p) {
         else if (rop == R_MAX) ev = op_max<T>(ev, from_bits<T>(bits));
         else ev = op_min<T>(ev, from_bits<T>(bits));
       }
-      const unsigned long long total = block_reduce(sv, ev);
+      unsigned long long total = block_reduce(sv, ev);
+      // multi-GPU: exchange with the peers over NVLink inside this kernel (warp 0 holds `total`)
+      if (p.peer_box != nullptr && warp == 0) total = peer_allreduce<T>(p, total, rop, lane);
       if (tid == 0) {
         T *out = reinterpret_cast<T *>(p.out[p.reduce_out]);
         // the store casts the accumulator to the column type (compiler.cpp:256-260)

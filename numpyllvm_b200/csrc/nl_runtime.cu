@@ -47,7 +47,16 @@ struct Device {
   Scratch scratch[NL_N_STREAMS];
   int64_t *gather = nullptr;        // world_size int64 for the count allgather
   ncclComm_t comm = nullptr;
+  // NVLink mailbox of this device's rank and the table of every rank's mailbox as mapped here
+  unsigned long long *box = nullptr;          // cudaMalloc (IPC-exportable), kMailboxBytes, zeroed
+  unsigned long long **box_table = nullptr;   // device array [world]
+  unsigned long long epoch = 0;               // fused reductions launched on this device so far
 };
+
+constexpr int kMaxWorld = 256;
+constexpr size_t kMailboxBytes = 2 * (size_t)kMaxWorld * 16;   // [2 parities][world][value, epoch]
+static bool g_peer_ready = false;
+static void *g_ipc_mapped[NL_MAX_DEVICES][kMaxWorld];          // IPC mappings to close at destroy
 
 static Device g_dev[NL_MAX_DEVICES];
 static int g_ndev = 0;
@@ -370,8 +379,8 @@ int nl_event_elapsed_ms(nl_event start, nl_event stop, float *ms_out) {
 }
 
 // ======================================================================= hot path
-int nl_launch_pipeline(const nl_plan *plan, void *const *outputs, const void *const *inputs, int64_t start,
-                       int64_t end, int64_t *output_sizes, int thread_nr, int dev, int stream) {
+static int launch_impl(const nl_plan *plan, void *const *outputs, const void *const *inputs, int64_t start, int64_t end,
+                       int64_t *output_sizes, int thread_nr, int dev, int stream, bool fuse_finish, int64_t *peer_offsets = nullptr) {
   int rc = check_dev(dev, stream);
   if (rc) return rc;
   if (!plan || plan->abi_version != NL_ABI_VERSION) { set_error("nl_launch_pipeline: bad plan / ABI version"); return NL_ERR_INVALID; }
@@ -420,6 +429,14 @@ int nl_launch_pipeline(const nl_plan *plan, void *const *outputs, const void *co
   for (int i = 0; i < plan->n_steps; i++)
     if (step_op(plan->step[i]) == S_REDUCE) { kp.reduce_rop = (int32_t)step_a(plan->step[i]); kp.reduce_out = (int32_t)step_b(plan->step[i]); }
 
+  if (fuse_finish) {
+    // every rank launches the same sequence of fused reductions: the per-device counter is the epoch
+    kp.peer_box = d.box_table;
+    kp.peer_world = g_world;
+    kp.peer_rank = g_first_rank + dev;
+    kp.peer_epoch = ++d.epoch;
+    kp.peer_offsets = (long long *)peer_offsets;
+  }
   if (end == start) return launch_empty_range(d.stream[stream], plan, kp);
 
   const int64_t tile = pipeline_tile_elems(plan, vec16, end - start, &kp);   // also selects the staged compaction pipeline
@@ -440,6 +457,27 @@ int nl_launch_pipeline(const nl_plan *plan, void *const *outputs, const void *co
   rc = launch_pipeline_kernel(plan, kp, vec16, d.sm_count, d.stream[stream], &info);
   if (rc == NL_OK) g_last_info = info;
   return rc;
+}
+
+int nl_launch_pipeline(const nl_plan *plan, void *const *outputs, const void *const *inputs, int64_t start,
+                       int64_t end, int64_t *output_sizes, int thread_nr, int dev, int stream) {
+  return launch_impl(plan, outputs, inputs, start, end, output_sizes, thread_nr, dev, stream, false);
+}
+
+int nl_launch_pipeline_allreduce(const nl_plan *plan, void *const *outputs, const void *const *inputs, int64_t start,
+                                 int64_t end, int64_t *output_sizes, int dev) {
+  if (!g_peer_ready) { set_error("nl_launch_pipeline_allreduce: peer mailboxes are not set up (nl_comm_init / nl_comm_mailbox_import)"); return NL_ERR_NCCL; }
+  if (!plan || !(plan->flags & NL_PLAN_HAS_REDUCE)) { set_error("nl_launch_pipeline_allreduce: the plan has no reduction"); return NL_ERR_INVALID; }
+  // one stream only: the mailboxes are two epochs deep and epochs must complete in launch order
+  return launch_impl(plan, outputs, inputs, start, end, output_sizes, 0, dev, 0, true);
+}
+
+int nl_launch_pipeline_allgather(const nl_plan *plan, void *const *outputs, const void *const *inputs, int64_t start,
+                                 int64_t end, int64_t *output_sizes, int64_t *offsets, int dev) {
+  if (!g_peer_ready) { set_error("nl_launch_pipeline_allgather: peer mailboxes are not set up (nl_comm_init / nl_comm_mailbox_import)"); return NL_ERR_NCCL; }
+  if (!plan || !(plan->flags & NL_PLAN_HAS_COMPACT) || (plan->flags & NL_PLAN_HAS_REDUCE)) { set_error("nl_launch_pipeline_allgather: the plan is not a filter"); return NL_ERR_INVALID; }
+  if (!offsets) { set_error("nl_launch_pipeline_allgather: null offsets"); return NL_ERR_INVALID; }
+  return launch_impl(plan, outputs, inputs, start, end, output_sizes, 0, dev, 0, true, offsets);
 }
 
 static int rop_of(int reduce_op) { return reduce_op == NL_OP_MAX ? R_MAX : reduce_op == NL_OP_MIN ? R_MIN : reduce_op == NL_OP_SUM ? R_SUM : -1; }
@@ -488,6 +526,8 @@ int nl_comm_unique_id(void *id_out) {
   return NL_OK;
 }
 
+static int setup_local_mailboxes();
+
 int nl_comm_init(const void *id, int world_size, int first_rank) {
   if (g_ndev == 0) { set_error("nl_comm_init before nl_init"); return NL_ERR_NO_DEVICE; }
   if (!id || world_size < g_ndev || first_rank < 0 || first_rank + g_ndev > world_size || world_size > 256) { set_error("nl_comm_init: bad argument"); return NL_ERR_INVALID; }
@@ -504,10 +544,108 @@ int nl_comm_init(const void *id, int world_size, int first_rank) {
   NCCL_TRY(g_nccl.GroupEnd());
   g_world = world_size;
   g_first_rank = first_rank;
+  g_peer_ready = false;
+  if (g_ndev == world_size) return setup_local_mailboxes();   // all ranks in this process: P2P mailboxes right away
   return NL_OK;
 }
 
 int nl_comm_world_size(void) { return g_world; }
+
+// ---- NVLink mailboxes (fused reduction finish, nl_pipeline.cuh: peer_allreduce) ----
+static int ensure_mailbox(int d) {
+  Device &dv = g_dev[d];
+  CUDA_TRY(cudaSetDevice(dv.id));
+  if (!dv.box) {
+    CUDA_TRY(cudaMalloc((void **)&dv.box, kMailboxBytes));
+    CUDA_TRY(cudaMemset(dv.box, 0, kMailboxBytes));
+  }
+  if (!dv.box_table) CUDA_TRY(cudaMalloc((void **)&dv.box_table, sizeof(unsigned long long *) * kMaxWorld));
+  return NL_OK;
+}
+
+// all ranks live in this process: map every local mailbox into every local device (P2P)
+static int setup_local_mailboxes() {
+  for (int d = 0; d < g_ndev; d++)
+    for (int e = 0; e < g_ndev; e++) {
+      if (d == e) continue;
+      int can = 0;
+      CUDA_TRY(cudaDeviceCanAccessPeer(&can, g_dev[d].id, g_dev[e].id));
+      if (!can) return NL_OK;                      // no P2P between some pair: stay on the NCCL finish
+    }
+  for (int d = 0; d < g_ndev; d++) {
+    int rc = ensure_mailbox(d);
+    if (rc) return rc;
+    for (int e = 0; e < g_ndev; e++) {
+      if (d == e) continue;
+      cudaError_t err = cudaDeviceEnablePeerAccess(g_dev[e].id, 0);
+      if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (err != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(err)); return NL_ERR_CUDA; }
+    }
+  }
+  unsigned long long *table[kMaxWorld] = {nullptr};
+  for (int d = 0; d < g_ndev; d++) table[d] = g_dev[d].box;
+  for (int d = 0; d < g_ndev; d++) {
+    CUDA_TRY(cudaSetDevice(g_dev[d].id));
+    CUDA_TRY(cudaMemcpy(g_dev[d].box_table, table, sizeof(table[0]) * (size_t)g_ndev, cudaMemcpyHostToDevice));
+    g_dev[d].epoch = 0;
+  }
+  g_peer_ready = true;
+  return NL_OK;
+}
+
+int nl_comm_peer_ready(void) { return g_peer_ready ? 1 : 0; }
+
+int nl_comm_mailbox_export(int dev, void *handle_out) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  if (!handle_out) { set_error("nl_comm_mailbox_export: null"); return NL_ERR_INVALID; }
+  if (!g_world) { set_error("nl_comm_mailbox_export before nl_comm_init"); return NL_ERR_NCCL; }
+  rc = ensure_mailbox(dev);
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == NL_MAILBOX_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, g_dev[dev].box));
+  memcpy(handle_out, &h, sizeof(h));
+  return NL_OK;
+}
+
+int nl_comm_mailbox_import(const void *handles) {
+  if (!handles) { set_error("nl_comm_mailbox_import: null"); return NL_ERR_INVALID; }
+  if (!g_world || g_world > kMaxWorld) { set_error("nl_comm_mailbox_import before nl_comm_init"); return NL_ERR_NCCL; }
+  const char *hb = (const char *)handles;
+  for (int d = 0; d < g_ndev; d++) {
+    int rc = ensure_mailbox(d);
+    if (rc) return rc;
+    unsigned long long *table[kMaxWorld] = {nullptr};
+    for (int r = 0; r < g_world; r++) {
+      const int local = r - g_first_rank;
+      if (local == d) { table[r] = g_dev[d].box; continue; }
+      if (local >= 0 && local < g_ndev) {
+        // another device of this process: plain peer access
+        int rc2 = ensure_mailbox(local);
+        if (rc2) return rc2;
+        CUDA_TRY(cudaSetDevice(g_dev[d].id));
+        cudaError_t err = cudaDeviceEnablePeerAccess(g_dev[local].id, 0);
+        if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (err != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(err)); return NL_ERR_CUDA; }
+        table[r] = g_dev[local].box;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, hb + (size_t)r * NL_MAILBOX_HANDLE_BYTES, sizeof(h));
+      void *mapped = nullptr;
+      CUDA_TRY(cudaSetDevice(g_dev[d].id));
+      CUDA_TRY(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+      g_ipc_mapped[d][r] = mapped;
+      table[r] = (unsigned long long *)mapped;
+    }
+    CUDA_TRY(cudaSetDevice(g_dev[d].id));
+    CUDA_TRY(cudaMemcpy(g_dev[d].box_table, table, sizeof(table[0]) * (size_t)g_world, cudaMemcpyHostToDevice));
+    g_dev[d].epoch = 0;
+  }
+  g_peer_ready = true;
+  return NL_OK;
+}
 
 int nl_comm_destroy(void) {
   for (int d = 0; d < g_ndev; d++) {
@@ -516,8 +654,15 @@ int nl_comm_destroy(void) {
       g_nccl.CommDestroy(g_dev[d].comm);
     }
     g_dev[d].comm = nullptr;
+    cudaSetDevice(g_dev[d].id);
+    for (int r = 0; r < kMaxWorld; r++)
+      if (g_ipc_mapped[d][r]) { cudaIpcCloseMemHandle(g_ipc_mapped[d][r]); g_ipc_mapped[d][r] = nullptr; }
+    if (g_dev[d].box) { cudaFree(g_dev[d].box); g_dev[d].box = nullptr; }
+    if (g_dev[d].box_table) { cudaFree(g_dev[d].box_table); g_dev[d].box_table = nullptr; }
+    g_dev[d].epoch = 0;
   }
   g_world = 0;
+  g_peer_ready = false;
   return NL_OK;
 }
 

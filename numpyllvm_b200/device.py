@@ -99,6 +99,22 @@ class Runtime:
         abi.check(self.lib.nl_launch_pipeline(C.byref(plan), abi.void_array(outputs), abi.void_array(inputs),
                                               start, end, C.c_void_p(sizes_ptr), thread_nr, dev, stream))
 
+    def launch_allreduce(self, plan: abi.Plan, outputs: Sequence[int], inputs: Sequence[Optional[int]], start: int,
+                         end: int, sizes_ptr: int, dev: int = 0):
+        """Reduction pipeline with the multi-GPU finish fused into the kernel (NVLink mailboxes)."""
+        abi.check(self.lib.nl_launch_pipeline_allreduce(C.byref(plan), abi.void_array(outputs), abi.void_array(inputs),
+                                                        start, end, C.c_void_p(sizes_ptr), dev))
+
+    def launch_allgather(self, plan: abi.Plan, outputs: Sequence[int], inputs: Sequence[Optional[int]], start: int,
+                         end: int, sizes_ptr: int, offsets_ptr: int, dev: int = 0):
+        """Filter pipeline whose kernel also exchanges the shard counts (NVLink mailboxes) and leaves
+        their exclusive scan in `offsets` (world + 1 int64 on the device)."""
+        abi.check(self.lib.nl_launch_pipeline_allgather(C.byref(plan), abi.void_array(outputs), abi.void_array(inputs),
+                                                        start, end, C.c_void_p(sizes_ptr), C.c_void_p(offsets_ptr), dev))
+
+    def peer_ready(self) -> bool:
+        return bool(self.lib.nl_comm_peer_ready())
+
     def last_launch(self):
         name = C.create_string_buffer(128)
         g, b, v = C.c_int(), C.c_int(), C.c_int()

@@ -2,7 +2,8 @@
 
 torch.distributed (gloo) carries the rendezvous, barriers and the tiny host-side
 exchanges (timings, the NCCL unique id); the data path never goes through torch:
-reductions are finished by the library's own NCCL communicator
+reductions are finished inside their kernel over NVLink mailboxes
+(nl_launch_pipeline_allreduce) or by the library's own NCCL communicator
 (nl_finish_reduce) and filters by the exclusive scan of the shard counts
 (nl_finish_filter).  The helpers below are the host logic of the N > 1 path and
 are exercised on CPU by tests/test_dist_gloo.py with world_size = 2.
@@ -90,6 +91,24 @@ class Ranks:
             abi.check(lib.nl_comm_unique_id(ident))
         raw = self.bcast_bytes(bytes(ident.raw))
         abi.check(lib.nl_comm_init(C.create_string_buffer(raw, abi.NL_UNIQUE_ID_BYTES), self.world, self.rank))
+        self.init_mailboxes(lib)
+
+    def init_mailboxes(self, lib) -> bool:
+        """Exchange the CUDA IPC handles of the ranks' NVLink mailboxes (one tiny host all-gather)
+        so that reductions can finish inside their kernel (nl_launch_pipeline_allreduce).  Returns
+        whether the fused finish is available; the NCCL finish stays as the other path."""
+        from . import abi
+        if self.world <= 1:
+            return bool(lib.nl_comm_peer_ready())
+        mine = C.create_string_buffer(abi.NL_MAILBOX_HANDLE_BYTES)
+        ok = lib.nl_comm_mailbox_export(0, mine) == 0
+        gathered = self.all_gather_array(np.frombuffer(mine.raw if ok else b"", dtype=np.uint8).copy())
+        if any(len(g) != abi.NL_MAILBOX_HANDLE_BYTES for g in gathered):
+            return False                      # some rank could not export: everybody stays on NCCL
+        blob = b"".join(bytes(g.tobytes()) for g in gathered)
+        rc = lib.nl_comm_mailbox_import(C.create_string_buffer(blob, len(blob)))
+        oks = self.all_gather_int(1 if rc == 0 else 0)
+        return all(oks) and bool(lib.nl_comm_peer_ready())
 
 
 # ---- host logic of the sharded path (pure functions) -------------------------------

@@ -1,0 +1,161 @@
+"""Fused multi-GPU reduction finish (nl_launch_pipeline_allreduce): the reduction kernel
+exchanges its result with the peers through NVLink mailboxes and folds in rank order.
+
+One GPU: world of 1 (the exchange degenerates to the kernel's own mailbox) — the code path the
+driver's single-GPU box can run.  Two or more GPUs in this process: every device reduces its
+shard, all devices must end up with the oracle's global result, bit-identical across devices.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from numpyllvm_b200 import abi
+from numpyllvm_b200.abi import Expr
+from numpyllvm_b200.device import Runtime
+from numpyllvm_b200.dist import shard_range
+
+pytestmark = pytest.mark.gpu
+
+OPS = [(abi.OP_MAX, "max"), (abi.OP_MIN, "min"), (abi.OP_SUM, "sum")]
+DTYPES = [np.int32, np.int64, np.float32, np.float64]
+
+
+@pytest.fixture(scope="module")
+def rt():
+    r = Runtime.get(0)
+    lib = r.lib
+    if lib.nl_comm_world_size() == 0:
+        ident = C.create_string_buffer(abi.NL_UNIQUE_ID_BYTES)
+        abi.check(lib.nl_comm_unique_id(ident))
+        abi.check(lib.nl_comm_init(ident, r.n_devices, 0))
+    if not lib.nl_comm_peer_ready():
+        pytest.skip("no peer access between the local GPUs")
+    return r
+
+
+def reference(op, dtype, x):
+    e = Expr(dtype)
+    e.materialize(e.unop(op, e.array()))
+    return e, oracle.run(e, [x], x.size, thread_count=1)[0][0]
+
+
+def run_fused(rt, e, x, sizes):
+    """Shard x over all local devices, launch the fused reduction on each, return every device's scalar."""
+    G = rt.n_devices
+    plan = abi.compile_plan(e)
+    cols, outs, szs = [], [], []
+    for g in range(G):
+        lo, hi = shard_range(x.size, G, g)
+        cols.append(rt.upload(x[lo:hi] if hi > lo else x[:0], g))
+        outs.append(rt.empty(x.dtype, 1, g))
+        szs.append(rt.empty(np.int64, 4, g))
+    for g in range(G):
+        lo, hi = shard_range(x.size, G, g)
+        rt.launch_allreduce(plan, [outs[g].ptr], [cols[g].ptr], 0, hi - lo, szs[g].ptr, dev=g)
+    got = [rt.download(outs[g])[0] for g in range(G)]
+    for a in cols + outs + szs:
+        a.free()
+    return got
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("op,name", OPS, ids=[n for _, n in OPS])
+@pytest.mark.parametrize("n", [1, 1000, 300_001, 1 << 22])
+def test_fused_finish_matches_oracle(rt, dtype, op, name, n):
+    x = oracle.fill(dtype, 0, n, 1 if np.dtype(dtype).kind == "i" else 3, 5)
+    e, want = reference(op, dtype, x)
+    got = run_fused(rt, e, x, None)
+    assert all(g.tobytes() == got[0].tobytes() for g in got), "ranks disagree"
+    if name == "sum" and np.dtype(dtype).kind == "f":
+        np.testing.assert_allclose(got[0], want, rtol=1e-6 if dtype == np.float32 else 1e-12)
+    else:
+        assert got[0] == want
+
+
+def test_many_epochs_in_a_row(rt):
+    """The mailboxes are two epochs deep: a long run of back-to-back fused reductions with
+    changing data must never read a stale slot."""
+    G = rt.n_devices
+    n = 200_000
+    e = Expr(np.int64)
+    e.materialize(e.unop(abi.OP_SUM, e.array()))
+    plan = abi.compile_plan(e)
+    xs = [oracle.fill(np.int64, 0, n, 1, 100 + i) for i in range(4)]
+    cols = [[rt.upload(x[slice(*shard_range(n, G, g))], g) for g in range(G)] for x in xs]
+    outs = [[rt.empty(np.int64, 1, g) for _ in range(40)] for g in range(G)]
+    szs = [rt.empty(np.int64, 4, g) for g in range(G)]
+    for it in range(40):
+        for g in range(G):
+            lo, hi = shard_range(n, G, g)
+            rt.launch_allreduce(plan, [outs[g][it].ptr], [cols[it % 4][g].ptr], 0, hi - lo, szs[g].ptr, dev=g)
+    for it in range(40):
+        want = np.int64(xs[it % 4].sum())
+        for g in range(G):
+            assert rt.download(outs[g][it])[0] == want, (it, g)
+
+
+def test_empty_shard_takes_part(rt):
+    """A rank whose range is empty contributes the identity but must still post its slot."""
+    G = rt.n_devices
+    e = Expr(np.float64)
+    e.materialize(e.unop(abi.OP_MAX, e.array()))
+    plan = abi.compile_plan(e)
+    x = oracle.fill(np.float64, 0, 5000, 3, 9)
+    outs = [rt.empty(np.float64, 1, g) for g in range(G)]
+    szs = [rt.empty(np.int64, 4, g) for g in range(G)]
+    col = rt.upload(x, G - 1)
+    dummies = [rt.empty(np.float64, 1, g) for g in range(G)]
+    for g in range(G):
+        if g == G - 1:
+            rt.launch_allreduce(plan, [outs[g].ptr], [col.ptr], 0, x.size, szs[g].ptr, dev=g)
+        else:
+            rt.launch_allreduce(plan, [outs[g].ptr], [dummies[g].ptr], 0, 0, szs[g].ptr, dev=g)
+    for g in range(G):
+        assert rt.download(outs[g])[0] == x.max()
+
+
+def test_needs_a_reduction_plan(rt):
+    e = Expr(np.float32)
+    e.materialize(e.mul(e.array(), e.array()))
+    plan = abi.compile_plan(e)
+    a = rt.empty(np.float32, 16)
+    s = rt.empty(np.int64, 4)
+    rc = rt.lib.nl_launch_pipeline_allreduce(C.byref(plan), abi.void_array([a.ptr]), abi.void_array([a.ptr, a.ptr]), 0, 16,
+                                             C.c_void_p(s.ptr), 0)
+    assert rc == abi.NL_ERR_INVALID
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.float64, np.float32], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [1000, 300_001, 3_000_000])
+def test_fused_filter_scan(rt, dtype, n):
+    """a[a > t] per shard + the in-kernel exchange of the shard counts: every device must hold the
+    exclusive scan of all counts, and the shards concatenated at those offsets are the oracle's result."""
+    G = rt.n_devices
+    kind = 1 if np.dtype(dtype).kind == "i" else 3
+    x = oracle.fill(dtype, 0, n, kind, 21)
+    thr = np.dtype(dtype).type(np.sort(x)[n // 3])
+    e = Expr(dtype)
+    xa = e.array()
+    e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(thr))))
+    want = oracle.run(e, [x, None], n, thread_count=1)[0]
+    plan = abi.compile_plan(e)
+    cols, ys, szs, offs = [], [], [], []
+    for g in range(G):
+        lo, hi = shard_range(n, G, g)
+        cols.append(rt.upload(x[lo:hi], g))
+        ys.append(rt.empty(dtype, max(hi - lo, 1), g))
+        szs.append(rt.empty(np.int64, 4, g))
+        offs.append(rt.empty(np.int64, G + 1, g))
+    for g in range(G):
+        lo, hi = shard_range(n, G, g)
+        rt.launch_allgather(plan, [ys[g].ptr], [cols[g].ptr, None], 0, hi - lo, szs[g].ptr, offs[g].ptr, dev=g)
+    scans = [rt.download(offs[g]) for g in range(G)]
+    counts = [int(rt.download(szs[g], 1)[0]) for g in range(G)]
+    for g in range(G):
+        assert np.array_equal(scans[g], scans[0])
+        assert scans[0][g + 1] - scans[0][g] == counts[g]
+    assert scans[0][0] == 0 and scans[0][G] == want.size
+    got = np.concatenate([rt.download(ys[g], counts[g]) for g in range(G)])
+    assert got.tobytes() == want.tobytes()
