@@ -83,6 +83,30 @@ WORKER = textwrap.dedent("""
     # timing plumbing
     assert ranks.max(float(ranks.rank)) == 1.0 and ranks.sum(1.0) == 2.0
     assert ranks.bcast_bytes(b"id-from-rank-%%d" %% ranks.rank) == b"id-from-rank-0"
+    # NVLink mailbox handshake (host side): every rank exports a 64-byte handle, all ranks import the
+    # same rank-ordered table; a rank that cannot export keeps EVERYBODY on the NCCL finish
+    from numpyllvm_b200 import abi
+
+    class FakeLib:
+        def __init__(self, rank, can_export=True):
+            self.rank, self.can_export, self.blob, self.ready = rank, can_export, None, 0
+        def nl_comm_mailbox_export(self, dev, buf):
+            if not self.can_export:
+                return abi.NL_ERR_CUDA
+            buf.raw = bytes([self.rank + 1]) * abi.NL_MAILBOX_HANDLE_BYTES
+            return 0
+        def nl_comm_mailbox_import(self, buf):
+            self.blob = bytes(buf.raw[:2 * abi.NL_MAILBOX_HANDLE_BYTES]); self.ready = 1
+            return 0
+        def nl_comm_peer_ready(self):
+            return self.ready
+
+    lib = FakeLib(ranks.rank)
+    assert ranks.init_mailboxes(lib) is True
+    assert lib.blob == bytes([1]) * 64 + bytes([2]) * 64, "handles must arrive in rank order"
+    lib = FakeLib(ranks.rank, can_export=(ranks.rank == 0))
+    assert ranks.init_mailboxes(lib) is False and lib.blob is None
+
     ranks.finish()
     print("rank", ranks.rank, "ok")
 """) % ROOT
