@@ -495,6 +495,33 @@ def run_extra(args, rt, lib, ranks, peak, timed):
         report("C5 (a[a >= t] * k).max() fused" + (" + NCCL allreduce" if G > 1 else ""), "f32", n5, 4 * n5, ms,
                {"result": float(rt.download(res)[0])})
     x.free(); res.free()
+
+    # next row: the sort() full breaker as a device radix sort, one GPU's shard
+    if G == 1:
+        n6 = 1 << 28
+        for dt, kind, nm in ((np.int64, 1, "i64 full range"), (np.float64, 3, "f64 in [0,1)"), (np.int64, 0, "i64 in [1,100) like Tests/")):
+            x = rt.empty(dt, n6)
+            tmp = rt.empty(dt, n6)
+            best, passes = None, 0
+            for rep in range(3):
+                rt.fill(x, 0, 5 + rep, kind)
+                rt.sync()
+                l0 = lib.nl_launch_count()
+                e0, e1 = rt.event(), rt.event()
+                rt.record(e0)
+                abi.check(lib.nl_sort(0, 0, abi.nl_dtype_of(dt), C.c_void_p(x.ptr), C.c_void_p(tmp.ptr), n6))
+                rt.record(e1)
+                rt.sync()
+                ms1 = rt.elapsed_ms(e0, e1)
+                best = ms1 if best is None else min(best, ms1)
+                passes = (lib.nl_launch_count() - l0 - 1) // 3
+            head = rt.download(x, 1 << 16)
+            traffic = n6 * 8 * (1 + 3 * passes + (2 if passes % 2 else 0))     # histogram read + (count read, scatter read+write) per pass
+            out.append({"config": f"sort() device radix sort, {nm}", "dtype": np.dtype(dt).name, "elements_per_gpu": n6,
+                        "ms_per_step": round(best, 4), "Gkeys/s": round(n6 / best / 1e6, 2), "radix_passes": int(passes),
+                        "GB/s": round(traffic / best / 1e6, 1), "frac_of_measured_peak": round(traffic / best / 1e6 / peak, 4),
+                        "sorted": bool(np.all(head[:-1] <= head[1:]))})
+            x.free(); tmp.free()
     return out
 
 

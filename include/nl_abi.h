@@ -21,6 +21,7 @@
  *                                                    nl_finalize_partials()
  *   thunk_assign_subscript()     thunk_as_mapping.cpp:80  nl_assign_fill(),
  *     (NumPy setitem on storage)                     nl_assign_copy()
+ *   _thunk_sort base (NumPy)     thunk_methods.cpp:37  nl_sort()
  *   PyThunk_FromArray() copy     thunk.cpp:30        nl_memcpy_h2d()
  *   PyThunk_AsArray()            thunk.cpp:119       nl_memcpy_d2h()
  *   create_threads()/RunThread   scheduler.cpp:161,227  nl_init() (streams)
@@ -310,6 +311,12 @@ NL_API int nl_assign_copy(int dev, int stream, void *dst, int dtype,
  * 3: floats in [0,1).   */
 NL_API int nl_fill(int dev, int stream, void *dst, int dtype, int64_t first_index,
             int64_t count, uint64_t seed, int kind);
+
+/* Sort `count` keys of `dtype` on the device, ascending, NaNs last (NumPy order) — the `base`
+ * function of the sort() full breaker (PyArray_Sort on a copy, thunk_methods.cpp:37-62; run by
+ * compiler.cpp:93-122).  In place in `keys`; `tmp` is scratch of the same size.  LSD radix
+ * sort; digit positions on which all keys agree cost no pass.  Synchronises the stream once. */
+NL_API int nl_sort(int dev, int stream, int dtype, void *keys, void *tmp, int64_t count);
 
 /* ======================= communicator (NCCL over NVLink) ================== */
 

@@ -7,6 +7,7 @@
 #include "scheduler.hpp"
 #include "optimizer.hpp"
 #include "debug_printer.hpp"
+#include "device_sort.hpp"
 
 #include <cstring>
 #include <vector>
@@ -51,7 +52,23 @@ static int run_base_function(Pipeline *pipeline) {
     return -1;
   }
   DataSource *in = pipeline->inputs[0].source;
+  if (!in->storage && in->object) {
+    if (PyThunk_EnsureDevice(in->object) < 0) return -1;
+    in->storage = in->object->storage;
+    storage_incref(in->storage);
+  }
   if (!in->storage) { PyErr_SetString(PyExc_ValueError, "base function input is not evaluated"); return -1; }
+  if (top->name == "sort" && !in->storage->host_scalar && !in->storage->replicated && nljit_ensure_runtime() == 0) {
+    // sort() runs where the data lives: radix sort per GPU, sample sort across GPUs (device_sort.cpp)
+    Storage *sorted = device_sort(in->storage);
+    if (!sorted) return -1;
+    Binding &out = pipeline->outputs[0];
+    out.source->storage = sorted;                       // the pipeline's reference
+    out.source->size = (ssize_t)sorted->cardinality();
+    storage_incref(sorted);
+    PyThunk_MarkEvaluated(out.source->object, sorted);  // the thunk holds its own reference
+    return 0;
+  }
   PyObject *host = storage_to_host(in->storage);
   if (!host) return -1;
   PyObject *result = top->base(host);

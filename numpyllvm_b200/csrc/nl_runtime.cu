@@ -514,6 +514,15 @@ int nl_fill(int dev, int stream, void *dst, int dtype, int64_t first_index, int6
   return launch_fill(g_dev[dev].stream[stream], g_dev[dev].sm_count, dst, dtype, first_index, count, seed, kind);
 }
 
+int nl_sort(int dev, int stream, int dtype, void *keys, void *tmp, int64_t count) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (count < 0 || (count > 0 && (!keys || !tmp))) { set_error("nl_sort: bad argument"); return NL_ERR_INVALID; }
+  if (count <= 1) return NL_OK;
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_sort(g_dev[dev].stream[stream], g_dev[dev].sm_count, dtype, keys, tmp, count);
+}
+
 // ======================================================================= communicator
 int nl_comm_unique_id(void *id_out) {
   if (!id_out) { set_error("nl_comm_unique_id: null"); return NL_ERR_INVALID; }

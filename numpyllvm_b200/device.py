@@ -112,6 +112,13 @@ class Runtime:
         abi.check(self.lib.nl_launch_pipeline_allgather(C.byref(plan), abi.void_array(outputs), abi.void_array(inputs),
                                                         start, end, C.c_void_p(sizes_ptr), C.c_void_p(offsets_ptr), dev))
 
+    def sort(self, d: "DevArray", stream: int = 0):
+        """In-place device radix sort of a column (the sort() full breaker)."""
+        tmp = DevArray(self, d.dev, d.dtype, max(d.size, 1))
+        abi.check(self.lib.nl_sort(d.dev, stream, abi.nl_dtype_of(d.dtype), C.c_void_p(d.ptr), C.c_void_p(tmp.ptr), d.size))
+        abi.check(self.lib.nl_stream_sync(d.dev, stream))
+        tmp.free()
+
     def peer_ready(self) -> bool:
         return bool(self.lib.nl_comm_peer_ready())
 

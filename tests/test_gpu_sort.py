@@ -1,0 +1,68 @@
+"""Device radix sort (nl_sort) — the sort() full breaker — against NumPy's sort, which is what the
+reference runs (PyArray_Sort on a copy, thunk_methods.cpp:37-62).  Bit-exact for ints; floats are
+compared bit-for-bit too on data without mixed-sign zeros (NumPy leaves the relative order of
+-0.0 / +0.0 unspecified; the radix order puts -0.0 first)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from numpyllvm_b200 import abi
+from numpyllvm_b200.device import Runtime
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rt():
+    return Runtime.get()
+
+
+def dev_sort(rt, x):
+    d = rt.upload(x)
+    rt.sort(d)
+    out = rt.download(d)
+    d.free()
+    return out
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [0, 1, 2, 100, 2047, 2048, 2049, 100_003, 3_000_001])
+@pytest.mark.parametrize("kind", ["small", "full"])
+def test_sort_matches_numpy(rt, dtype, n, kind):
+    if np.dtype(dtype).kind == "i":
+        x = oracle.fill(dtype, 0, n, 0 if kind == "small" else 1, 77)     # [1,100) like the reference's tests / full range
+    else:
+        x = oracle.fill(dtype, 0, n, 2 if kind == "small" else 3, 77)
+        if kind == "full" and n:
+            x = ((x - 0.5) * np.dtype(dtype).type(1e6)).astype(dtype)     # both signs, wide exponent range
+            x[x == 0] = 1                                                 # no mixed-sign zeros
+    got = dev_sort(rt, x)
+    assert got.tobytes() == np.sort(x).tobytes()
+
+
+def test_sort_is_the_reference_test_vector(rt, golden):
+    """Tests/multiplication.py: res2 = sort(d*e*f) * (a*b*c) on the seed-42 vectors (committed golden result)."""
+    m = golden["multiplication"]
+    a, b, c, d, e, f = (np.array(m["inputs"][k], dtype=np.int64) for k in "abcdef")
+    assert np.array_equal(dev_sort(rt, d * e * f) * (a * b * c), np.array(m["res2"], dtype=np.int64))
+
+
+def test_special_floats(rt):
+    x = np.array([3.0, -np.inf, np.nan, 1.5, np.inf, -2.0, np.nan, 0.0, -1e-310, 1e-310, 7.0] * 300, dtype=np.float64)
+    got = dev_sort(rt, x)
+    want = np.sort(x)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.isnan(got[-600:]).all() and not np.isnan(got[:-600]).any()
+    neg_nan = np.array([np.nan, 1.0, -np.nan, -1.0, np.inf], dtype=np.float32)
+    neg_nan[2] = np.frombuffer(np.uint32(0xFFC00000).tobytes(), dtype=np.float32)[0]   # NaN with the sign bit set
+    got = dev_sort(rt, np.tile(neg_nan, 1000))
+    assert np.isnan(got[-2000:]).all() and got[0] == -1.0 and got[2999] == np.inf
+
+
+def test_sort_is_stable_for_equal_keys_and_handles_duplicates(rt):
+    x = np.repeat(np.arange(50, dtype=np.int64)[::-1], 4001)
+    assert np.array_equal(dev_sort(rt, x), np.sort(x))
+    x = np.full(10_000, 7, dtype=np.int32)          # every digit position is trivial: zero passes
+    assert np.array_equal(dev_sort(rt, x), x)

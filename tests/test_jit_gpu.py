@@ -185,3 +185,40 @@ def test_pinned_host_edge():
     r = (t * 2).asnumpyarray()
     assert np.array_equal(r, np.arange(n, dtype=np.float32) * 2)
     assert jit.device_count() >= 1 and jit.launch_count() > 0
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [2, 1000, 2_000_003])
+def test_sort_runs_on_the_device(dtype, n):
+    """sort() is a full breaker whose work now happens where the data lives (radix sort per GPU,
+    sample sort across GPUs); the result is a regular column that fuses with others."""
+    rng = np.random.default_rng(n)
+    if np.dtype(dtype).kind == "i":
+        a_n = rng.integers(-10**6, 10**6, n).astype(dtype)
+    else:
+        a_n = ((rng.random(n) - 0.5) * 1e4).astype(dtype)
+        a_n[a_n == 0] = 1
+    b_n = rng.integers(1, 5, n).astype(dtype)
+    a, b = jit.thunk(a_n), jit.thunk(b_n)
+    before = jit.launch_count()
+    s = a.sort()
+    r = s * b                                            # sorted column meets an unsorted one of the same length
+    assert r.asnumpyarray().tobytes() == (np.sort(a_n) * b_n).tobytes()
+    assert s.asnumpyarray().tobytes() == np.sort(a_n).tobytes()
+    assert np.array_equal(a.asnumpyarray(), a_n)         # sort() returned a copy
+    if n > 1:
+        assert jit.launch_count() - before >= 4          # histogram + at least one radix pass + the multiply
+
+
+def test_sort_of_a_filter_result_and_skewed_data():
+    n = 1_500_001
+    rng = np.random.default_rng(3)
+    a_n = rng.integers(0, 100, n)
+    a = jit.thunk(a_n)
+    f = a[a >= 50]                                       # ragged shards on several GPUs
+    assert np.array_equal(f.sort().asnumpyarray(), np.sort(a_n[a_n >= 50]))
+    skew = np.concatenate([np.zeros(n - 10, dtype=np.int64), np.arange(10, dtype=np.int64)[::-1]])
+    assert np.array_equal(jit.thunk(skew).sort().asnumpyarray(), np.sort(skew))   # almost every key equal: empty buckets
+    asc = np.arange(n, dtype=np.int64)
+    assert np.array_equal(jit.thunk(asc).sort().asnumpyarray(), asc)
+    assert np.array_equal(jit.thunk(asc[::-1].copy()).sort().asnumpyarray(), asc)
