@@ -134,6 +134,33 @@ static int execute_one(Pipeline *pipeline) {
   if (debug_plan_enabled()) PrintPlan(pipeline, &lp.plan);
 
   const int G = nljit_device_count();
+  // A ragged column (a filter result: per-shard counts) that meets a column with another layout but
+  // the same length is first re-cut into the regular partition — the reference's gather
+  // (compiler.cpp:30-49) always leaves one contiguous array, so such pipelines are legal there.
+  {
+    Storage *first = NULL;
+    bool mixed = false, same_len = true;
+    for (int k = 0; k < lp.n_inputs; k++) {
+      if (lp.inputs[k].kind != NL_IN_ARRAY) continue;
+      Storage *s = lp.input_sources[k]->storage;
+      if (!first) { first = s; continue; }
+      if (s->cardinality() != first->cardinality()) same_len = false;
+      bool same = s->shards.size() == first->shards.size();
+      for (size_t g = 0; same && g < s->shards.size(); g++) same = s->shards[g].count == first->shards[g].count;
+      if (!same) mixed = true;
+    }
+    if (mixed && same_len) {
+      for (int k = 0; k < lp.n_inputs; k++) {
+        if (lp.inputs[k].kind != NL_IN_ARRAY) continue;
+        Storage *s = lp.input_sources[k]->storage;
+        if (!s->ragged) continue;
+        Storage *r = storage_repartition(s);
+        if (!r) return -1;
+        storage_decref(s);
+        lp.input_sources[k]->storage = r;
+      }
+    }
+  }
   // shard geometry: every column of a pipeline shares one partition (compiler.cpp:413, 428)
   Storage *shape = NULL;
   for (int k = 0; k < lp.n_inputs; k++) {

@@ -222,3 +222,21 @@ def test_sort_of_a_filter_result_and_skewed_data():
     asc = np.arange(n, dtype=np.int64)
     assert np.array_equal(jit.thunk(asc).sort().asnumpyarray(), asc)
     assert np.array_equal(jit.thunk(asc[::-1].copy()).sort().asnumpyarray(), asc)
+
+
+def test_ragged_filter_result_meets_a_regular_column():
+    """With several GPUs a filter result is sharded by per-shard counts; combined with a regular
+    column of the same length it is first re-cut into the regular partition."""
+    n = 1_200_007
+    rng = np.random.default_rng(11)
+    a_n = rng.integers(0, 100, n)
+    keep = a_n[a_n >= 37]
+    w_n = rng.integers(1, 9, keep.size)
+    a, w = jit.thunk(a_n), jit.thunk(w_n)
+    f = a[a >= 37]
+    f.evaluate()
+    assert np.array_equal((f * w).asnumpyarray(), keep * w_n)
+    assert np.array_equal((w * f + f).asnumpyarray(), w_n * keep + keep)
+    g = a[a < 63]                                        # another ragged layout, different length
+    with pytest.raises(TypeError):
+        (f * g).evaluate()
