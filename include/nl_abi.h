@@ -90,6 +90,8 @@ typedef enum {
   NL_OP_MUL    = 1,  /* llvm_generate_multiply, thunk_as_number.cpp:45 (ints wrap)   */
   NL_OP_ADD    = 2,
   NL_OP_SUB    = 3,
+  NL_OP_DIV    = 4,  /* true division, float columns only (IEEE, correctly rounded)   */
+  NL_OP_FLOORDIV = 5, /* NumPy floor_divide: ints floor (x // 0 == 0), floats npy_divmod */
   /* T x T -> bool */
   NL_OP_GE     = 8,  /* llvm_generate_ge, thunk_as_number.cpp:9 (signed / ordered)   */
   NL_OP_GT     = 9,

@@ -34,12 +34,13 @@ _NL2NP = {v: k for k, v in _NP2NL.items()}
 
 # ops
 OP_INPUT, OP_MUL, OP_ADD, OP_SUB = 0, 1, 2, 3
+OP_DIV, OP_FLOORDIV = 4, 5
 OP_GE, OP_GT, OP_LE, OP_LT, OP_EQ, OP_NE = 8, 9, 10, 11, 12, 13
 OP_AND, OP_OR, OP_XOR, OP_NOT = 16, 17, 18, 19
 OP_FILTER = 24
 OP_MAX, OP_MIN, OP_SUM = 32, 33, 34
 OP_WHERE_STORE = 40
-OP_NAMES = {OP_INPUT: "in", OP_MUL: "*", OP_ADD: "+", OP_SUB: "-", OP_GE: ">=", OP_GT: ">",
+OP_NAMES = {OP_INPUT: "in", OP_MUL: "*", OP_ADD: "+", OP_SUB: "-", OP_DIV: "/", OP_FLOORDIV: "//", OP_GE: ">=", OP_GT: ">",
             OP_LE: "<=", OP_LT: "<", OP_EQ: "==", OP_NE: "!=", OP_AND: "&", OP_OR: "|",
             OP_XOR: "^", OP_NOT: "~", OP_FILTER: "[]", OP_MAX: "max", OP_MIN: "min",
             OP_SUM: "sum", OP_WHERE_STORE: "where="}
@@ -136,6 +137,8 @@ class Expr:
     def mul(self, l, r): return self.binop(OP_MUL, l, r)
     def add(self, l, r): return self.binop(OP_ADD, l, r)
     def sub(self, l, r): return self.binop(OP_SUB, l, r)
+    def div(self, l, r): return self.binop(OP_DIV, l, r)
+    def floordiv(self, l, r): return self.binop(OP_FLOORDIV, l, r)
     def ge(self, l, r): return self.binop(OP_GE, l, r)
     def gt(self, l, r): return self.binop(OP_GT, l, r)
     def le(self, l, r): return self.binop(OP_LE, l, r)

@@ -66,6 +66,39 @@ static PyObject *lazy_binary(PyObject *v, PyObject *w, int opcode, const char *o
 static PyObject *thunk_lazymultiply(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_MUL, "*"); }
 static PyObject *thunk_lazyadd(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_ADD, "+"); }
 static PyObject *thunk_lazysubtract(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_SUB, "-"); }
+// Division is not in the reference.  `/` exists for float thunks only — NumPy's int / int
+// is a float and this engine keeps the left operand's dtype (Q3); `//` is NumPy's floor_divide.
+static PyObject *thunk_lazytruedivide(PyObject *v, PyObject *w) {
+  PyObject *r = lazy_binary(v, w, NL_OP_DIV, "/");
+  if (r && r != Py_NotImplemented) {
+    const int t = ((PyThunkObject *)r)->npy_type;
+    if (t != NPY_FLOAT32 && t != NPY_FLOAT64) {
+      Py_DECREF(r);
+      PyErr_SetString(PyExc_TypeError, "true division of integer thunks would change the dtype; use // or convert to float first");
+      return NULL;
+    }
+  }
+  return r;
+}
+static PyObject *thunk_lazyfloordivide(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_FLOORDIV, "//"); }
+// -a == a * (-1): exact for floats (sign flip, also of zeros) and wrapping for ints like NumPy
+static PyObject *thunk_lazynegative(PyObject *v) {
+  PyThunkObject *l = (PyThunkObject *)v;
+  if (l->npy_type == NPY_BOOL) {
+    PyErr_SetString(PyExc_TypeError, "unary - is not defined on boolean thunks (use ~)");
+    return NULL;
+  }
+  npy_intp one = 1;
+  PyObject *m = PyArray_SimpleNew(1, &one, l->npy_type);
+  if (!m) return NULL;
+  PyObject *minus_one = PyLong_FromLong(-1);
+  const int rc = minus_one ? PyArray_SETITEM((PyArrayObject *)m, (char *)PyArray_DATA((PyArrayObject *)m), minus_one) : -1;
+  Py_XDECREF(minus_one);
+  if (rc < 0) { Py_DECREF(m); return NULL; }
+  PyObject *r = lazy_binary(v, m, NL_OP_MUL, "neg");
+  Py_DECREF(m);
+  return r;
+}
 
 PyObject *PyThunk_LazyRichCompare(PyObject *self, PyObject *other, int cmp_op) {
   if (!PyThunk_Check(self)) {
@@ -133,7 +166,7 @@ PyNumberMethods thunk_as_number = {
     0,                               /* nb_remainder */
     0,                               /* nb_divmod */
     0,                               /* nb_power */
-    0,                               /* nb_negative */
+    (unaryfunc)thunk_lazynegative,   /* nb_negative */
     0,                               /* nb_positive */
     0,                               /* nb_absolute */
     0,                               /* nb_bool */
@@ -143,4 +176,10 @@ PyNumberMethods thunk_as_number = {
     (binaryfunc)thunk_lazyand,       /* nb_and */
     (binaryfunc)thunk_lazyxor,       /* nb_xor */
     (binaryfunc)thunk_lazyor,        /* nb_or */
+    0,                               /* nb_int */
+    0,                               /* nb_reserved */
+    0,                               /* nb_float */
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0,    /* nb_inplace_add .. nb_inplace_or */
+    (binaryfunc)thunk_lazyfloordivide,  /* nb_floor_divide */
+    (binaryfunc)thunk_lazytruedivide,   /* nb_true_divide */
 };

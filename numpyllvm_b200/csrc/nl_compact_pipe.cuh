@@ -128,7 +128,16 @@ template <typename T>
 __device__ __forceinline__ void sparse_step(const KParams &p, uint32_t op, uint32_t a, uint32_t b, T &v, long long pos) {
   if (op == S_BIN) {
     const T sc = (p.in_kind[b] == NL_IN_SCALAR_IMM) ? from_bits<T>(p.imm[b]) : *reinterpret_cast<const T *>(p.in[b]);
-    v = (a == V_MUL) ? op_mul<T>(v, sc) : (a == V_ADD) ? op_add<T>(v, sc) : (a == V_SUB) ? op_sub<T>(v, sc) : op_sub<T>(sc, v);
+    switch (a) {
+      case V_MUL: v = op_mul<T>(v, sc); break;
+      case V_ADD: v = op_add<T>(v, sc); break;
+      case V_SUB: v = op_sub<T>(v, sc); break;
+      case V_RSUB: v = op_sub<T>(sc, v); break;
+      case V_DIV: v = op_div<T>(v, sc); break;
+      case V_RDIV: v = op_div<T>(sc, v); break;
+      case V_FDIV: v = op_floordiv<T>(v, sc); break;
+      default: v = op_floordiv<T>(sc, v); break;
+    }
   } else if (op == S_STORE) {
     reinterpret_cast<T *>(p.out[a])[pos] = v;
   }

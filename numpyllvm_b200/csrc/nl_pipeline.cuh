@@ -74,6 +74,33 @@ template <typename T> __device__ __forceinline__ T op_add(T a, T b) {
 template <typename T> __device__ __forceinline__ T op_sub(T a, T b) {
   if constexpr (TT<T>::is_float) return a - b; else return (T)((typename TT<T>::U)a - (typename TT<T>::U)b);
 }
+// true division: floats only (the plan compiler rejects integer columns); IEEE, correctly rounded
+template <typename T> __device__ __forceinline__ T op_div(T a, T b) {
+  if constexpr (TT<T>::is_float) return a / b; else return T(0);
+}
+// NumPy floor_divide.  Ints: rounds towards -inf, x // 0 == 0, INT_MIN // -1 wraps.  Floats: npy_divmod
+// (fmod-based, so the quotient is exact where a / b would round to the wrong side of an integer).
+template <typename T> __device__ __forceinline__ T op_floordiv(T a, T b) {
+  if constexpr (TT<T>::is_float) {
+    if (b == T(0)) return a / b;
+    T mod = fmod(a, b);
+    T div = (a - mod) / b;
+    if (mod != T(0) && ((b < T(0)) != (mod < T(0)))) div -= T(1);
+    if (div != T(0)) {
+      T fl = floor(div);
+      if (div - fl > T(0.5)) fl += T(1);
+      return fl;
+    }
+    return copysign(T(0), a / b);
+  } else {
+    using U = typename TT<T>::U;
+    if (b == T(0)) return T(0);
+    if (b == T(-1)) return (T)((U)0 - (U)a);
+    T q = a / b;
+    if ((a % b != T(0)) && ((a < T(0)) != (b < T(0)))) q -= T(1);
+    return q;
+  }
+}
 // max/min with NumPy semantics: NaN is sticky
 template <typename T> __device__ __forceinline__ T op_max(T cur, T l) {
   if constexpr (TT<T>::is_float) return (l > cur || l != l) ? l : cur; else return l > cur ? l : cur;
@@ -482,9 +509,25 @@ struct Tile {
 #pragma unroll
         for (int e = 0; e < E; e++) acc[e] = op_sub<T>(acc[e], x(e));
         break;
-      default:
+      case V_RSUB:
 #pragma unroll
         for (int e = 0; e < E; e++) acc[e] = op_sub<T>(x(e), acc[e]);
+        break;
+      case V_DIV:
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e] = op_div<T>(acc[e], x(e));
+        break;
+      case V_RDIV:
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e] = op_div<T>(x(e), acc[e]);
+        break;
+      case V_FDIV:
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e] = op_floordiv<T>(acc[e], x(e));
+        break;
+      default:
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e] = op_floordiv<T>(x(e), acc[e]);
         break;
     }
   }

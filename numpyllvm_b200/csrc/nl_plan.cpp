@@ -23,7 +23,7 @@ void set_error(const char *fmt, ...) {
 
 static bool is_cmp(int op) { return op >= NL_OP_GE && op <= NL_OP_NE; }
 static bool is_boolop(int op) { return op >= NL_OP_AND && op <= NL_OP_NOT; }
-static bool is_vop(int op) { return op == NL_OP_MUL || op == NL_OP_ADD || op == NL_OP_SUB; }
+static bool is_vop(int op) { return op == NL_OP_MUL || op == NL_OP_ADD || op == NL_OP_SUB || op == NL_OP_DIV || op == NL_OP_FLOORDIV; }
 static bool is_reduce(int op) { return op == NL_OP_MAX || op == NL_OP_MIN || op == NL_OP_SUM; }
 
 struct Lower {
@@ -171,6 +171,8 @@ struct Lower {
     switch (op) {
       case NL_OP_MUL: return V_MUL;
       case NL_OP_ADD: return V_ADD;
+      case NL_OP_DIV: return reversed ? V_RDIV : V_DIV;
+      case NL_OP_FLOORDIV: return reversed ? V_RFDIV : V_FDIV;
       default: return reversed ? V_RSUB : V_SUB;
     }
   }
@@ -215,6 +217,10 @@ struct Lower {
     if (nd.op == NL_OP_INPUT) {
       gen_leaf_value(n);
     } else if (is_vop(nd.op)) {
+      if (nd.op == NL_OP_DIV && plan->dtype != NL_F32 && plan->dtype != NL_F64) {
+        fail(NL_ERR_UNSUPPORTED, "true division of integer columns yields floats (no dtype promotion): use floor division");
+        return;
+      }
       uint32_t src; bool rev; int tf;
       gen_operands(nd.lhs, nd.rhs, &src, &rev, &tf);
       emit(make_step(S_BIN, vop_of(nd.op, rev), src));

@@ -40,7 +40,8 @@ enum StepOp : uint32_t {
   S_WHERE  = 15   // a = output o                if (pacc) out[o][i] <- acc
 };
 
-enum VOp : uint32_t { V_MUL = 0, V_ADD = 1, V_SUB = 2, V_RSUB = 3 };           // RSUB: X - acc
+enum VOp : uint32_t { V_MUL = 0, V_ADD = 1, V_SUB = 2, V_RSUB = 3,              // RSUB: X - acc
+                      V_DIV = 4, V_RDIV = 5, V_FDIV = 6, V_RFDIV = 7 };         // true / floor division, R: X op acc
 enum COp : uint32_t { C_GE = 0, C_GT = 1, C_LE = 2, C_LT = 3, C_EQ = 4, C_NE = 5 };
 enum POp : uint32_t { P_AND = 0, P_OR = 1, P_XOR = 2 };
 enum ROp : uint32_t { R_MAX = 0, R_MIN = 1, R_SUM = 2 };

@@ -399,3 +399,65 @@ def test_large_filter_and_reduce(rt, dtype):
     e = Expr(dtype)
     e.materialize(e.max(e.array()))
     assert_same(oracle.run(e, [x], n, n_workers=8), run_pipeline(rt, e, [x], n))
+
+
+# ---- division (extension on the operator slots) -----------------------------
+def assert_same_up_to_nan_payload(ref, got):
+    """Bit-exact, except that a NaN CREATED by an operation (0/0, inf - inf) carries the host's
+    default payload on x86 (0xFFC00000) and the GPU's canonical one (0x7FFFFFFF): where the oracle has
+    a NaN the kernel must have a NaN; every other element must match bitwise."""
+    assert len(ref) == len(got)
+    for r, g in zip(ref, got):
+        assert r.dtype == g.dtype and r.shape == g.shape
+        if r.dtype.kind != "f":
+            assert np.array_equal(r, g)
+            continue
+        nan = np.isnan(r)
+        assert np.array_equal(nan, np.isnan(g)), "NaN positions differ"
+        u = np.uint32 if r.dtype.itemsize == 4 else np.uint64
+        assert np.array_equal(r.view(u)[~nan], g.view(u)[~nan]), "outputs differ bitwise"
+
+
+def _div_columns(dtype, n):
+    rng = np.random.default_rng(12)
+    if np.dtype(dtype).kind == "i":
+        info = np.iinfo(dtype)
+        a = rng.integers(-1000, 1000, n).astype(dtype)
+        b = rng.integers(-9, 10, n).astype(dtype)
+        a[:4] = [info.min, info.min, info.max, 0]
+        b[:4] = [-1, 1, -1, 0]
+    else:
+        a = ((rng.random(n) - 0.5) * 100).astype(dtype)
+        b = ((rng.random(n) - 0.5) * 7).astype(dtype)
+        a[:12] = [1.0, -1.0, 0.0, -0.0, 7.5, np.inf, np.nan, 1e30, 0.3, 0.9, 6.0, -6.0]
+        b[:12] = [0.0, 0.0, 0.0, 3.0, -2.5, 2.0, 1.0, 1e-30, 0.1, 0.3, 0.1, 0.1]
+    return a, b
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1000, 300_001])
+def test_floor_division(rt, dtype, n):
+    a, b = _div_columns(dtype, n)
+    e = Expr(dtype)
+    e.materialize(e.floordiv(e.array(), e.array()))
+    assert_same_up_to_nan_payload(*both(rt, e, [a, b], n))
+    k = np.dtype(dtype).type(-3)
+    e = Expr(dtype)
+    e.materialize(e.floordiv(e.array(), e.scalar(k)))
+    assert_same_up_to_nan_payload(*both(rt, e, [a, None], n))
+    e = Expr(dtype)
+    e.materialize(e.add(e.floordiv(e.scalar(k), e.array()), e.scalar(np.dtype(dtype).type(1))))
+    assert_same_up_to_nan_payload(*both(rt, e, [None, b, None], n))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_true_division(rt, dtype):
+    n = 300_001
+    a, b = _div_columns(dtype, n)
+    e = Expr(dtype)
+    e.materialize(e.div(e.array(), e.array()))
+    assert_same_up_to_nan_payload(*both(rt, e, [a, b], n))
+    e = Expr(dtype)
+    xa = e.array()
+    e.materialize(e.filter(e.div(e.scalar(np.dtype(dtype).type(1)), xa), e.gt(e.ref(xa), e.scalar(np.dtype(dtype).type(0)))))
+    assert_same_up_to_nan_payload(*both(rt, e, [a, None, None], n))          # 1/a where a > 0: division before a compaction

@@ -240,3 +240,29 @@ def test_ragged_filter_result_meets_a_regular_column():
     g = a[a < 63]                                        # another ragged layout, different length
     with pytest.raises(TypeError):
         (f * g).evaluate()
+
+
+def test_division_and_negation():
+    rng = np.random.default_rng(5)
+    n = 100_003
+    a_n = rng.integers(-1000, 1000, n)
+    b_n = rng.integers(-9, 10, n)
+    a, b = jit.thunk(a_n), jit.thunk(b_n)
+    with np.errstate(all="ignore"):
+        assert np.array_equal((a // b).asnumpyarray(), a_n // b_n)            # x // 0 == 0 like NumPy
+        assert np.array_equal((a // 7).asnumpyarray(), a_n // 7)
+        assert np.array_equal((1000 // b).asnumpyarray(), 1000 // b_n)
+    assert np.array_equal((-a).asnumpyarray(), -a_n)
+    assert np.array_equal((-(a * b) + a).asnumpyarray(), -(a_n * b_n) + a_n)
+    with pytest.raises(TypeError):
+        a / b                                                                  # int / int would change the dtype
+    x_n = (rng.random(n) - 0.5) * 10
+    y_n = (rng.random(n) - 0.5) * 3
+    x, y = jit.thunk(x_n), jit.thunk(y_n)
+    assert (x / y).asnumpyarray().tobytes() == (x_n / y_n).tobytes()
+    assert (x / 3.0).asnumpyarray().tobytes() == (x_n / 3.0).tobytes()
+    assert (2.0 / y).asnumpyarray().tobytes() == (2.0 / y_n).tobytes()
+    assert np.array_equal((x // y).asnumpyarray(), x_n // y_n)
+    assert (-x).asnumpyarray().tobytes() == (-x_n).tobytes()
+    with pytest.raises(TypeError):
+        -(a > 3)

@@ -295,3 +295,57 @@ def test_fast_loops_match_generic_oracle():
     e.materialize(e.max(e.mul(e.filter(xa, e.ge(e.ref(xa), e.scalar(0.25))), e.scalar(3.0))))
     (m,) = oracle.run(e, [xf, None, None], n)
     assert oracle.fast_filter_mul_max_f32(xf, 0.25, 3.0) == m[0] == (xf[xf >= 0.25] * np.float32(3.0)).max()
+
+
+# ---- division and negation: extensions on the operator slots, pinned by NumPy -----
+def _div_columns(dtype, n=4001):
+    rng = np.random.default_rng(12)
+    if np.dtype(dtype).kind == "i":
+        info = np.iinfo(dtype)
+        a = rng.integers(-1000, 1000, n).astype(dtype)
+        b = rng.integers(-9, 10, n).astype(dtype)          # contains zeros
+        a[:4] = [info.min, info.min, info.max, 0]
+        b[:4] = [-1, 1, -1, 0]
+    else:
+        a = ((rng.random(n) - 0.5) * 100).astype(dtype)
+        b = ((rng.random(n) - 0.5) * 7).astype(dtype)
+        a[:8] = [1.0, -1.0, 0.0, -0.0, 7.5, np.inf, np.nan, 1e30]
+        b[:8] = [0.0, 0.0, 0.0, 3.0, -2.5, 2.0, 1.0, 1e-30]
+        a[8:12] = [0.3, 0.9, 6.0, -6.0]
+        b[8:12] = [0.1, 0.3, 0.1, 0.1]                      # quotients that round onto an integer
+    return a, b
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+def test_floor_division_is_numpy_floor_divide(dtype):
+    a, b = _div_columns(dtype)
+    e = Expr(dtype)
+    e.materialize(e.floordiv(e.array(), e.array()))
+    (got,) = oracle.run(e, [a, b], a.size)
+    with np.errstate(all="ignore"):
+        want = np.floor_divide(a, b)
+    assert np.array_equal(got, want, equal_nan=np.dtype(dtype).kind == "f")
+    # scalar on either side (the plan compiler reverses the operands)
+    for k in (3, -4):
+        e = Expr(dtype)
+        e.materialize(e.floordiv(e.array(), e.scalar(np.dtype(dtype).type(k))))
+        e2 = Expr(dtype)
+        e2.materialize(e2.floordiv(e2.scalar(np.dtype(dtype).type(k)), e2.array()))
+        with np.errstate(all="ignore"):
+            assert np.array_equal(oracle.run(e, [a, None], a.size)[0], np.floor_divide(a, np.dtype(dtype).type(k)), equal_nan=True)
+            assert np.array_equal(oracle.run(e2, [None, b], b.size)[0], np.floor_divide(np.dtype(dtype).type(k), b), equal_nan=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+def test_true_division_is_ieee(dtype):
+    a, b = _div_columns(dtype)
+    e = Expr(dtype)
+    e.materialize(e.div(e.array(), e.array()))
+    (got,) = oracle.run(e, [a, b], a.size)
+    with np.errstate(all="ignore"):
+        want = a / b
+    assert got.tobytes() == want.tobytes() or np.array_equal(got, want, equal_nan=True)
+    with pytest.raises(Exception):
+        ei = Expr(np.int64)
+        ei.materialize(ei.div(ei.array(), ei.array()))
+        abi.compile_plan(ei)                               # int / int would be a float: rejected
