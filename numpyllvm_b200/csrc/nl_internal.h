@@ -53,7 +53,11 @@ constexpr int kRows = 4;          // U: vectors per thread per tile
 #endif
 constexpr int kMinBlocksCompact = 4;  // resident CTAs per SM of the build-time compaction shapes
 constexpr int kRowsCompact = 8;   // U of the build-time compaction shapes
-constexpr int kMinBlocks = 2;     // resident CTAs per SM the register allocation must allow
+#ifndef NL_MIN_BLOCKS
+#define NL_MIN_BLOCKS 2
+#endif
+constexpr int kMinBlocksLight = 3; // ... of the interpreter variant without value temporaries
+constexpr int kMinBlocks = NL_MIN_BLOCKS;     // resident CTAs per SM the register allocation must allow
 
 struct LaunchInfo {
   char kernel[96];

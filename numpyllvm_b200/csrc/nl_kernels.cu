@@ -121,26 +121,31 @@ __global__ void __launch_bounds__(256) fill_kernel(T *__restrict__ dst, int64_t 
 template <> struct TT<unsigned char> { static constexpr bool is_float = false; };
 
 // ------------------------------------------------------------------ host-side dispatch
-template <typename T>
+template <typename T, class Prog>
 static pipeline_fn pick_T(bool vec16, bool compact, bool reduce) {
   constexpr int V16 = 16 / sizeof(T);
   if (vec16) {
-    if (compact) return reduce ? pipeline_kernel<T, V16, kRows, true, true, DynProg> : pipeline_kernel<T, V16, kRows, true, false, DynProg>;
-    return reduce ? pipeline_kernel<T, V16, kRows, false, true, DynProg> : pipeline_kernel<T, V16, kRows, false, false, DynProg>;
+    if (compact) return reduce ? pipeline_kernel<T, V16, kRows, true, true, Prog> : pipeline_kernel<T, V16, kRows, true, false, Prog>;
+    return reduce ? pipeline_kernel<T, V16, kRows, false, true, Prog> : pipeline_kernel<T, V16, kRows, false, false, Prog>;
   }
-  if (compact) return reduce ? pipeline_kernel<T, 1, kRows, true, true, DynProg> : pipeline_kernel<T, 1, kRows, true, false, DynProg>;
-  return reduce ? pipeline_kernel<T, 1, kRows, false, true, DynProg> : pipeline_kernel<T, 1, kRows, false, false, DynProg>;
+  if (compact) return reduce ? pipeline_kernel<T, 1, kRows, true, true, Prog> : pipeline_kernel<T, 1, kRows, true, false, Prog>;
+  return reduce ? pipeline_kernel<T, 1, kRows, false, true, Prog> : pipeline_kernel<T, 1, kRows, false, false, Prog>;
 }
 
-// the dynamic interpreter for (dtype, row width, mode)
-static pipeline_fn pick_dynamic(int dtype, bool vec16, bool compact, bool reduce) {
+// the dynamic interpreter for (dtype, row width, mode); plans that never save a value temporary
+// take the light variant (fewer registers, one more resident CTA per SM: measured +10-17 %)
+template <class Prog>
+static pipeline_fn pick_dynamic_P(int dtype, bool vec16, bool compact, bool reduce) {
   switch (dtype) {
-    case NL_I32: return pick_T<int32_t>(vec16, compact, reduce);
-    case NL_I64: return pick_T<long long>(vec16, compact, reduce);
-    case NL_F32: return pick_T<float>(vec16, compact, reduce);
-    case NL_F64: return pick_T<double>(vec16, compact, reduce);
+    case NL_I32: return pick_T<int32_t, Prog>(vec16, compact, reduce);
+    case NL_I64: return pick_T<long long, Prog>(vec16, compact, reduce);
+    case NL_F32: return pick_T<float, Prog>(vec16, compact, reduce);
+    case NL_F64: return pick_T<double, Prog>(vec16, compact, reduce);
   }
   return nullptr;
+}
+static pipeline_fn pick_dynamic(int dtype, bool vec16, bool compact, bool reduce, bool uses_temps) {
+  return uses_temps ? pick_dynamic_P<DynProg>(dtype, vec16, compact, reduce) : pick_dynamic_P<DynProgLight>(dtype, vec16, compact, reduce);
 }
 
 // kernel-template selection: a build-time instantiation when the plan's step sequence is in
@@ -169,7 +174,7 @@ static pipeline_fn pick(const nl_plan *plan, bool vec16, const char **static_nam
   const bool reduce = (plan->flags & NL_PLAN_HAS_REDUCE) != 0;
   const StaticEntry *e = find_static(plan, vec16);
   if (static_name) *static_name = e ? e->name : nullptr;
-  return e ? e->fn : pick_dynamic(plan->dtype, vec16, compact, reduce);
+  return e ? e->fn : pick_dynamic(plan->dtype, vec16, compact, reduce, plan->n_temps > 0);
 }
 
 static const char *dt_name(int d) {
@@ -293,7 +298,8 @@ int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t
   const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
   if (name && name_len) {
     if (sname) snprintf(name, name_len, "pipeline_kernel<%s,V=%d,static:%s>", dt_name(plan->dtype), v, sname);
-    else snprintf(name, name_len, "pipeline_kernel<%s,V=%d,compact=%d,reduce=%d,dynamic>", dt_name(plan->dtype), v, (int)compact, (int)reduce);
+    else snprintf(name, name_len, "pipeline_kernel<%s,V=%d,compact=%d,reduce=%d,dynamic%s>", dt_name(plan->dtype), v, (int)compact, (int)reduce,
+                  plan->n_temps > 0 ? "" : "-light");
   }
   if (is_static) *is_static = sname != nullptr;
   return NL_OK;

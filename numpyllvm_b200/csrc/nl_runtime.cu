@@ -423,6 +423,7 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
   kp.end = end;
   kp.out_sizes = output_sizes;
   kp.n_steps = plan->n_steps;
+  kp.n_inputs = plan->n_inputs;
   kp.n_outputs = plan->n_outputs;
   kp.thread_nr = thread_nr;
   memcpy(kp.step, plan->step, sizeof(uint32_t) * (size_t)plan->n_steps);

@@ -209,4 +209,10 @@ def test_benchmark_shapes_resolve_to_build_time_kernels():
     assert not is_static and "dynamic" in name
     # scalar rows (misaligned operands) always use the interpreter
     e = Expr(np.float32); e.materialize(e.mul(e.array(), e.array()))
-    assert abi.plan_kernel(abi.compile_plan(e), vec16=False) == ("pipeline_kernel<f32,V=1,compact=0,reduce=0,dynamic>", False)
+    # ... the light variant when the plan has no value temporary, the general one otherwise
+    assert abi.plan_kernel(abi.compile_plan(e), vec16=False) == ("pipeline_kernel<f32,V=1,compact=0,reduce=0,dynamic-light>", False)
+    e = Expr(np.float32); a, b, c, d = (e.array() for _ in range(4)); e.materialize(e.add(e.mul(a, b), e.mul(c, d)))
+    assert abi.plan_kernel(abi.compile_plan(e), vec16=True) == ("pipeline_kernel<f32,V=4,compact=0,reduce=0,dynamic>", False)
+    # a column read twice is not parked in a temporary when that would be the plan's only one
+    e = Expr(np.float32); x = e.array(); e.materialize(e.mul(e.add(e.ref(x), e.scalar(np.float32(1))), e.ref(x)))
+    assert abi.compile_plan(e).n_temps == 0
