@@ -177,6 +177,7 @@ def run_gpu(args):
     t1 = time.time()
     gpu_launches = lib.nl_launch_count() - launches_warm
     clocks = sampler.summary(t0, t1)
+    sampler.stop()                              # nvidia-smi polling perturbs latency-sensitive kernels: headline region only
     alg_bytes = 12 * n + 4                     # 2 f32 reads + 1 f32 write per element + the 4-byte update
     value = G * alg_bytes * K / (ms_total * 1e-3) / 1e9
     kern_ms = statistics.mean(launch_ms)
@@ -358,9 +359,9 @@ def run_extra(args, rt, lib, ranks, peak, timed):
     from numpyllvm_b200.abi import Expr
     G, rank = ranks.world, ranks.rank
     out = []
-    # sharded configs run 0.2-0.4 ms per step: a longer warm-up keeps the allocation pause before each
-    # config (clocks ramp down) out of the 20 timed steps
-    k, w = max(3, min(args.steps, 20)), (3 if G == 1 else 25)
+    # the configs run 0.1-3 ms per step: a long warm-up keeps the allocation pause before each config
+    # (clocks ramp down, the pool maps fresh pages) out of the 20 timed steps
+    k, w = max(3, min(args.steps, 20)), 25
     sizes = rt.empty(np.int64, 4)
     fused = rt.peer_ready()                     # NVLink mailboxes exchanged: reductions finish inside their kernel
 

@@ -52,6 +52,7 @@ constexpr int kRows = 4;          // U: vectors per thread per tile
 #define NL_DESC_STRIDE 16          // 8-byte words between consecutive tile descriptors (16 = one per 128-byte line)
 #endif
 constexpr int kMinBlocksCompact = 4;  // resident CTAs per SM of the build-time compaction shapes
+constexpr int kRowsStream = 8;    // U of the build-time elementwise / reduction shapes
 constexpr int kRowsCompact = 8;   // U of the build-time compaction shapes
 #ifndef NL_MIN_BLOCKS
 #define NL_MIN_BLOCKS 2
@@ -82,6 +83,7 @@ int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t
 void set_static_kernels_enabled(int on);
 void set_compact_pipe_enabled(int on);
 void set_compact_pipe_side(int on);
+void set_max_ctas_per_sm(int n);
 void set_compact_pipe_lag(int l);
 
 void count_launch(int n = 1);

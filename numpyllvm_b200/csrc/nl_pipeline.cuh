@@ -80,7 +80,9 @@ template <typename T> __device__ __forceinline__ T op_div(T a, T b) {
 }
 // NumPy floor_divide.  Ints: rounds towards -inf, x // 0 == 0, INT_MIN // -1 wraps.  Floats: npy_divmod
 // (fmod-based, so the quotient is exact where a / b would round to the wrong side of an integer).
-template <typename T> __device__ __forceinline__ T op_floordiv(T a, T b) {
+// (not inlined: fmod and 64-bit integer division are long sequences, and the interpreter would
+// otherwise carry 64 unrolled copies of them)
+template <typename T> __device__ __noinline__ T op_floordiv(T a, T b) {
   if constexpr (TT<T>::is_float) {
     if (b == T(0)) return a / b;
     T mod = fmod(a, b);

@@ -31,6 +31,7 @@ template <uint32_t... S> constexpr bool has_compact() {
   return (((step_op(S) == S_STORE || step_op(S) == S_PSTORE) && step_b(S) == NL_IDX_COMPACT) || ...);
 }
 template <uint32_t... S> constexpr bool has_reduce() { return ((step_op(S) == S_REDUCE) || ...); }
+template <uint32_t... S> constexpr bool has_filter() { return ((step_op(S) == S_FILTER) || ...); }
 // a shape that re-reads a value temporary keeps a second register set alive: 4 rows, not 8
 template <uint32_t... S> constexpr bool reads_temp() {
   return ((step_op(S) == S_LOADT || ((step_op(S) == S_BIN || step_op(S) == S_CMP) && (step_b(S) & SRC_TEMP))) || ...);
@@ -41,6 +42,10 @@ template <typename T, uint32_t... S> struct PipeFor<T, true, S...> {
   static constexpr pipeline_fn fn = &compact_pipe_kernel<T, 16 / sizeof(T), StaticSplit<S...>>;
 };
 template <uint32_t... S> constexpr int rows_for() {
+  // eight 16-byte rows per thread for the streaming shapes too (twice the loads in flight per
+  // thread at 2 CTAs/SM: C1 +2 %, C3 +1 %, C2 +0.5 % over four rows at 3-5 CTAs/SM)
+  // (not the filter-then-reduce shapes: their keep masks push them over the register budget, C5 -12 %)
+  if (!has_compact<S...>() && !has_filter<S...>()) return kRowsStream;
   return (has_compact<S...>() && !reads_temp<S...>()) ? kRowsCompact : kRows;
 }
 }  // namespace sp
