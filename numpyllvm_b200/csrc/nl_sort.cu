@@ -160,14 +160,17 @@ __global__ void __launch_bounds__(kSortBlock) scatter_kernel(const UK *__restric
       key[i] = ok ? in[base + e] : (UK)0;
       dig[i] = ok ? (int)((order_key<UK, kFloat>(key[i]) >> shift) & 0xff) : -1;
     }
+    // the matches do not depend on the counters: issue all of them first so their latency overlaps
+    unsigned int peers[kSortItems];
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) peers[i] = __match_any_sync(0xffffffffu, dig[i] >= 0 ? dig[i] : (0x100 | lane));
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
-      const unsigned int peers = __match_any_sync(0xffffffffu, dig[i] >= 0 ? dig[i] : (0x100 | lane));
       unsigned int before = 0;
       if (dig[i] >= 0) before = cnt[warp][dig[i]];
       __syncwarp();
-      rank[i] = before + __popc(peers & lt);
-      if (dig[i] >= 0 && (peers & lt) == 0) cnt[warp][dig[i]] = before + __popc(peers);
+      rank[i] = before + __popc(peers[i] & lt);
+      if (dig[i] >= 0 && (peers[i] & lt) == 0) cnt[warp][dig[i]] = before + __popc(peers[i]);
       __syncwarp();
     }
     __syncthreads();
