@@ -13,7 +13,7 @@ for the reference's `import jit`.
 import importlib
 import sys
 
-__all__ = ["abi", "install_jit_alias"]
+__all__ = ["abi", "install_jit_alias", "device_shards", "DeviceShard"]
 
 
 def install_jit_alias():
@@ -21,3 +21,24 @@ def install_jit_alias():
     mod = importlib.import_module("numpyllvm_b200.jit")
     sys.modules.setdefault("jit", mod)
     return mod
+
+
+class DeviceShard:
+    """One shard of an evaluated thunk where it lives: exposes ``__cuda_array_interface__`` (v3), so
+    ``torch.as_tensor(shard, device=f"cuda:{shard.device}")`` / ``cupy.asarray(shard)`` see the data
+    without a copy.  Keeps the thunk alive; the memory is the thunk's own storage (do not assign to
+    the thunk while a view is in use)."""
+
+    def __init__(self, owner, device, ptr, start, count, typestr):
+        self.owner, self.device, self.start, self.count = owner, device, start, count
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+    def __len__(self):
+        return self.count
+
+
+def device_shards(thunk):
+    """Evaluate `thunk` and return its shards as DeviceShard views, in global index order
+    (the host<->device edge of SURVEY 8f-3: results can stay on the GPUs)."""
+    return [DeviceShard(thunk, *t) for t in thunk.device_shards()]

@@ -70,6 +70,38 @@ static PyObject *_thunk_max(PyThunkObject *self, PyObject *unused) { (void)unuse
 static PyObject *_thunk_min(PyThunkObject *self, PyObject *unused) { (void)unused; return lazy_reduce(self, NL_OP_MIN, "min"); }
 static PyObject *_thunk_sum(PyThunkObject *self, PyObject *unused) { (void)unused; return lazy_reduce(self, NL_OP_SUM, "sum"); }
 
+// Host<->device edge: where the evaluated data lives, so a consumer can keep working
+// on the GPUs instead of paying the D2H copy of asnumpyarray().  One (device, pointer, first global
+// index, count, typestr) tuple per shard; the pointers stay valid while the thunk is alive and is
+// not assigned to.  numpyllvm_b200.device_shards() wraps them as __cuda_array_interface__ objects.
+static PyObject *_thunk_device_shards(PyThunkObject *self, PyObject *args) {
+  (void)args;
+  if (PyThunk_Evaluate(self) == NULL) return NULL;
+  if (PyThunk_EnsureDevice(self) < 0) return NULL;
+  Storage *s = self->storage;
+  if (!s || s->host_scalar) {
+    PyErr_SetString(PyExc_ValueError, "a size-1 thunk made from host data has no device buffer");
+    return NULL;
+  }
+  const char *typestr = s->dtype == NL_I32 ? "<i4" : s->dtype == NL_I64 ? "<i8" : s->dtype == NL_F32 ? "<f4"
+                        : s->dtype == NL_F64 ? "<f8" : "|b1";
+  int rc = NL_OK;
+  Py_BEGIN_ALLOW_THREADS
+  for (int g = 0; g < nljit_device_count() && rc == NL_OK; g++) rc = nl_stream_sync(g, 0);
+  Py_END_ALLOW_THREADS
+  if (rc != NL_OK) { nljit_raise(rc, "jit: device synchronisation failed"); return NULL; }
+  PyObject *list = PyList_New(0);
+  if (!list) return NULL;
+  for (const Shard &sh : s->shards) {
+    if (s->replicated && sh.dev != 0) continue;          // an allreduced scalar is the same everywhere
+    PyObject *t = Py_BuildValue("(iKLLs)", sh.dev, (unsigned long long)(uintptr_t)sh.ptr, (long long)sh.start,
+                                (long long)(s->replicated ? 1 : sh.count), typestr);
+    if (!t || PyList_Append(list, t) < 0) { Py_XDECREF(t); Py_DECREF(list); return NULL; }
+    Py_DECREF(t);
+  }
+  return list;
+}
+
 struct PyMethodDef thunk_methods[] = {
     {"evaluate", (PyCFunction)_thunk_evaluate, METH_NOARGS, "evaluate() => "},
     {"isevaluated", (PyCFunction)_thunk_isevaluated, METH_NOARGS, "isevaluated() => "},
@@ -78,5 +110,7 @@ struct PyMethodDef thunk_methods[] = {
     {"max", (PyCFunction)_thunk_max, METH_NOARGS, "max() => "},
     {"min", (PyCFunction)_thunk_min, METH_NOARGS, "min() => "},
     {"sum", (PyCFunction)_thunk_sum, METH_NOARGS, "sum() => "},
+    {"device_shards", (PyCFunction)_thunk_device_shards, METH_NOARGS,
+     "device_shards() => [(device, pointer, first_index, count, typestr), ...] of the evaluated thunk"},
     {NULL, NULL, 0, NULL} /* Sentinel */
 };

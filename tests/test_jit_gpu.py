@@ -266,3 +266,27 @@ def test_division_and_negation():
     assert (-x).asnumpyarray().tobytes() == (-x_n).tobytes()
     with pytest.raises(TypeError):
         -(a > 3)
+
+
+def test_results_can_stay_on_the_device():
+    """device_shards(): (device, pointer, first index, count) of the evaluated data, wrapped as
+    __cuda_array_interface__ objects; read back here through the C-ABI without asnumpyarray()."""
+    import ctypes as C
+    import numpyllvm_b200
+    from numpyllvm_b200 import abi
+    lib = abi.load_library()
+    n = 300_001
+    a_n = np.arange(n, dtype=np.float32)
+    r = jit.thunk(a_n) * 2 + 1
+    shards = numpyllvm_b200.device_shards(r)
+    assert sum(len(s) for s in shards) == n and r.isevaluated()
+    got = np.empty(n, dtype=np.float32)
+    for s in shards:
+        cai = s.__cuda_array_interface__
+        assert cai["typestr"] == "<f4" and cai["version"] == 3 and cai["shape"] == (s.count,)
+        if s.count:
+            abi.check(lib.nl_memcpy_d2h(s.device, 0, C.c_void_p(got[s.start:].ctypes.data), C.c_void_p(cai["data"][0]), s.count * 4))
+            abi.check(lib.nl_stream_sync(s.device, 0))
+    assert np.array_equal(got, a_n * 2 + 1)
+    total = numpyllvm_b200.device_shards(jit.thunk(np.arange(1000, dtype=np.int64)).sum())
+    assert len(total) == 1 and total[0].count == 1
