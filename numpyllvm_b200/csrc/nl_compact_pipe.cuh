@@ -55,7 +55,8 @@ constexpr int kPipeMaxSlots = 8;
 constexpr uint32_t kPipeWaitHintNs = NL_PIPE_WAIT_NS;   // suspend-time hint of the mbarrier waits
 constexpr int kPipeArriveShift = 20;          // SlotMeta::agg: survivors below this bit, warp arrivals above
 constexpr int kPipeMeta = 16;                // bookkeeping ring (power of two), see SlotMeta
-constexpr int kPipeSideBytes = 96 * kPipeRows;  // side buffer of one consumer warp per lag entry: 3/16 of its rows
+constexpr int kPipeRowsNarrow = 4;               // ... of the instantiation for two or three staged columns (half the slot size)
+constexpr int pipe_side_bytes(int rows) { return 96 * rows; }   // side buffer of one consumer warp per lag entry: 3/16 of its rows
 
 // ---- mbarrier / TMA bulk copy (PTX) ------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -225,9 +226,9 @@ struct StaticSplit {
 #endif
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <typename T, int V, class Split>
+template <typename T, int V, class Split, int U = kPipeRows>
 __global__ void __launch_bounds__(kPipeThreads, 1) compact_pipe_kernel(const __grid_constant__ KParams p) {
-  constexpr int U = kPipeRows;
+  constexpr int kPipeSideBytes = 96 * U;           // == pipe_side_bytes(U)
   using TileT = Tile<T, V, U, true, false, kPipeConsumers, true>;
   constexpr uint32_t kColBytes = (uint32_t)(TileT::TILE * sizeof(T));
   constexpr int kSideElems = kPipeSideBytes / (int)sizeof(T);      // side-buffer capacity of one warp, elements

@@ -38,6 +38,7 @@ struct KParams {
   int32_t lag;                        // tiles between the count phase and the store phase
   int32_t filter_step;                // index of the S_FILTER step
   int32_t side_cap;                   // survivors per warp and tile that may wait in the side buffer (0: none)
+  int32_t pipe_rows;                  // 16-byte rows per consumer thread and tile of the chosen instantiation
   // fused multi-GPU finish of a reduction over peer memory (NVLink mailboxes, nl_pipeline.cuh)
   unsigned long long *const *peer_box;   // device array: mailbox of every rank, mapped here (NULL: no fused finish)
   int32_t peer_world, peer_rank;
@@ -83,6 +84,7 @@ int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t
 void set_static_kernels_enabled(int on);
 void set_compact_pipe_enabled(int on);
 void set_compact_pipe_side(int on);
+void set_compact_pipe_dynamic(int on);
 void set_max_ctas_per_sm(int n);
 void set_compact_pipe_lag(int l);
 

@@ -192,7 +192,16 @@ static const char *dt_name(int d) {
   } while (0)
 
 // the interpreter's staged compaction pipeline, one per dtype
-static pipeline_fn pick_dynamic_pipe(int dtype) {
+static pipeline_fn pick_dynamic_pipe(int dtype, int rows) {
+  if (rows == kPipeRowsNarrow) {
+    switch (dtype) {
+      case NL_I32: return compact_pipe_kernel<int32_t, 4, DynSplit, kPipeRowsNarrow>;
+      case NL_I64: return compact_pipe_kernel<long long, 2, DynSplit, kPipeRowsNarrow>;
+      case NL_F32: return compact_pipe_kernel<float, 4, DynSplit, kPipeRowsNarrow>;
+      case NL_F64: return compact_pipe_kernel<double, 2, DynSplit, kPipeRowsNarrow>;
+    }
+    return nullptr;
+  }
   switch (dtype) {
     case NL_I32: return compact_pipe_kernel<int32_t, 4, DynSplit>;
     case NL_I64: return compact_pipe_kernel<long long, 2, DynSplit>;
@@ -203,6 +212,8 @@ static pipeline_fn pick_dynamic_pipe(int dtype) {
 }
 
 static int g_pipe_enabled = 1;
+static int g_pipe_dynamic = 0;     // allow the interpreter-driven staged pipeline (tests)
+void set_compact_pipe_dynamic(int on) { g_pipe_dynamic = on; }
 static int g_pipe_no_side = 0;
 static int g_max_ctas_per_sm = 0;   // tuning: cap on resident CTAs per SM of the streaming kernels (0: occupancy)
 void set_max_ctas_per_sm(int n) { g_max_ctas_per_sm = n; }
@@ -214,11 +225,11 @@ void set_compact_pipe_lag(int l) { g_pipe_lag = l; }
 // Can this plan run on the staged compaction pipeline?  One filter, nothing stored before it,
 // at least one value column to stage, enough tiles to fill the machine.  Fills the staged fields.
 // dynamic shared memory of compact_pipe_kernel (must mirror the carve-up at the top of the kernel)
-static size_t pipe_smem_bytes(int slots, int lag, int cols, bool side, size_t es) {
-  const size_t col_bytes = (size_t)kPipeConsumers * kPipeRows * 16;
+static size_t pipe_smem_bytes(int slots, int lag, int cols, bool side, size_t es, int rows) {
+  const size_t col_bytes = (size_t)kPipeConsumers * rows * 16;
   const size_t entries = (size_t)lag + 1;
-  return ((sizeof(PipeShared) + 127) / 128) * 128 + entries * kPipeConsumers * ((kPipeRows * 16 / es <= 16) ? 2 : 4) +
-         (side ? entries * kPipeConsumerWarps * kPipeSideBytes : 0) + (size_t)slots * cols * col_bytes;
+  return ((sizeof(PipeShared) + 127) / 128) * 128 + entries * kPipeConsumers * (((size_t)rows * 16 / es <= 16) ? 2 : 4) +
+         (side ? entries * kPipeConsumerWarps * pipe_side_bytes(rows) : 0) + (size_t)slots * cols * col_bytes;
 }
 
 static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
@@ -238,15 +249,26 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
   }
   if (filter < 0) return false;
   const size_t es = nl_dtype_size(plan->dtype);
-  const int64_t tile = (int64_t)kPipeConsumers * kPipeRows * (int64_t)(16 / es);
-  if (n_elems < tile * 2 * 148) return false;
   int cols = 0;
   uint8_t map[NL_MAX_INPUTS];
   for (int k = 0; k < NL_MAX_INPUTS; k++) map[k] = 0xff;
   for (int k = 0; k < plan->n_inputs; k++)
     if (plan->in[k].kind == NL_IN_ARRAY && plan->in[k].dtype == plan->dtype) map[k] = (uint8_t)cols++;
   if (cols == 0) return false;
-  const size_t col_bytes = (size_t)tile * es;
+  // one staged column: 32 KB slots (8 rows per thread); two or three: the 4-row instantiation with
+  // 16 KB per column and slot, so the ring keeps at least four slots.  Build-time shapes exist for
+  // the 8-row geometry only.
+  const StaticEntry *se = find_static(plan, true);
+  const bool has_static_pipe = se && se->pipe;
+  // The interpreter-driven pipeline is kept for testing only: with eight consumer warps per SM the
+  // step interpreter is issue-bound (measured 0.8-1.0 TB/s vs 1.2-1.9 for the plain interpreter
+  // kernel and 5-6 TB/s for the build-time shapes), so plans without a build-time shape stay on the
+  // plain kernel unless the tuning flag asks for it.
+  if (!has_static_pipe && !g_pipe_dynamic) return false;
+  const int rows = (cols == 1) ? kPipeRows : kPipeRowsNarrow;
+  if (rows != kPipeRows && has_static_pipe) return false;
+  const int64_t tile = (int64_t)kPipeConsumers * rows * (int64_t)(16 / es);
+  if (n_elems < tile * 2 * 148) return false;
   // the side buffer can take a survivor only if everything after the filter works on a bare
   // value: scalar operands and compacted stores
   bool sparse_ok = true;
@@ -268,7 +290,7 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
     int d = (g_pipe_lag > 0) ? g_pipe_lag : s_try / 2;   // half the ring hides the look-back, half is prefetch (measured best)
     if (d > s_try - 2) d = s_try - 2;                    // a parked tile must be stored before the producer needs its slot
     if (s_try + d + 1 > kPipeMeta) continue;
-    if (pipe_smem_bytes(s_try, d, cols, sparse_ok, es) <= (size_t)227 * 1024 - 1024) { slots = s_try; lag = d; break; }
+    if (pipe_smem_bytes(s_try, d, cols, sparse_ok, es, rows) <= (size_t)227 * 1024 - 1024) { slots = s_try; lag = d; break; }
   }
   if (slots == 0) return false;
   if (kp) {
@@ -278,14 +300,17 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
     kp->lag = lag;
     kp->filter_step = filter;
     kp->n_inputs = plan->n_inputs;
-    kp->side_cap = sparse_ok ? (int32_t)(kPipeSideBytes / es) : 0;
+    kp->pipe_rows = rows;
+    kp->side_cap = sparse_ok ? (int32_t)(pipe_side_bytes(rows) / es) : 0;
   }
   return true;
 }
 
 int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
   const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
-  if (pipe_eligible(plan, vec16, n_elems, kp)) return (int64_t)kPipeConsumers * kPipeRows * v;
+  KParams local;
+  KParams *q = kp ? kp : &local;
+  if (pipe_eligible(plan, vec16, n_elems, q)) return (int64_t)kPipeConsumers * q->pipe_rows * v;
   const StaticEntry *e = find_static(plan, vec16);
   const int rows = e ? e->rows : kRows;
   return (int64_t)kBlock * rows * v;
@@ -309,9 +334,9 @@ int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t
 
 static int launch_compact_pipe(const nl_plan *plan, const KParams &kp, int sm_count, void *stream, LaunchInfo *info) {
   const StaticEntry *e = find_static(plan, true);
-  pipeline_fn fn = (e && e->pipe) ? e->pipe : pick_dynamic_pipe(plan->dtype);
+  pipeline_fn fn = (e && e->pipe && kp.pipe_rows == kPipeRows) ? e->pipe : pick_dynamic_pipe(plan->dtype, kp.pipe_rows);
   if (!fn) { set_error("no compaction pipeline for dtype %d", plan->dtype); return NL_ERR_UNSUPPORTED; }
-  const size_t smem = pipe_smem_bytes(kp.n_slots, kp.lag, kp.n_stage_cols, kp.side_cap != 0, nl_dtype_size(plan->dtype));
+  const size_t smem = pipe_smem_bytes(kp.n_slots, kp.lag, kp.n_stage_cols, kp.side_cap != 0, nl_dtype_size(plan->dtype), kp.pipe_rows);
   CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = sm_count;
   if (grid > kp.n_tiles) grid = kp.n_tiles;
@@ -320,7 +345,7 @@ static int launch_compact_pipe(const nl_plan *plan, const KParams &kp, int sm_co
   count_launch();
   if (info) {
     const int v = (int)(16 / nl_dtype_size(plan->dtype));
-    snprintf(info->kernel, sizeof(info->kernel), "compact_pipe_kernel<%s,V=%d,%s%s,slots=%d,lag=%d,side=%d>", dt_name(plan->dtype), v,
+    snprintf(info->kernel, sizeof(info->kernel), "compact_pipe_kernel<%s,V=%d,U=%d,%s%s,slots=%d,lag=%d,side=%d>", dt_name(plan->dtype), v, kp.pipe_rows,
              (e && e->pipe) ? "static:" : "dynamic", (e && e->pipe) ? e->name : "", kp.n_slots, kp.lag, kp.side_cap);
     info->grid = (int)grid;
     info->block = kPipeThreads;

@@ -362,7 +362,30 @@ int nl_plan_compile(const nl_expr_node *nodes, int n_nodes, const nl_input_desc 
       if (seen != n_filters) { set_error("a filtered result is materialised between two filters: split the pipeline there"); return NL_ERR_UNSUPPORTED; }
     }
   }
-  plan->n_temps = lw.max_temps;
+  // Dead saves: a column parked in a temporary "for later" whose later use found it still in the
+  // accumulator.  Dropping them is what lets such plans run on the temporary-free interpreter.
+  {
+    int w = 0, max_t = 0;
+    for (int i = 0; i < plan->n_steps; i++) {
+      const uint32_t st = plan->step[i];
+      if (step_op(st) == S_SAVE) {
+        const uint32_t j = step_a(st);
+        bool used = false;
+        for (int k = i + 1; k < plan->n_steps && !used; k++) {
+          const uint32_t t = plan->step[k], op = step_op(t);
+          if (op == S_SAVE && step_a(t) == j) break;                        // overwritten before any read
+          if (op == S_LOADT && step_a(t) == j) used = true;
+          if ((op == S_BIN || op == S_CMP) && step_b(t) == (SRC_TEMP | j)) used = true;
+        }
+        if (!used) continue;
+        if ((int)j + 1 > max_t) max_t = (int)j + 1;
+      }
+      plan->step[w++] = st;
+    }
+    for (int i = w; i < plan->n_steps; i++) plan->step[i] = 0;
+    plan->n_steps = w;
+    plan->n_temps = max_t;
+  }
   return NL_OK;
 }
 

@@ -53,14 +53,14 @@ template <uint32_t... S> constexpr int rows_for() {
 // X(name, steps...)
 #define NL_CMP_SHAPES(X, tag, cop)                                                                          \
   /* a[a cmp s]            (Tests/filter.py family, C4) */                                                  \
-  X(filter_##tag, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::ST(0, sp::COMPACT))                       \
+  X(filter_##tag, sp::L(0), sp::C(cop, 1), sp::F(), sp::ST(0, sp::COMPACT))                       \
   /* a[a cmp s].sum()/max()/min()   (Tests/max.py family) */                                                \
-  X(filter_##tag##_sum, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::R(R_SUM, 0))                        \
-  X(filter_##tag##_max, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::R(R_MAX, 0))                        \
-  X(filter_##tag##_min, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::R(R_MIN, 0))                        \
+  X(filter_##tag##_sum, sp::L(0), sp::C(cop, 1), sp::F(), sp::R(R_SUM, 0))                        \
+  X(filter_##tag##_max, sp::L(0), sp::C(cop, 1), sp::F(), sp::R(R_MAX, 0))                        \
+  X(filter_##tag##_min, sp::L(0), sp::C(cop, 1), sp::F(), sp::R(R_MIN, 0))                        \
   /* (a[a cmp s] * k).max()   (C5) */                                                                       \
-  X(filter_##tag##_mul_max, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::B(V_MUL, 2), sp::R(R_MAX, 0))   \
-  X(filter_##tag##_mul_sum, sp::L(0), sp::SV(1), sp::C(cop, 1), sp::F(), sp::B(V_MUL, 2), sp::R(R_SUM, 0))   \
+  X(filter_##tag##_mul_max, sp::L(0), sp::C(cop, 1), sp::F(), sp::B(V_MUL, 2), sp::R(R_MAX, 0))   \
+  X(filter_##tag##_mul_sum, sp::L(0), sp::C(cop, 1), sp::F(), sp::B(V_MUL, 2), sp::R(R_SUM, 0))   \
   /* a cmp s  -> materialised mask */                                                                       \
   X(mask_##tag, sp::L(0), sp::C(cop, 1), sp::PST(0, sp::LOOP))
 

@@ -12,7 +12,7 @@ from numpyllvm_b200.device import Runtime, run_pipeline
 pytestmark = pytest.mark.gpu
 
 # flags of nl_set_static_kernels(): bit 0 = build-time shapes, bit 1 = keep compaction on the plain kernel
-MODES = {"pipe-static": 1, "pipe-dynamic": 0, "plain-static": 3, "plain-dynamic": 2}
+MODES = {"pipe-static": 1 | 8, "pipe-dynamic": 0 | 8, "plain-static": 3, "plain-dynamic": 2}   # bit 3: interpreter-driven pipeline allowed
 
 
 @pytest.fixture(scope="module")
@@ -95,11 +95,35 @@ def test_ineligible_pipelines_stay_on_the_plain_kernel(rt, mode):
     e.materialize(dbl)
     e.materialize(e.filter(e.ref(xa), e.ge(dbl, e.scalar(50))))
     check(rt, mode, e, [x, None, None], n, expect_pipe=False)
-    # two staged columns would leave fewer than four ring slots
+    # nine columns cannot be staged (the plan compiler caps a pipeline at eight inputs anyway); five
+    # staged columns leave fewer than four ring slots even with the narrow tiles
     e = Expr(np.int64)
-    xa, ya = e.array(), e.array()
-    e.materialize(e.filter(xa, e.gt(ya, e.scalar(40))))
-    check(rt, mode, e, [x, y, None], n, expect_pipe=False)
+    cols = [e.array() for _ in range(5)]
+    acc = cols[0]
+    for c in cols[1:]:
+        acc = e.add(acc, c)
+    e.materialize(e.filter(acc, e.gt(e.ref(cols[0]), e.scalar(40))))
+    check(rt, mode, e, [x, y, x, y, x, None], n, expect_pipe=False)
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("sel", [0.02, 0.5, 0.97])
+def test_two_and_three_staged_columns_use_the_narrow_tiles(rt, mode, dtype, sel):
+    """b[a > t] and (a*b + c)[a > t]: several columns share a ring slot (4-row instantiation)."""
+    n = tile_elems(dtype) * 330 + 17
+    kind = 0 if np.dtype(dtype).kind == "i" else 3
+    a = oracle.fill(dtype, 0, n, kind, 1)
+    b = oracle.fill(dtype, 0, n, kind, 2)
+    c = oracle.fill(dtype, 0, n, kind, 3)
+    thr = np.dtype(dtype).type(np.sort(a)[int((1 - sel) * (n - 1))])
+    e = Expr(dtype)
+    xa, xb = e.array(), e.array()
+    e.materialize(e.filter(xb, e.gt(xa, e.scalar(thr))))
+    check(rt, mode, e, [a, b, None], n)
+    e = Expr(dtype)
+    xa, xb, xc = e.array(), e.array(), e.array()
+    e.materialize(e.filter(e.add(e.mul(e.ref(xa), xb), xc), e.gt(xa, e.scalar(thr))))
+    check(rt, mode, e, [a, b, c, None], n)
 
 
 def test_repeated_launches_reuse_the_descriptors(rt, mode):

@@ -2,7 +2,7 @@
 """Run ONE pipeline config a few times (for ncu / quick timing).
 
   python tools/profile_one.py c2 --log2n 27 --reps 3
-Configs: c1 c2 c3_f64_max c3_f64_sum c3_i64_max c3_i64_sum c4_1 c4_10 c4_50 c4_90 c5 fill
+Configs: c1 c2 c3_f64_max c3_f64_sum c3_i64_max c3_i64_sum c4_1 c4_10 c4_50 c4_90 c4b_1 c4b_50 c4b_90 c5
 Prints the CUDA-event time per launch and the implied GB/s (never quote a number
 taken under a profiler).
 """
@@ -50,6 +50,22 @@ def build(name, rt, n):
         e = Expr(np.float64); xa = e.array()
         e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(1.0 - sel))))
         return abi.compile_plan(e), [y.ptr], [x.ptr, None], int(8 * n * (1 + sel)), (x, y, sizes)
+    if name.startswith("c4d_"):          # (a*2+1)[a > t]: one staged column, no build-time shape
+        sel = int(name.split("_")[1]) / 100.0
+        a = rt.empty(np.float64, n); rt.fill(a, 0, 9, 3)
+        y = rt.empty(np.float64, n)
+        e = Expr(np.float64); xa = e.array()
+        e.materialize(e.filter(e.add(e.mul(xa, e.scalar(2.0)), e.scalar(1.0)), e.gt(e.ref(xa), e.scalar(1.0 - sel))))
+        plan = abi.compile_plan(e)
+        return plan, [y.ptr], [a.ptr if plan.in_[i].kind == abi.IN_ARRAY else None for i in range(plan.n_inputs)], int(8 * n * (1 + sel)), (a, y, sizes)
+    if name.startswith("c4b_"):          # b[a > t]: two staged columns
+        sel = int(name.split("_")[1]) / 100.0
+        a = rt.empty(np.float64, n); rt.fill(a, 0, 9, 3)
+        b = rt.empty(np.float64, n); rt.fill(b, 0, 10, 2)
+        y = rt.empty(np.float64, n)
+        e = Expr(np.float64); xa, xb = e.array(), e.array()
+        e.materialize(e.filter(xb, e.gt(xa, e.scalar(1.0 - sel))))
+        return abi.compile_plan(e), [y.ptr], [a.ptr, b.ptr, None], int(8 * n * (2 + sel)), (a, b, y, sizes)
     if name == "c5":
         x = rt.empty(np.float32, n); rt.fill(x, 0, 11, 3)
         res = rt.empty(np.float32, 1)
