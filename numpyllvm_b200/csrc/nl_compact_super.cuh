@@ -1,0 +1,138 @@
+// nl_compact_super.cuh — compaction over super-tiles (sm_100a).
+//
+// Measured on B200: a compaction kernel's rate is
+//       resident CTAs per SM  x  bytes a CTA moves per tile  /  latency of one tile,
+// and the latency (ticket, loads, look-back, stores: 4-6 us) hardly depends on the bytes.  The
+// plain kernel keeps a tile's values in registers across the look-back, so its tile is bounded by
+// the register file (32 KB) and it stops at 0.7-0.8 of the roofline; `b[a > t]`, which moves two
+// columns per tile with the same registers, runs at 0.97-1.0.
+//
+// This kernel gives every filter that ratio.  A CTA claims a SUPER-tile of K consecutive tiles:
+//   count pass   for each of the K tiles: run the program up to the filter, keep ONLY the keep
+//                mask (one bit per element) and the warp's survivor count; rows are loaded with
+//                normal L2 residency;
+//   one look-back for the whole super-tile (K x fewer descriptors, K x fewer latencies);
+//   store pass   for each tile: re-run the value part of the program — its rows come back from L2,
+//                not from HBM (K x 32 KB per CTA, a few tens of MB chip-wide, far below the 126 MB
+//                L2) — rank, run the steps after the filter, store compacted.
+// HBM traffic stays one read of the inputs and one write of the survivors; no shared-memory ring, no
+// warp specialisation, and the same code serves build-time shapes and the step interpreter.
+#pragma once
+#include "nl_compact_pipe.cuh"   // StaticSplit / DynSplit: the program split at the filter step
+
+namespace nl {
+
+#ifndef NL_SUPER_K
+#define NL_SUPER_K 4
+#endif
+constexpr int kSuperK = NL_SUPER_K;        // tiles per super-tile
+
+template <typename T, int V, int U, class Split, bool kTemps, int kMinCtas>
+__global__ void __launch_bounds__(kBlock, kMinCtas) compact_super_kernel(const __grid_constant__ KParams p) {
+  using TileT = Tile<T, V, U, true, false, kBlock, false, kTemps>;
+  constexpr int NW = kBlock / 32;
+  constexpr int K = kSuperK;
+  static_assert(K * NW <= 32, "one warp scans all (tile, warp) counts of a super-tile");
+  __shared__ TileShared sh;
+  __shared__ uint32_t wtot[K][NW];     // survivors of warp w in tile k
+  __shared__ uint32_t woff[K][NW];     // exclusive scan over (k, w): offset of the warp's run inside the super-tile
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long n_sub = (p.end - p.start + TileT::TILE - 1) / TileT::TILE;
+
+  if (blockIdx.x == 0 && tid == 0) {
+    for (int o = 0; o < p.n_outputs; o++)
+      if (p.out_space[o] == NL_IDX_LOOP) p.out_sizes[o] = p.end;
+  }
+
+  TileT t;
+  t.rsum = 0;
+  t.rext = T(0);
+  while (true) {
+    if (tid == 0) sh.tile = (long long)atomicAdd(p.tile_ticket, 1u);
+    __syncthreads();
+    const long long super = sh.tile;
+    if (super >= p.n_tiles) break;
+
+    // ---- count pass ----
+    uint32_t keepm[K];
+    t.keep_in_l2 = true;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const long long sub = super * K + k;
+      keepm[k] = 0;
+      uint32_t cnt = 0;
+      if (sub < n_sub) {
+        t.begin_tile(p, sub, tid);
+        Split::template before<false>(t, p, sh, lane, warp);
+        keepm[k] = t.keep & t.pacc;
+        cnt = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(keepm[k]));
+      }
+      if (lane == 0) wtot[k][warp] = cnt;
+    }
+    __syncthreads();
+
+    // ---- offsets of the (tile, warp) runs + one decoupled look-back for the super-tile ----
+    if (warp == 0) {
+      const uint32_t val = (lane < K * NW) ? (&wtot[0][0])[lane] : 0u;
+      uint32_t sc = val;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t nb = __shfl_up_sync(0xffffffffu, sc, d);
+        if (lane >= d) sc += nb;
+      }
+      if (lane < K * NW) (&woff[0][0])[lane] = sc - val;
+      const unsigned long long agg = __shfl_sync(0xffffffffu, sc, 31);
+      unsigned long long excl = 0;
+      if (super == 0) {
+        if (lane == 0) st_relaxed_u64(&p.tile_desc[0], kDescPrefix | agg);
+      } else {
+        if (lane == 0) st_relaxed_u64(&p.tile_desc[super * kDescStride], kDescAggregate | agg);
+        long long j = super - 1;
+        bool done = false;
+        while (!done) {
+          const long long q = j - lane;
+          unsigned long long d = (q >= 0) ? ld_relaxed_u64(&p.tile_desc[q * kDescStride]) : kDescPrefix;
+          while ((d >> 62) == 0) d = ld_relaxed_u64(&p.tile_desc[q * kDescStride]);
+          const uint32_t has_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+          const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
+          unsigned long long v = (lane <= first) ? (d & kDescValueMask) : 0ull;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          excl += v;
+          if (has_prefix) done = true;
+          j -= 32;
+        }
+        if (lane == 0) st_relaxed_u64(&p.tile_desc[super * kDescStride], kDescPrefix | ((excl + agg) & kDescValueMask));
+      }
+      if (lane == 0) {
+        sh.prefix = (long long)excl;
+        if (super == p.n_tiles - 1) {
+          for (int o = 0; o < p.n_outputs; o++)
+            if (p.out_space[o] == NL_IDX_COMPACT) p.out_sizes[o] = p.start + (long long)(excl + agg);
+        }
+      }
+      // multi-GPU: the shard's count goes to the peers from inside the kernel
+      if (super == p.n_tiles - 1 && p.peer_offsets != nullptr) peer_scan_counts(p, excl + agg, lane);
+    }
+    __syncthreads();
+
+    // ---- store pass: values come back from L2 ----
+    t.keep_in_l2 = false;
+    const long long base_out = p.start + sh.prefix;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (wtot[k][warp] == 0) continue;             // warp-uniform
+      const long long sub = super * K + k;
+      t.begin_tile(p, sub, tid);
+      if (keepm[k]) Split::template before<true>(t, p, sh, lane, warp);
+      t.keep = keepm[k];
+      t.rank_rows(lane);
+      t.cbase = base_out + (long long)woff[k][warp];
+      if (keepm[k]) Split::after(t, p, sh, lane, warp);
+    }
+    __syncthreads();                                // sh.tile / wtot are rewritten by the next round
+  }
+}
+
+}  // namespace nl

@@ -39,6 +39,8 @@ struct KParams {
   int32_t filter_step;                // index of the S_FILTER step
   int32_t side_cap;                   // survivors per warp and tile that may wait in the side buffer (0: none)
   int32_t pipe_rows;                  // 16-byte rows per consumer thread and tile of the chosen instantiation
+  int32_t super_k;                    // > 0: super-tile compaction kernel (nl_compact_super.cuh), tiles per super-tile
+  int32_t super_rows;                 // ... and its rows per thread
   // fused multi-GPU finish of a reduction over peer memory (NVLink mailboxes, nl_pipeline.cuh)
   unsigned long long *const *peer_box;   // device array: mailbox of every rank, mapped here (NULL: no fused finish)
   int32_t peer_world, peer_rank;
@@ -85,6 +87,7 @@ void set_static_kernels_enabled(int on);
 void set_compact_pipe_enabled(int on);
 void set_compact_pipe_side(int on);
 void set_compact_pipe_dynamic(int on);
+void set_compact_prefer_pipe(int on);
 void set_max_ctas_per_sm(int n);
 void set_compact_pipe_lag(int l);
 

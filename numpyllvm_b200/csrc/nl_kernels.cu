@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "nl_compact_pipe.cuh"
+#include "nl_compact_super.cuh"
 
 namespace nl {
 
@@ -232,21 +233,67 @@ static size_t pipe_smem_bytes(int slots, int lag, int cols, bool side, size_t es
          (side ? entries * kPipeConsumerWarps * pipe_side_bytes(rows) : 0) + (size_t)slots * cols * col_bytes;
 }
 
-static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
-  if (!g_pipe_enabled || !vec16) return false;
-  if (!(plan->flags & NL_PLAN_HAS_COMPACT) || (plan->flags & (NL_PLAN_HAS_REDUCE | NL_PLAN_HAS_WHERE))) return false;
+// A plan can be split at its filter into "count" and "store" halves (staged pipeline, super-tile
+// kernel) when it has exactly one filter, stores nothing before it and reads no predicate
+// temporary after it (the store half skips the predicate steps).  Returns the filter's step or -1.
+static int split_point(const nl_plan *plan) {
+  if (!(plan->flags & NL_PLAN_HAS_COMPACT) || (plan->flags & (NL_PLAN_HAS_REDUCE | NL_PLAN_HAS_WHERE))) return -1;
   int filter = -1;
   for (int i = 0; i < plan->n_steps; i++) {
     const uint32_t op = step_op(plan->step[i]);
     if (op == S_FILTER) {
-      if (filter >= 0) return false;
+      if (filter >= 0) return -1;
       filter = i;
     } else if ((op == S_STORE || op == S_PSTORE || op == S_WHERE) && filter < 0) {
-      return false;
+      return -1;
     } else if ((op == S_PLOADT || op == S_PBIN || op == S_PSTORE) && filter >= 0) {
-      return false;   // phase B skips the predicate steps before the filter: nothing after it may read them
+      return -1;
     }
   }
+  return filter;
+}
+
+static int g_prefer_pipe = 0;      // tuning: staged pipeline before the super-tile kernel
+void set_compact_prefer_pipe(int on) { g_prefer_pipe = on; }
+
+// the interpreter's super-tile kernel
+template <typename T>
+static pipeline_fn pick_super_T(bool uses_temps) {
+  constexpr int V16 = 16 / sizeof(T);
+  return uses_temps ? compact_super_kernel<T, V16, kRows, DynSplit, true, kMinBlocks>
+                    : compact_super_kernel<T, V16, kRows, DynSplit, false, kMinBlocksLight>;
+}
+static pipeline_fn pick_dynamic_super(int dtype, bool uses_temps) {
+  switch (dtype) {
+    case NL_I32: return pick_super_T<int32_t>(uses_temps);
+    case NL_I64: return pick_super_T<long long>(uses_temps);
+    case NL_F32: return pick_super_T<float>(uses_temps);
+    case NL_F64: return pick_super_T<double>(uses_temps);
+  }
+  return nullptr;
+}
+
+// super-tile compaction kernel for this plan?  Fills kp->super_k / super_rows / filter_step.
+static bool super_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
+  if (!g_pipe_enabled || !vec16) return false;        // "plain kernel only" switches both off
+  const int filter = split_point(plan);
+  if (filter < 0) return false;
+  const StaticEntry *se = find_static(plan, true);
+  const int rows = (se && se->super) ? se->super_rows : kRows;
+  const int64_t tile = (int64_t)kBlock * rows * (int64_t)(16 / nl_dtype_size(plan->dtype));
+  if (n_elems < tile * kSuperK * 148) return false;      // at least one super-tile per SM
+  if (kp) {
+    kp->super_k = kSuperK;
+    kp->super_rows = rows;
+    kp->filter_step = filter;
+    kp->n_inputs = plan->n_inputs;
+  }
+  return true;
+}
+
+static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
+  if (!g_pipe_enabled || !vec16) return false;
+  const int filter = split_point(plan);
   if (filter < 0) return false;
   const size_t es = nl_dtype_size(plan->dtype);
   int cols = 0;
@@ -265,8 +312,9 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
   // kernel and 5-6 TB/s for the build-time shapes), so plans without a build-time shape stay on the
   // plain kernel unless the tuning flag asks for it.
   if (!has_static_pipe && !g_pipe_dynamic) return false;
+  if (se && !se->pipe) return false;          // a build-time shape whose plain kernel is the fast one
   const int rows = (cols == 1) ? kPipeRows : kPipeRowsNarrow;
-  if (rows != kPipeRows && has_static_pipe) return false;
+  if (has_static_pipe && se->pipe_rows != rows) return false;   // e.g. a scalar slot of the shape bound to a column
   const int64_t tile = (int64_t)kPipeConsumers * rows * (int64_t)(16 / es);
   if (n_elems < tile * 2 * 148) return false;
   // the side buffer can take a survivor only if everything after the filter works on a bare
@@ -310,7 +358,11 @@ int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KP
   const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
   KParams local;
   KParams *q = kp ? kp : &local;
-  if (pipe_eligible(plan, vec16, n_elems, q)) return (int64_t)kPipeConsumers * q->pipe_rows * v;
+  q->super_k = 0;
+  q->n_slots = 0;
+  if (g_prefer_pipe && pipe_eligible(plan, vec16, n_elems, q)) return (int64_t)kPipeConsumers * q->pipe_rows * v;
+  if (super_eligible(plan, vec16, n_elems, q)) return (int64_t)kBlock * q->super_rows * v * q->super_k;
+  if (!g_prefer_pipe && pipe_eligible(plan, vec16, n_elems, q)) return (int64_t)kPipeConsumers * q->pipe_rows * v;
   const StaticEntry *e = find_static(plan, vec16);
   const int rows = e ? e->rows : kRows;
   return (int64_t)kBlock * rows * v;
@@ -334,7 +386,7 @@ int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t
 
 static int launch_compact_pipe(const nl_plan *plan, const KParams &kp, int sm_count, void *stream, LaunchInfo *info) {
   const StaticEntry *e = find_static(plan, true);
-  pipeline_fn fn = (e && e->pipe && kp.pipe_rows == kPipeRows) ? e->pipe : pick_dynamic_pipe(plan->dtype, kp.pipe_rows);
+  pipeline_fn fn = (e && e->pipe && kp.pipe_rows == e->pipe_rows) ? e->pipe : pick_dynamic_pipe(plan->dtype, kp.pipe_rows);
   if (!fn) { set_error("no compaction pipeline for dtype %d", plan->dtype); return NL_ERR_UNSUPPORTED; }
   const size_t smem = pipe_smem_bytes(kp.n_slots, kp.lag, kp.n_stage_cols, kp.side_cap != 0, nl_dtype_size(plan->dtype), kp.pipe_rows);
   CUDA_TRY(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -354,7 +406,34 @@ static int launch_compact_pipe(const nl_plan *plan, const KParams &kp, int sm_co
   return NL_OK;
 }
 
+static int launch_compact_super(const nl_plan *plan, const KParams &kp, int sm_count, void *stream, LaunchInfo *info) {
+  const StaticEntry *e = find_static(plan, true);
+  const bool is_static = e && e->super && e->super_rows == kp.super_rows;
+  pipeline_fn fn = is_static ? e->super : pick_dynamic_super(plan->dtype, plan->n_temps > 0);
+  if (!fn) { set_error("no super-tile compaction kernel for dtype %d", plan->dtype); return NL_ERR_UNSUPPORTED; }
+  int bps = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, kBlock, 0));
+  if (bps < 1) bps = 1;
+  if (g_max_ctas_per_sm > 0 && bps > g_max_ctas_per_sm) bps = g_max_ctas_per_sm;
+  int64_t grid = (int64_t)sm_count * bps;
+  if (grid > kp.n_tiles) grid = kp.n_tiles;
+  if (grid < 1) grid = 1;
+  fn<<<(unsigned)grid, kBlock, 0, (cudaStream_t)stream>>>(kp);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  if (info) {
+    const int v = (int)(16 / nl_dtype_size(plan->dtype));
+    snprintf(info->kernel, sizeof(info->kernel), "compact_super_kernel<%s,V=%d,U=%d,K=%d,%s%s>", dt_name(plan->dtype), v, kp.super_rows, kp.super_k,
+             is_static ? "static:" : (plan->n_temps > 0 ? "dynamic" : "dynamic-light"), is_static ? e->name : "");
+    info->grid = (int)grid;
+    info->block = kBlock;
+    info->vec_elems = v;
+  }
+  return NL_OK;
+}
+
 int launch_pipeline_kernel(const nl_plan *plan, const KParams &kp, bool vec16, int sm_count, void *stream, LaunchInfo *info) {
+  if (kp.super_k > 0) return launch_compact_super(plan, kp, sm_count, stream, info);
   if (kp.n_slots > 0) return launch_compact_pipe(plan, kp, sm_count, stream, info);
   pipeline_fn fn = pick(plan, vec16, nullptr);
   if (!fn) { set_error("no pipeline kernel for dtype %d", plan->dtype); return NL_ERR_UNSUPPORTED; }

@@ -121,6 +121,17 @@ template <> struct VecOf<4> { using type = unsigned int; };
 template <> struct VecOf<2> { using type = unsigned short; };
 template <> struct VecOf<1> { using type = unsigned char; };
 
+// the same row read with normal L2 residency (ld.global.cg): used when the row will be read again
+// shortly (count pass of the super-tile compaction kernel)
+template <typename T, int V>
+__device__ __forceinline__ void load_vec_l2(const T *__restrict__ ptr, T *dst) {
+  using Vec = typename VecOf<sizeof(T) * V>::type;
+  union { Vec q; T t[V]; } u;
+  u.q = __ldcg(reinterpret_cast<const Vec *>(ptr));
+#pragma unroll
+  for (int v = 0; v < V; v++) dst[v] = u.t[v];
+}
+
 // one row = V consecutive elements of one thread; streaming (evict-first) 128-bit access
 template <typename T, int V>
 __device__ __forceinline__ void load_vec(const T *__restrict__ ptr, T *dst) {
@@ -292,6 +303,7 @@ struct Tile {
   uint32_t crow[U];          // + offset of each of this lane's rows inside the run
   int64_t thr_base, tile;
   bool full;
+  bool keep_in_l2 = false;      // column rows are loaded with normal L2 residency (they will be read again)
   const unsigned char *stage;   // kStaged: shared-memory slot of the current tile (column 0)
   uint32_t stage_off;           // kStaged: byte offset of this lane's row 0 inside a staged column
   // running reduction state (lives across tiles)
@@ -361,8 +373,13 @@ struct Tile {
         }
         const T *base = reinterpret_cast<const T *>(p.in[src]) + thr_base;
         if (full) {
+          if (keep_in_l2) {
 #pragma unroll
-          for (int u = 0; u < U; u++) load_vec<T, V>(base + u * ROWSTRIDE, &x[u * V]);
+            for (int u = 0; u < U; u++) load_vec_l2<T, V>(base + u * ROWSTRIDE, &x[u * V]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) load_vec<T, V>(base + u * ROWSTRIDE, &x[u * V]);
+          }
         } else {
 #pragma unroll
           for (int e = 0; e < E; e++) x[e] = ((valid >> e) & 1u) ? base[(e / V) * ROWSTRIDE + (e % V)] : T(0);
@@ -688,7 +705,7 @@ struct Tile {
             uint32_t ci = crow[u];
 #pragma unroll
             for (int v = 0; v < V; v++)
-              if ((keep >> (u * V + v)) & 1u) base[ci++] = acc[u * V + v];
+              if ((keep >> (u * V + v)) & 1u) __stcs(&base[ci++], acc[u * V + v]);   // streaming: must not evict rows waiting in L2 for the store pass
           }
         }
         break;
@@ -965,6 +982,9 @@ struct StaticEntry {
   int rows;            // U of the instantiation: rows per thread per tile
   pipeline_fn fn;
   pipeline_fn pipe;    // staged compaction pipeline (nl_compact_pipe.cuh) or nullptr
+  int pipe_rows;       // ... and the rows per thread it was instantiated for
+  pipeline_fn super;   // super-tile compaction kernel (nl_compact_super.cuh) or nullptr
+  int super_rows;
 };
 
 // per-dtype tables, defined in nl_static_<dtype>.cu

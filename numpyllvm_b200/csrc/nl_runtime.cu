@@ -732,7 +732,8 @@ int nl_set_static_kernels(int enabled) {
   set_compact_pipe_enabled((enabled & 2) ? 0 : 1);      // bit 1 set: keep compaction on the plain kernel
   set_max_ctas_per_sm((enabled >> 8) & 0xf);                                 // bits 8..11: cap on CTAs per SM (tuning)
   set_compact_pipe_side((enabled & 4) ? 0 : 1);
-  set_compact_pipe_dynamic((enabled & 8) ? 1 : 0);                           // bit 3 set: interpreter-driven staged pipeline allowed (tests)                              // bit 2 set: no side buffers (tuning)
+  set_compact_pipe_dynamic((enabled & 8) ? 1 : 0);
+  set_compact_prefer_pipe((enabled & 16) ? 1 : 0);                           // bit 4 set: staged pipeline before the super-tile kernel (tuning/tests)                           // bit 3 set: interpreter-driven staged pipeline allowed (tests)                              // bit 2 set: no side buffers (tuning)
   set_compact_pipe_lag((enabled >> 12) & 0xf);                              // bits 12..15: lag override (tuning)
   return NL_OK;
 }

@@ -11,6 +11,7 @@
 // benchmark expressions resolve to a static kernel.
 #pragma once
 #include "nl_compact_pipe.cuh"
+#include "nl_compact_super.cuh"
 
 namespace nl {
 namespace sp {
@@ -36,10 +37,30 @@ template <uint32_t... S> constexpr bool has_filter() { return ((step_op(S) == S_
 template <uint32_t... S> constexpr bool reads_temp() {
   return ((step_op(S) == S_LOADT || ((step_op(S) == S_BIN || step_op(S) == S_CMP) && (step_b(S) & SRC_TEMP))) || ...);
 }
+// columns a shape loads (distinct inputs of its LOAD steps): they are what the staged pipeline keeps in
+// a ring slot, and two or more take the narrow 4-row instantiation (half the slot size per column)
+template <uint32_t... S> constexpr int loaded_columns() {
+  constexpr uint32_t st[] = {S...};
+  uint32_t seen = 0;
+  for (uint32_t s : st)
+    if (step_op(s) == S_LOAD) seen |= 1u << step_a(s);
+  int n = 0;
+  for (int k = 0; k < NL_MAX_INPUTS; k++) n += (seen >> k) & 1u;
+  return n;
+}
+template <uint32_t... S> constexpr int pipe_rows_for() { return loaded_columns<S...>() > 1 ? kPipeRowsNarrow : kPipeRows; }
 // the staged compaction pipeline is instantiated for the compaction shapes only
 template <typename T, bool kOn, uint32_t... S> struct PipeFor { static constexpr pipeline_fn fn = nullptr; };
 template <typename T, uint32_t... S> struct PipeFor<T, true, S...> {
-  static constexpr pipeline_fn fn = &compact_pipe_kernel<T, 16 / sizeof(T), StaticSplit<S...>>;
+  static constexpr pipeline_fn fn = &compact_pipe_kernel<T, 16 / sizeof(T), StaticSplit<S...>, pipe_rows_for<S...>()>;
+};
+// the super-tile compaction kernel: 8 rows per thread at 4 CTAs/SM, or 4 rows at 2 CTAs/SM when the shape
+// keeps a value temporary alive
+template <uint32_t... S> constexpr int super_rows_for() { return reads_temp<S...>() ? kRows : kRowsCompact; }
+template <typename T, bool kOn, uint32_t... S> struct SuperFor { static constexpr pipeline_fn fn = nullptr; };
+template <typename T, uint32_t... S> struct SuperFor<T, true, S...> {
+  static constexpr pipeline_fn fn = &compact_super_kernel<T, 16 / sizeof(T), super_rows_for<S...>(), StaticSplit<S...>, reads_temp<S...>(),
+                                                          (reads_temp<S...>() ? kMinBlocks : kMinBlocksCompact)>;
 };
 template <uint32_t... S> constexpr int rows_for() {
   // eight 16-byte rows per thread for the streaming shapes too (twice the loads in flight per
@@ -61,6 +82,10 @@ template <uint32_t... S> constexpr int rows_for() {
   /* (a[a cmp s] * k).max()   (C5) */                                                                       \
   X(filter_##tag##_mul_max, sp::L(0), sp::C(cop, 1), sp::F(), sp::B(V_MUL, 2), sp::R(R_MAX, 0))   \
   X(filter_##tag##_mul_sum, sp::L(0), sp::C(cop, 1), sp::F(), sp::B(V_MUL, 2), sp::R(R_SUM, 0))   \
+  /* b[a cmp s]: select one column by a predicate on another; inputs (a, b, s) or, as the jit    */        \
+  /* extension numbers them (value first), (b, a, s)                                               */        \
+  X(filter2_##tag, sp::L(0), sp::C(cop, 2), sp::F(), sp::L(1), sp::ST(0, sp::COMPACT))                       \
+  X(filter2r_##tag, sp::L(1), sp::C(cop, 2), sp::F(), sp::L(0), sp::ST(0, sp::COMPACT))                      \
   /* a cmp s  -> materialised mask */                                                                       \
   X(mask_##tag, sp::L(0), sp::C(cop, 1), sp::PST(0, sp::LOOP))
 
@@ -95,7 +120,13 @@ template <uint32_t... S> constexpr int rows_for() {
    sp::rows_for<__VA_ARGS__>(),                                                                              \
    &pipeline_kernel<NL_STATIC_T, 16 / sizeof(NL_STATIC_T), sp::rows_for<__VA_ARGS__>(),                      \
                     sp::has_compact<__VA_ARGS__>(), sp::has_reduce<__VA_ARGS__>(), StaticProg<__VA_ARGS__>>,   \
-   sp::PipeFor<NL_STATIC_T, (sp::has_compact<__VA_ARGS__>() && !sp::has_reduce<__VA_ARGS__>()), __VA_ARGS__>::fn},
+   /* shapes that load two columns move twice the bytes per tile: the plain kernel already runs them at    */ \
+   /* 6.2-6.6 TB/s (the staged pipeline: 5.1-5.9), so only single-column shapes get a pipeline            */ \
+   sp::PipeFor<NL_STATIC_T, (sp::has_compact<__VA_ARGS__>() && !sp::has_reduce<__VA_ARGS__>() &&             \
+                             sp::loaded_columns<__VA_ARGS__>() == 1), __VA_ARGS__>::fn,                        \
+   sp::pipe_rows_for<__VA_ARGS__>(),                                                                         \
+   sp::SuperFor<NL_STATIC_T, (sp::has_compact<__VA_ARGS__>() && !sp::has_reduce<__VA_ARGS__>()), __VA_ARGS__>::fn, \
+   sp::super_rows_for<__VA_ARGS__>()},
 
 #define NL_DEFINE_STATIC_TABLE(fn_name)                                                                     \
   const StaticEntry *fn_name(int *n) {                                                                      \

@@ -12,7 +12,10 @@ from numpyllvm_b200.device import Runtime, run_pipeline
 pytestmark = pytest.mark.gpu
 
 # flags of nl_set_static_kernels(): bit 0 = build-time shapes, bit 1 = keep compaction on the plain kernel
-MODES = {"pipe-static": 1 | 8, "pipe-dynamic": 0 | 8, "plain-static": 3, "plain-dynamic": 2}   # bit 3: interpreter-driven pipeline allowed
+# bit 0: build-time shapes, bit 1: plain kernel only, bit 3: interpreter-driven pipeline allowed,
+# bit 4: staged pipeline before the super-tile kernel
+MODES = {"pipe-static": 1 | 8 | 16, "pipe-dynamic": 0 | 8 | 16, "super-static": 1, "super-dynamic": 0,
+         "plain-static": 3, "plain-dynamic": 2}
 
 
 @pytest.fixture(scope="module")
@@ -31,11 +34,15 @@ def tile_elems(dtype):
     return 512 * 4 * (16 // np.dtype(dtype).itemsize)
 
 
-def check(rt, mode, e, inputs, n, expect_pipe=True):
+def check(rt, mode, e, inputs, n, expect_pipe=True, expect_super=True):
     ref = oracle.run(e, inputs, n, n_workers=8)
     got = run_pipeline(rt, e, inputs, n)
     name = rt.last_launch()[0]
-    assert ("compact_pipe_kernel" in name) == (expect_pipe and mode.startswith("pipe")), name
+    if mode.startswith("super"):
+        # below its own size threshold the super-tile kernel hands over to the staged pipeline / plain kernel
+        assert ("compact_super_kernel" in name) == expect_super, name
+    else:
+        assert ("compact_pipe_kernel" in name) == (expect_pipe and mode.startswith("pipe")), name
     assert len(ref) == len(got)
     for r, g in zip(ref, got):
         assert r.shape == g.shape and np.array_equal(r.view(np.uint8), g.view(np.uint8))
@@ -45,7 +52,7 @@ def check(rt, mode, e, inputs, n, expect_pipe=True):
 @pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64])
 @pytest.mark.parametrize("sel", [0.0, 0.003, 0.5, 1.0])
 def test_filter_all_dtypes(rt, mode, dtype, sel):
-    n = tile_elems(dtype) * 300 + 12345          # above the pipeline threshold, ragged last tile
+    n = tile_elems(dtype) * 1300 + 12345          # above the pipeline threshold, ragged last tile
     if np.issubdtype(dtype, np.floating):
         x, thr = oracle.fill(dtype, 0, n, 5, 3), (1.0 - sel if sel > 0 else 2.0)
     else:
@@ -64,13 +71,24 @@ def test_threshold_and_tile_boundaries(rt, mode, extra):
     e = Expr(np.float64)
     xa = e.array()
     e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(0.25))))
-    check(rt, mode, e, [x, None], n, expect_pipe=(extra >= 0))
+    # (the interpreter's super-tile kernel has 4-row tiles: the same size is exactly ITS switch-over point)
+    check(rt, mode, e, [x, None], n, expect_pipe=(extra >= 0), expect_super=(mode == "super-dynamic" and extra >= 0))
+
+
+@pytest.mark.parametrize("extra", [0, 1, -1, 4096 * 4 - 1, 4096 * 4 + 1])
+def test_super_tile_threshold_and_boundaries(rt, mode, extra):
+    n = 256 * 8 * 2 * 4 * 148 + extra             # one super-tile (4 x 4096 f64) per SM: the switch-over size
+    x = oracle.fill(np.float64, 0, n, 9, 3)
+    e = Expr(np.float64)
+    xa = e.array()
+    e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(0.25))))
+    check(rt, mode, e, [x, None], n, expect_super=(extra >= 0 or mode == "super-dynamic"))
 
 
 def test_reference_filter_shape_and_two_outputs(rt, mode):
     # Tests/filter.py's a[a*2 >= 50] (re-reads a temporary after the filter) and a pipeline that
     # stores two compacted outputs
-    n = tile_elems(np.int64) * 300 + 7
+    n = tile_elems(np.int64) * 1300 + 7
     x = oracle.fill(np.int64, 0, n, 42, 0)
     e = Expr(np.int64)
     xa = e.array()
@@ -85,7 +103,7 @@ def test_reference_filter_shape_and_two_outputs(rt, mode):
 
 
 def test_ineligible_pipelines_stay_on_the_plain_kernel(rt, mode):
-    n = tile_elems(np.int64) * 300
+    n = tile_elems(np.int64) * 1300
     x = oracle.fill(np.int64, 0, n, 1, 0)
     y = oracle.fill(np.int64, 0, n, 2, 0)
     # an intermediate stored BEFORE the filter (loop index, every element)
@@ -94,7 +112,7 @@ def test_ineligible_pipelines_stay_on_the_plain_kernel(rt, mode):
     dbl = e.mul(xa, e.scalar(2))
     e.materialize(dbl)
     e.materialize(e.filter(e.ref(xa), e.ge(dbl, e.scalar(50))))
-    check(rt, mode, e, [x, None, None], n, expect_pipe=False)
+    check(rt, mode, e, [x, None, None], n, expect_pipe=False, expect_super=False)
     # nine columns cannot be staged (the plan compiler caps a pipeline at eight inputs anyway); five
     # staged columns leave fewer than four ring slots even with the narrow tiles
     e = Expr(np.int64)
@@ -110,7 +128,7 @@ def test_ineligible_pipelines_stay_on_the_plain_kernel(rt, mode):
 @pytest.mark.parametrize("sel", [0.02, 0.5, 0.97])
 def test_two_and_three_staged_columns_use_the_narrow_tiles(rt, mode, dtype, sel):
     """b[a > t] and (a*b + c)[a > t]: several columns share a ring slot (4-row instantiation)."""
-    n = tile_elems(dtype) * 330 + 17
+    n = tile_elems(dtype) * 1330 + 17
     kind = 0 if np.dtype(dtype).kind == "i" else 3
     a = oracle.fill(dtype, 0, n, kind, 1)
     b = oracle.fill(dtype, 0, n, kind, 2)
@@ -119,7 +137,8 @@ def test_two_and_three_staged_columns_use_the_narrow_tiles(rt, mode, dtype, sel)
     e = Expr(dtype)
     xa, xb = e.array(), e.array()
     e.materialize(e.filter(xb, e.gt(xa, e.scalar(thr))))
-    check(rt, mode, e, [a, b, None], n)
+    # b[a > t] has a build-time shape whose plain kernel is the faster one: no pipeline in static mode
+    check(rt, mode, e, [a, b, None], n, expect_pipe=(mode == "pipe-dynamic"))
     e = Expr(dtype)
     xa, xb, xc = e.array(), e.array(), e.array()
     e.materialize(e.filter(e.add(e.mul(e.ref(xa), xb), xc), e.gt(xa, e.scalar(thr))))
@@ -129,7 +148,7 @@ def test_two_and_three_staged_columns_use_the_narrow_tiles(rt, mode, dtype, sel)
 def test_repeated_launches_reuse_the_descriptors(rt, mode):
     # the descriptor array and the ticket are reset per launch; back-to-back launches on one
     # stream with different selectivities must not see each other's state
-    n = tile_elems(np.float32) * 300 + 99
+    n = tile_elems(np.float32) * 1300 + 99
     x = oracle.fill(np.float32, 0, n, 3, 3)
     for thr in (0.9, 0.1, 0.5, 0.9):
         e = Expr(np.float32)

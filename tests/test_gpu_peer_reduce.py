@@ -128,7 +128,7 @@ def test_needs_a_reduction_plan(rt):
 
 
 @pytest.mark.parametrize("dtype", [np.int64, np.float64, np.float32], ids=lambda d: np.dtype(d).name)
-@pytest.mark.parametrize("n", [1000, 300_001, 3_000_000])
+@pytest.mark.parametrize("n", [1000, 300_001, 3_000_000, 20_000_003])   # the last one: super-tile kernel on every shard
 def test_fused_filter_scan(rt, dtype, n):
     """a[a > t] per shard + the in-kernel exchange of the shard counts: every device must hold the
     exclusive scan of all counts, and the shards concatenated at those offsets are the oracle's result."""
