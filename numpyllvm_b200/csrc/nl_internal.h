@@ -41,6 +41,7 @@ struct KParams {
   int32_t pipe_rows;                  // 16-byte rows per consumer thread and tile of the chosen instantiation
   int32_t super_k;                    // > 0: super-tile compaction kernel (nl_compact_super.cuh), tiles per super-tile
   int32_t super_rows;                 // ... and its rows per thread
+  int32_t super_drop_from;            // CTAs with blockIdx >= this retire when they meet a dense super-tile
   // fused multi-GPU finish of a reduction over peer memory (NVLink mailboxes, nl_pipeline.cuh)
   unsigned long long *const *peer_box;   // device array: mailbox of every rank, mapped here (NULL: no fused finish)
   int32_t peer_world, peer_rank;

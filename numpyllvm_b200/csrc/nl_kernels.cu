@@ -418,7 +418,10 @@ static int launch_compact_super(const nl_plan *plan, const KParams &kp, int sm_c
   int64_t grid = (int64_t)sm_count * bps;
   if (grid > kp.n_tiles) grid = kp.n_tiles;
   if (grid < 1) grid = 1;
-  fn<<<(unsigned)grid, kBlock, 0, (cudaStream_t)stream>>>(kp);
+  KParams kq = kp;
+  // the fourth wave of CTAs (hardware places CTA b on SM b mod #SMs) may retire on dense input
+  kq.super_drop_from = (bps >= 4 && grid == (int64_t)sm_count * bps) ? 3 * sm_count : 0x7fffffff;
+  fn<<<(unsigned)grid, kBlock, 0, (cudaStream_t)stream>>>(kq);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   if (info) {

@@ -126,8 +126,20 @@ template <> struct VecOf<1> { using type = unsigned char; };
 template <typename T, int V>
 __device__ __forceinline__ void load_vec_l2(const T *__restrict__ ptr, T *dst) {
   using Vec = typename VecOf<sizeof(T) * V>::type;
-  union { Vec q; T t[V]; } u;
-  u.q = __ldcg(reinterpret_cast<const Vec *>(ptr));
+  union { Vec q; T t[V]; uint4 r; } u;
+#ifdef NL_L2_EVICT_LAST
+  if constexpr (sizeof(Vec) == 16) {
+    // L2 eviction priority "last" for rows the store pass reads again
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(u.r.x), "=r"(u.r.y), "=r"(u.r.z), "=r"(u.r.w)
+                 : "l"(ptr), "l"(pol));
+  } else
+#endif
+  {
+    u.q = __ldcg(reinterpret_cast<const Vec *>(ptr));
+  }
 #pragma unroll
   for (int v = 0; v < V; v++) dst[v] = u.t[v];
 }
