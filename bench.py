@@ -363,6 +363,7 @@ def run_extra(args, rt, lib, ranks, peak, timed):
     # (clocks ramp down, the pool maps fresh pages) out of the 20 timed steps
     k, w = max(3, min(args.steps, 20)), 25
     sizes = rt.empty(np.int64, 4)
+    lib.nl_pool_trim(0)                         # columns of the earlier arms go back to the driver: fresh, large chunks for these
     fused = rt.peer_ready()                     # NVLink mailboxes exchanged: reductions finish inside their kernel
 
     def report(name, dtype, n_per_gpu, bytes_per_gpu, ms, extra=None, k=k):
@@ -430,6 +431,7 @@ def run_extra(args, rt, lib, ranks, peak, timed):
                 ms, _ = timed(c3, k, w)
                 report(f"C3 Tests/max.py a.{opname}()" + (" + NCCL allreduce" if G > 1 else ""), nm, n3, 8 * n3, ms)
         x.free(); res.free()
+        lib.nl_pool_trim(0)
 
     # C4: a[a > t] on 2^30 f64 at 1/10/50/90 % selectivity, counts scanned across shards
     n4 = (1 << args.log2n) // G
@@ -466,6 +468,7 @@ def run_extra(args, rt, lib, ranks, peak, timed):
             report(f"C4 Tests/filter.py a[a > t] sel={int(sel * 100)}%" + (" + count scan" if G > 1 else ""), "f64", n4,
                    8 * n4 + 8 * cnt, ms, {"kept": cnt, "selectivity": round(cnt / n4, 5)})
     x.free(); y.free(); offs.free()
+    lib.nl_pool_trim(0)
 
     # C5: (a[a >= t] * k).max() over 4e9 f32 on 8 GPUs = 5e8 per GPU, single pass, no compaction
     n5 = 500_000_000

@@ -220,6 +220,10 @@ NL_API int nl_device_info(int dev, char *name, size_t name_len, int *sm_count,
 
 NL_API int nl_malloc(int dev, size_t bytes, void **ptr_out);
 NL_API int nl_free(int dev, void *ptr);
+/* Give the free blocks of the device's stream-ordered pool back to the driver (synchronises the
+ * device).  After many allocations of different sizes the pool's virtual ranges are backed by small
+ * scattered physical chunks; large columns allocated afterwards then stream a few per cent slower. */
+NL_API int nl_pool_trim(int dev);
 NL_API int nl_memset(int dev, int stream, void *ptr, int value, size_t bytes);
 NL_API int nl_host_alloc(size_t bytes, void **ptr_out);   /* pinned */
 NL_API int nl_host_free(void *ptr);

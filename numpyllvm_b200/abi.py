@@ -198,6 +198,7 @@ _SIGNATURES = {
                                  C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     "nl_malloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_VP)]),
     "nl_free": (C.c_int, [C.c_int, _VP]),
+    "nl_pool_trim": (C.c_int, [C.c_int]),
     "nl_memset": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, C.c_size_t]),
     "nl_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_VP)]),
     "nl_host_free": (C.c_int, [_VP]),

@@ -250,6 +250,17 @@ int nl_malloc(int dev, size_t bytes, void **ptr_out) {
   return NL_OK;
 }
 
+int nl_pool_trim(int dev) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  CUDA_TRY(cudaDeviceSynchronize());
+  cudaMemPool_t pool;
+  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, g_dev[dev].id));
+  CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+  return NL_OK;
+}
+
 int nl_free(int dev, void *ptr) {
   int rc = check_dev(dev, 0);
   if (rc) return rc;
