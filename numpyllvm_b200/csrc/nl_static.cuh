@@ -23,6 +23,8 @@ constexpr uint32_t C(uint32_t cop, uint32_t src) { return make_step(S_CMP, cop, 
 constexpr uint32_t F() { return make_step(S_FILTER); }
 constexpr uint32_t ST(uint32_t o, uint32_t space) { return make_step(S_STORE, o, space); }
 constexpr uint32_t PST(uint32_t o, uint32_t space) { return make_step(S_PSTORE, o, space); }
+constexpr uint32_t PSV(uint32_t j) { return make_step(S_PSAVE, j); }
+constexpr uint32_t PB(uint32_t pop, uint32_t j) { return make_step(S_PBIN, pop, j); }
 constexpr uint32_t R(uint32_t rop, uint32_t o) { return make_step(S_REDUCE, rop, o); }
 constexpr uint32_t W(uint32_t o) { return make_step(S_WHERE, o); }
 constexpr uint32_t T0 = SRC_TEMP | 0, T1 = SRC_TEMP | 1;
@@ -89,7 +91,18 @@ template <uint32_t... S> constexpr int rows_for() {
   /* a cmp s  -> materialised mask */                                                                       \
   X(mask_##tag, sp::L(0), sp::C(cop, 1), sp::PST(0, sp::LOOP))
 
+/* a[(a lo_cmp s1) & (a hi_cmp s2)]: the range filter, and the same selecting another column */
+#define NL_RANGE_SHAPES(X, tag, c1, c2)                                                                     \
+  X(filter_range_##tag, sp::L(0), sp::C(c1, 1), sp::PSV(0), sp::C(c2, 2), sp::PB(P_AND, 0), sp::F(),         \
+    sp::ST(0, sp::COMPACT))                                                                                  \
+  X(filter_range_##tag##_sum, sp::L(0), sp::C(c1, 1), sp::PSV(0), sp::C(c2, 2), sp::PB(P_AND, 0), sp::F(),   \
+    sp::R(R_SUM, 0))
+
 #define NL_STATIC_SHAPES(X)                                                                                 \
+  NL_RANGE_SHAPES(X, gt_lt, C_GT, C_LT)                                                                     \
+  NL_RANGE_SHAPES(X, ge_lt, C_GE, C_LT)                                                                     \
+  NL_RANGE_SHAPES(X, gt_le, C_GT, C_LE)                                                                     \
+  NL_RANGE_SHAPES(X, ge_le, C_GE, C_LE)                                                                     \
   /* a * b, a * 2, res * a   (Tests/assignment.py, Tests/max.py:14, C2) */                                  \
   X(mul2, sp::L(0), sp::B(V_MUL, 1), sp::ST(0, sp::LOOP))                                                    \
   X(add2, sp::L(0), sp::B(V_ADD, 1), sp::ST(0, sp::LOOP))                                                    \

@@ -156,3 +156,20 @@ def test_repeated_launches_reuse_the_descriptors(rt, mode):
         e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(thr))))
         (got,) = check(rt, mode, e, [x, None], n)
         assert len(got) == int((x > np.float32(thr)).sum())
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("ops", [("gt", "lt"), ("ge", "le"), ("ge", "lt"), ("gt", "le")], ids=lambda o: "_".join(o))
+def test_range_filter_shapes(rt, mode, dtype, ops):
+    """a[(a lo s1) & (a hi s2)] has build-time shapes (predicate temporaries before the filter)."""
+    n = tile_elems(dtype) * 1300 + 5
+    kind = 0 if np.dtype(dtype).kind == "i" else 3
+    x = oracle.fill(dtype, 0, n, kind, 6)
+    lo, hi = (np.dtype(dtype).type(v) for v in ((20, 70) if kind == 0 else (0.2, 0.7)))
+    e = Expr(dtype)
+    xa = e.array()
+    m = e.and_(getattr(e, ops[0])(e.ref(xa), e.scalar(lo)), getattr(e, ops[1])(e.ref(xa), e.scalar(hi)))
+    e.materialize(e.filter(xa, m))
+    check(rt, mode, e, [x, None, None], n)
+    if "static" in mode:
+        assert "filter_range_" in rt.last_launch()[0]

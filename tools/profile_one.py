@@ -58,6 +58,13 @@ def build(name, rt, n):
         e.materialize(e.filter(e.add(e.mul(xa, e.scalar(2.0)), e.scalar(1.0)), e.gt(e.ref(xa), e.scalar(1.0 - sel))))
         plan = abi.compile_plan(e)
         return plan, [y.ptr], [a.ptr if plan.in_[i].kind == abi.IN_ARRAY else None for i in range(plan.n_inputs)], int(8 * n * (1 + sel)), (a, y, sizes)
+    if name.startswith("c4r_"):          # a[(a > lo) & (a < hi)]: the range filter, selectivity = hi - lo
+        sel = int(name.split("_")[1]) / 100.0
+        a = rt.empty(np.float64, n); rt.fill(a, 0, 9, 3)
+        y = rt.empty(np.float64, n)
+        e = Expr(np.float64); xa = e.array()
+        e.materialize(e.filter(xa, e.and_(e.gt(e.ref(xa), e.scalar(0.25)), e.lt(e.ref(xa), e.scalar(0.25 + sel)))))
+        return abi.compile_plan(e), [y.ptr], [a.ptr, None, None], int(8 * n * (1 + sel)), (a, y, sizes)
     if name.startswith("c4b_"):          # b[a > t]: two staged columns
         sel = int(name.split("_")[1]) / 100.0
         a = rt.empty(np.float64, n); rt.fill(a, 0, 9, 3)
