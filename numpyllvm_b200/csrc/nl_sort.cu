@@ -160,10 +160,21 @@ __global__ void __launch_bounds__(kSortBlock) scatter_kernel(const UK *__restric
       key[i] = ok ? in[base + e] : (UK)0;
       dig[i] = ok ? (int)((order_key<UK, kFloat>(key[i]) >> shift) & 0xff) : -1;
     }
-    // the matches do not depend on the counters: issue all of them first so their latency overlaps
+    // lanes holding the same digit, item by item.  Eight ballots (one per digit bit) instead of
+    // match.any: measured on B200, half of the kernel's stall samples sat behind MATCH.ANY results.
     unsigned int peers[kSortItems];
 #pragma unroll
-    for (int i = 0; i < kSortItems; i++) peers[i] = __match_any_sync(0xffffffffu, dig[i] >= 0 ? dig[i] : (0x100 | lane));
+    for (int i = 0; i < kSortItems; i++) {
+      const bool ok = dig[i] >= 0;
+      unsigned int m = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+      for (int b = 0; b < 8; b++) {
+        const bool bit = (dig[i] >> b) & 1;
+        const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? bal : ~bal;
+      }
+      peers[i] = ok ? m : (1u << lane);
+    }
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
       unsigned int before = 0;
