@@ -36,6 +36,9 @@
 
 namespace nl {
 
+#ifndef NL_SORT_MIN_CTAS
+#define NL_SORT_MIN_CTAS 4
+#endif
 constexpr int kSortBlock = 256;
 constexpr int kSortItems = 8;                          // keys per thread per tile
 constexpr int kSortTile = kSortBlock * kSortItems;     // 2048
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(kSortBlock) chunk_offsets_kernel(const unsigne
 }
 
 template <typename UK, bool kFloat>
-__global__ void __launch_bounds__(kSortBlock) scatter_kernel(const UK *__restrict__ in, UK *__restrict__ out, long long n, long long chunk,
+__global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) scatter_kernel(const UK *__restrict__ in, UK *__restrict__ out, long long n, long long chunk,
                                                               int shift, const long long *__restrict__ offs) {
   __shared__ unsigned int cnt[kSortWarps][256];     // per warp: keys of each digit seen so far in the tile
   __shared__ unsigned int tile_start[256];          // exclusive scan of the tile's digit counts
@@ -233,7 +236,7 @@ template <typename UK, bool kFloat>
 static int sort_impl(cudaStream_t st, int sm_count, void *keys_v, void *tmp_v, int64_t n) {
   constexpr int P = sizeof(UK);
   UK *a = (UK *)keys_v, *b = (UK *)tmp_v;
-  int n_chunks = sm_count * 8;
+  int n_chunks = sm_count * NL_SORT_MIN_CTAS * 2;        // two full waves of resident CTAs
   long long chunk = (n + n_chunks - 1) / n_chunks;
   chunk = (chunk + kSortTile - 1) / kSortTile * kSortTile;
   n_chunks = (int)((n + chunk - 1) / chunk);
