@@ -36,6 +36,9 @@
 
 namespace nl {
 
+#ifndef NL_SORT_ITEMS32
+#define NL_SORT_ITEMS32 8
+#endif
 #ifndef NL_SORT_MIN_CTAS
 #define NL_SORT_MIN_CTAS 4
 #endif
@@ -129,14 +132,14 @@ __global__ void __launch_bounds__(kSortBlock) chunk_offsets_kernel(const unsigne
   }
 }
 
-template <typename UK, bool kFloat>
+template <typename UK, bool kFloat, int ITEMS>
 __global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) scatter_kernel(const UK *__restrict__ in, UK *__restrict__ out, long long n, long long chunk,
                                                               int shift, const long long *__restrict__ offs) {
   __shared__ unsigned int cnt[kSortWarps][256];     // per warp: keys of each digit seen so far in the tile
   __shared__ unsigned int tile_start[256];          // exclusive scan of the tile's digit counts
   __shared__ unsigned int tile_count[256];
   __shared__ long long goff[256];                   // where the next key of each digit goes
-  __shared__ UK staged[kSortTile];
+  __shared__ UK staged[(kSortBlock * ITEMS)];
   __shared__ unsigned int wsum[kSortWarps];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -146,28 +149,28 @@ __global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) scatter_kernel(c
   long long hi = lo + chunk;
   if (hi > n) hi = n;
 
-  for (long long base = lo; base < hi; base += kSortTile) {
-    const int valid = (int)((hi - base < kSortTile) ? (hi - base) : kSortTile);
+  for (long long base = lo; base < hi; base += (kSortBlock * ITEMS)) {
+    const int valid = (int)((hi - base < (kSortBlock * ITEMS)) ? (hi - base) : (kSortBlock * ITEMS));
 #pragma unroll
     for (int w = 0; w < kSortWarps; w++) cnt[w][tid] = 0;
     __syncthreads();
     // warp-striped keys: item i of lane l in warp w is tile element w*256 + i*32 + l, so the
     // order (warp, item, lane) is the input order and the ranking below is stable
-    UK key[kSortItems];
-    unsigned int rank[kSortItems];
-    int dig[kSortItems];
+    UK key[ITEMS];
+    unsigned int rank[ITEMS];
+    int dig[ITEMS];
 #pragma unroll
-    for (int i = 0; i < kSortItems; i++) {
-      const int e = warp * (32 * kSortItems) + i * 32 + lane;
+    for (int i = 0; i < ITEMS; i++) {
+      const int e = warp * (32 * ITEMS) + i * 32 + lane;
       const bool ok = e < valid;
       key[i] = ok ? in[base + e] : (UK)0;
       dig[i] = ok ? (int)((order_key<UK, kFloat>(key[i]) >> shift) & 0xff) : -1;
     }
     // lanes holding the same digit, item by item.  Eight ballots (one per digit bit) instead of
     // match.any: measured on B200, half of the kernel's stall samples sat behind MATCH.ANY results.
-    unsigned int peers[kSortItems];
+    unsigned int peers[ITEMS];
 #pragma unroll
-    for (int i = 0; i < kSortItems; i++) {
+    for (int i = 0; i < ITEMS; i++) {
       const bool ok = dig[i] >= 0;
       unsigned int m = __ballot_sync(0xffffffffu, ok);
 #pragma unroll
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) scatter_kernel(c
       peers[i] = ok ? m : (1u << lane);
     }
 #pragma unroll
-    for (int i = 0; i < kSortItems; i++) {
+    for (int i = 0; i < ITEMS; i++) {
       unsigned int before = 0;
       if (dig[i] >= 0) before = cnt[warp][dig[i]];
       __syncwarp();
@@ -215,11 +218,11 @@ __global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) scatter_kernel(c
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kSortItems; i++)
+    for (int i = 0; i < ITEMS; i++)
       if (dig[i] >= 0) staged[tile_start[dig[i]] + cnt[warp][dig[i]] + rank[i]] = key[i];
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < kSortItems; i++) {
+    for (int i = 0; i < ITEMS; i++) {
       const int pos = i * kSortBlock + tid;
       if (pos < valid) {
         const UK k = staged[pos];
@@ -235,10 +238,13 @@ __global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) scatter_kernel(c
 template <typename UK, bool kFloat>
 static int sort_impl(cudaStream_t st, int sm_count, void *keys_v, void *tmp_v, int64_t n) {
   constexpr int P = sizeof(UK);
+  // keys per thread and tile in the scatter: 16 KB of keys per tile for either key width
+  constexpr int ITEMS = (sizeof(UK) == 4) ? NL_SORT_ITEMS32 : kSortItems;
+  constexpr int TILE = kSortBlock * ITEMS;
   UK *a = (UK *)keys_v, *b = (UK *)tmp_v;
   int n_chunks = sm_count * NL_SORT_MIN_CTAS * 2;        // two full waves of resident CTAs
   long long chunk = (n + n_chunks - 1) / n_chunks;
-  chunk = (chunk + kSortTile - 1) / kSortTile * kSortTile;
+  chunk = (chunk + TILE - 1) / TILE * TILE;
   n_chunks = (int)((n + chunk - 1) / chunk);
 
   unsigned long long *ghist = nullptr;
@@ -263,7 +269,7 @@ static int sort_impl(cudaStream_t st, int sm_count, void *keys_v, void *tmp_v, i
     if (trivial) continue;
     chunk_histogram_kernel<UK, kFloat><<<n_chunks, kSortBlock, 0, st>>>(src, n, chunk, 8 * p, hist);
     chunk_offsets_kernel<<<256, kSortBlock, 0, st>>>(ghist + p * 256, hist, n_chunks, offs);
-    scatter_kernel<UK, kFloat><<<n_chunks, kSortBlock, 0, st>>>(src, dst, n, chunk, 8 * p, offs);
+    scatter_kernel<UK, kFloat, ITEMS><<<n_chunks, kSortBlock, 0, st>>>(src, dst, n, chunk, 8 * p, offs);
     CUDA_TRY(cudaGetLastError());
     count_launch(3);
     UK *t = src; src = dst; dst = t;
