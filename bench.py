@@ -353,6 +353,50 @@ def run_e2e_jit(args, ranks, n):
             "parity": "bit-exact on sampled windows" if ok else "MISMATCH"}
 
 
+def _reduce_device(rt, abi, Expr, op, dtype, ptr, n, sizes):
+    """op over a device column through the reduction pipeline (used for full-size property checks)."""
+    res = rt.empty(dtype, 1)
+    e = Expr(dtype)
+    e.materialize(e.unop(op, e.array()))
+    rt.launch(abi.compile_plan(e), [res.ptr], [ptr], 0, n, sizes.ptr)
+    v = rt.download(res)[0]
+    res.free()
+    return v
+
+
+def filter_properties(rt, abi, Expr, x, y, n, cnt, thr, sizes):
+    """Size-independent checks of a[a > t] at full size: every survivor passes the predicate and the
+    survivors' sum equals the fused a[a > t].sum() pipeline's (same multiset)."""
+    dt = np.float64
+    ok_min = bool(cnt == 0 or _reduce_device(rt, abi, Expr, abi.OP_MIN, dt, y.ptr, cnt, sizes) > thr)
+    s_out = _reduce_device(rt, abi, Expr, abi.OP_SUM, dt, y.ptr, cnt, sizes) if cnt else 0.0
+    res = rt.empty(dt, 1)
+    e = Expr(dt)
+    xa = e.array()
+    e.materialize(e.sum(e.filter(xa, e.gt(e.ref(xa), e.scalar(thr)))))
+    rt.launch(abi.compile_plan(e), [res.ptr], [x.ptr, None], 0, n, sizes.ptr)
+    s_fused = rt.download(res)[0]
+    res.free()
+    return {"all_survivors_pass": ok_min, "sum_equals_fused_filter_sum": bool(abs(s_out - s_fused) <= 1e-9 * max(1.0, abs(s_fused)))}
+
+
+def sort_properties(rt, abi, Expr, lib, x, n, dt, sum_before, sizes):
+    """Full-size checks of the device sort: no inversion anywhere (count of y[i+1] < y[i] is zero) and,
+    for integers, the wrapping sum is unchanged (same multiset)."""
+    es = np.dtype(dt).itemsize
+    scratch = rt.empty(dt, n)
+    e = Expr(dt)
+    nxt, cur = e.array(), e.array()
+    e.materialize(e.filter(nxt, e.lt(e.ref(nxt), cur)))
+    rt.launch(abi.compile_plan(e), [scratch.ptr], [x.ptr + es, x.ptr], 0, n - 1, sizes.ptr)
+    inversions = int(rt.download(sizes, 1)[0])
+    scratch.free()
+    out = {"inversions": inversions}
+    if np.dtype(dt).kind == "i":
+        out["sum_unchanged"] = bool(_reduce_device(rt, abi, Expr, abi.OP_SUM, dt, x.ptr, n, sizes) == sum_before)
+    return out
+
+
 def run_extra(args, rt, lib, ranks, peak, timed):
     """C1, C3, C4, C5 of BASELINE.json: GB/s, elements/s and fraction of the HBM roofline."""
     from numpyllvm_b200 import abi
@@ -465,8 +509,11 @@ def run_extra(args, rt, lib, ranks, peak, timed):
         else:
             ms, _ = timed(c4, k, w)
             cnt = int(rt.download(sizes, 1)[0])
+            extra = {"kept": cnt, "selectivity": round(cnt / n4, 5)}
+            if G == 1:
+                extra["properties_at_full_size"] = filter_properties(rt, abi, Expr, x, y, n4, cnt, 1.0 - sel, sizes)
             report(f"C4 Tests/filter.py a[a > t] sel={int(sel * 100)}%" + (" + count scan" if G > 1 else ""), "f64", n4,
-                   8 * n4 + 8 * cnt, ms, {"kept": cnt, "selectivity": round(cnt / n4, 5)})
+                   8 * n4 + 8 * cnt, ms, extra)
     x.free(); y.free(); offs.free()
     lib.nl_pool_trim(0)
 
@@ -506,9 +553,11 @@ def run_extra(args, rt, lib, ranks, peak, timed):
         for dt, kind, nm in ((np.int64, 1, "i64 full range"), (np.float64, 3, "f64 in [0,1)"), (np.int64, 0, "i64 in [1,100) like Tests/")):
             x = rt.empty(dt, n6)
             tmp = rt.empty(dt, n6)
-            best, passes = None, 0
+            best, passes, sum_before = None, 0, None
             for rep in range(3):
                 rt.fill(x, 0, 5 + rep, kind)
+                if np.dtype(dt).kind == "i":
+                    sum_before = _reduce_device(rt, abi, Expr, abi.OP_SUM, dt, x.ptr, n6, sizes)
                 rt.sync()
                 l0 = lib.nl_launch_count()
                 e0, e1 = rt.event(), rt.event()
@@ -524,7 +573,8 @@ def run_extra(args, rt, lib, ranks, peak, timed):
             out.append({"config": f"sort() device radix sort, {nm}", "dtype": np.dtype(dt).name, "elements_per_gpu": n6,
                         "ms_per_step": round(best, 4), "Gkeys/s": round(n6 / best / 1e6, 2), "radix_passes": int(passes),
                         "GB/s": round(traffic / best / 1e6, 1), "frac_of_measured_peak": round(traffic / best / 1e6 / peak, 4),
-                        "sorted": bool(np.all(head[:-1] <= head[1:]))})
+                        "sorted": bool(np.all(head[:-1] <= head[1:])),
+                        "properties_at_full_size": sort_properties(rt, abi, Expr, lib, x, n6, dt, sum_before, sizes)})
             x.free(); tmp.free()
     return out
 
