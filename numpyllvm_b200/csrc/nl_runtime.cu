@@ -33,7 +33,6 @@ constexpr size_t kRedPartialsOff = 256;        // 8 B x kMaxGrid
 constexpr size_t kMaxGrid = 8192;
 constexpr size_t kTileTicketOff = kRedPartialsOff + 8 * kMaxGrid;   // u32, zeroed per compact launch
 constexpr size_t kTileDescOff = kTileTicketOff + 256;               // 8 B x n_tiles, zeroed per compact launch
-constexpr size_t kGatherOff = 0;               // gather buffer lives in its own small allocation
 
 struct Scratch {
   char *base = nullptr;
