@@ -318,6 +318,17 @@ NL_API int nl_assign_copy(int dev, int stream, void *dst, int dtype,
 NL_API int nl_fill(int dev, int stream, void *dst, int dtype, int64_t first_index,
             int64_t count, uint64_t seed, int kind);
 
+/* Integer-array indexing (declared but never implemented in the reference: `a[idx]` with an int64
+ * index has a cardinality function but no emitter, thunk_as_mapping.cpp:51-55):
+ *   out[i] = column[idx[i]],  i in [0, count)
+ * `column` is passed as its shards — device pointers that may live on other local GPUs (read with
+ * peer loads over NVLink; requires nl_comm_init) — with the global index of each shard's first
+ * element.  Negative indices wrap as in NumPy; *bad (DEVICE int64, caller-zeroed) counts the
+ * indices outside [-total, total). */
+NL_API int nl_gather(int dev, int stream, int dtype, void *out, const int64_t *idx, int64_t count,
+              const void *const *shard_ptr, const int64_t *shard_start, int n_shards, int64_t total,
+              int64_t *bad);
+
 /* Sort `count` keys of `dtype` on the device, ascending, NaNs last (NumPy order) — the `base`
  * function of the sort() full breaker (PyArray_Sort on a copy, thunk_methods.cpp:37-62; run by
  * compiler.cpp:93-122).  In place in `keys`; `tmp` is scratch of the same size.  LSD radix

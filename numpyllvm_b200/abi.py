@@ -227,6 +227,7 @@ _SIGNATURES = {
     "nl_assign_copy": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, C.c_int64, C.c_int64, C.c_int64, _VP]),
     "nl_fill": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_int]),
     "nl_sort": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int64]),
+    "nl_gather": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int64, C.POINTER(_VP), C.POINTER(C.c_int64), C.c_int, C.c_int64, _VP]),
     "nl_comm_unique_id": (C.c_int, [_VP]),
     "nl_comm_init": (C.c_int, [_VP, C.c_int, C.c_int]),
     "nl_comm_world_size": (C.c_int, []),

@@ -6,6 +6,7 @@
 // the target, force the target, then update it in place (thunk_as_mapping.cpp:80-86) — but
 // the update runs on the device (the reference delegated to NumPy setitem on host storage).
 #include "thunk.hpp"
+#include <vector>
 #include "scheduler.hpp"
 
 #include <algorithm>
@@ -15,8 +16,88 @@ static ssize_t subscript_cardinality_function(ssize_t *inputs) {
   return inputs[1];     // upper bound: the mask's size (thunk_as_mapping.cpp:32-35)
 }
 
+// a[idx] with an int64 index thunk: declared in the reference (cardinality function, IndexError
+// FIXME) but without an emitter (thunk_as_mapping.cpp:51-55).  Here it is an eager operation: both
+// operands are evaluated, every GPU gathers the elements its shard of `idx` names — from whichever
+// GPU holds them, with peer loads over NVLink — and the result is an evaluated thunk laid out like
+// `idx`.  Negative indices wrap as in NumPy; an index outside [-n, n) raises IndexError.
+static PyObject *thunk_gather(PyThunkObject *self, PyThunkObject *index) {
+  if (PyThunk_Evaluate(self) == NULL || PyThunk_Evaluate(index) == NULL) return NULL;
+  if (PyThunk_EnsureDevice(self) < 0 || PyThunk_EnsureDevice(index) < 0) return NULL;
+  Storage *col = self->storage, *idx = index->storage;
+  if (col->host_scalar || idx->host_scalar || col->replicated || idx->replicated) {
+    PyErr_SetString(PyExc_IndexError, "integer-array indexing of / by a one-element thunk is not supported");
+    return NULL;
+  }
+  if (nljit_ensure_runtime() < 0) return NULL;
+  const int64_t total = col->cardinality();
+  const void *ptrs[NL_MAX_DEVICES];
+  int64_t starts[NL_MAX_DEVICES];
+  int n_shards = 0;
+  int64_t run = 0;
+  for (const Shard &sh : col->shards) {
+    ptrs[n_shards] = sh.ptr ? sh.ptr : (const void *)16;
+    starts[n_shards] = run;
+    run += sh.count;
+    n_shards++;
+  }
+  Storage *out = storage_new(col->dtype, idx->bound);
+  out->ragged = idx->ragged;
+  const size_t es = nl_dtype_size(col->dtype);
+  int rc = NL_OK;
+  std::vector<int64_t *> bad(idx->shards.size(), (int64_t *)NULL);
+  for (size_t g = 0; g < idx->shards.size() && rc == NL_OK; g++) {
+    const Shard &is = idx->shards[g];
+    Shard os = is;
+    os.ptr = NULL;
+    os.capacity = is.count;
+    if (is.count > 0) rc = nl_malloc(is.dev, (size_t)is.count * es, &os.ptr);
+    out->shards.push_back(os);
+    if (rc != NL_OK || is.count == 0) continue;
+    rc = nl_malloc(is.dev, sizeof(int64_t), (void **)&bad[g]);
+    if (rc == NL_OK) rc = nl_memset(is.dev, 0, bad[g], 0, sizeof(int64_t));
+    if (rc == NL_OK)
+      rc = nl_gather(is.dev, 0, col->dtype, os.ptr, (const int64_t *)is.ptr, is.count, ptrs, starts, n_shards, total, bad[g]);
+  }
+  int64_t n_bad = 0;
+  for (size_t g = 0; g < bad.size(); g++) {
+    if (!bad[g]) continue;
+    int64_t v = 0;
+    if (rc == NL_OK) rc = nl_memcpy_d2h(idx->shards[g].dev, 0, &v, bad[g], sizeof(v));
+    if (rc == NL_OK) rc = nl_stream_sync(idx->shards[g].dev, 0);
+    n_bad += v;
+    nl_free(idx->shards[g].dev, bad[g]);
+  }
+  if (rc != NL_OK) { storage_decref(out); nljit_raise(rc, "jit: gather failed"); return NULL; }
+  if (n_bad > 0) {
+    storage_decref(out);
+    PyErr_Format(PyExc_IndexError, "%lld indices are out of bounds for a thunk of %lld elements", (long long)n_bad, (long long)total);
+    return NULL;
+  }
+  // an evaluated thunk around the gathered storage
+  npy_intp zero = 0;
+  PyObject *empty = PyArray_SimpleNew(1, &zero, self->npy_type);
+  if (!empty) { storage_decref(out); return NULL; }
+  PyObject *t = PyThunk_FromArray(NULL, empty);
+  Py_DECREF(empty);
+  if (!t) { storage_decref(out); return NULL; }
+  PyThunk_MarkEvaluated((PyThunkObject *)t, out);
+  return t;
+}
+
 static PyObject *thunk_subscript(PyObject *self_o, PyObject *other) {
   PyThunkObject *self = (PyThunkObject *)self_o;
+  if (PyArray_Check(other) && PyArray_ISINTEGER((PyArrayObject *)other) && PyArray_NDIM((PyArrayObject *)other) == 1) {
+    // an integer ndarray as index: wrap it (as int64) and gather
+    PyObject *as64 = PyArray_FromAny(other, PyArray_DescrFromType(NPY_INT64), 1, 1, NPY_ARRAY_C_CONTIGUOUS | NPY_ARRAY_FORCECAST, NULL);
+    if (!as64) return NULL;
+    PyObject *it = PyThunk_FromArray(NULL, as64);
+    Py_DECREF(as64);
+    if (!it) return NULL;
+    PyObject *r = thunk_gather(self, (PyThunkObject *)it);
+    Py_DECREF(it);
+    return r;
+  }
   if (!PyThunk_Check(other)) {
     PyErr_SetString(PyExc_IndexError, "FIXME: other types of array access");   // thunk_as_mapping.cpp:61
     return NULL;
@@ -37,9 +118,9 @@ static PyObject *thunk_subscript(PyObject *self_o, PyObject *other) {
     if (!op) return PyErr_NoMemory();
     return PyThunk_FromOperation(op, subscript_cardinality_function, CardinalityKind::UpperBound, self->npy_type);
   }
-  if (other_thunk->npy_type == NPY_INT64 || other_thunk->npy_type == NPY_INT32) {
-    // declared but never implemented in the reference (no emitter, thunk_as_mapping.cpp:51-55)
-    PyErr_SetString(PyExc_IndexError, "integer-array indexing (gather) is not implemented");
+  if (other_thunk->npy_type == NPY_INT64) return thunk_gather(self, other_thunk);
+  if (other_thunk->npy_type == NPY_INT32) {
+    PyErr_SetString(PyExc_IndexError, "integer-array indexing takes int64 indices");
     return NULL;
   }
   PyErr_SetString(PyExc_IndexError, "arrays used as indices must be of integer (or boolean) type");

@@ -81,6 +81,8 @@ int launch_assign_copy(void *stream, int sm_count, void *dst, int dtype, int64_t
 int launch_scan_offsets(void *stream, const int64_t *counts, int n, int64_t *offsets);
 int launch_fill(void *stream, int sm_count, void *dst, int dtype, int64_t first_index, int64_t count, uint64_t seed, int kind);
 int launch_empty_range(void *stream, const nl_plan *plan, const KParams &kp);
+int launch_gather(void *stream, int sm_count, int dtype, void *out, const int64_t *idx, int64_t count, const void *const *shard_ptr,
+                  const int64_t *shard_start, int n_shards, int64_t total, int64_t *bad);
 // nl_sort.cu
 int launch_sort(void *stream, int sm_count, int dtype, void *keys, void *tmp, int64_t n);
 int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t name_len, int *is_static);

@@ -489,6 +489,57 @@ int launch_finalize_partials(void *stream, int rop, int dtype, const void *parti
   return NL_OK;
 }
 
+// ---- gather: out[i] = column[idx[i]] --------------------------------------------------------
+// The column is given as its shards; a shard may live on another GPU of the box and is then read
+// with peer loads over NVLink (the mappings exist once the communicator is up).  Negative indices
+// wrap like NumPy's; indices outside [-total, total) are counted in *bad and read element 0.
+struct GatherShards {
+  const void *ptr[NL_MAX_DEVICES];
+  long long start[NL_MAX_DEVICES + 1];   // first global index of each shard; start[n] = total
+  int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_kernel(T *__restrict__ out, const long long *__restrict__ idx, long long count,
+                                                      const __grid_constant__ GatherShards sh, unsigned long long *bad) {
+  const long long total = sh.start[sh.n];
+  unsigned int my_bad = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    long long j = __ldcs(idx + i);
+    if (j < 0) j += total;
+    if (j < 0 || j >= total) { my_bad++; j = 0; }
+    int s = 0;
+#pragma unroll 1
+    while (s + 1 < sh.n && j >= sh.start[s + 1]) s++;
+    out[i] = total > 0 ? reinterpret_cast<const T *>(sh.ptr[s])[j - sh.start[s]] : T(0);
+  }
+  my_bad = __reduce_add_sync(0xffffffffu, my_bad);
+  if ((threadIdx.x & 31) == 0 && my_bad) atomicAdd(bad, (unsigned long long)my_bad);
+}
+
+int launch_gather(void *stream, int sm_count, int dtype, void *out, const int64_t *idx, int64_t count, const void *const *shard_ptr,
+                  const int64_t *shard_start, int n_shards, int64_t total, int64_t *bad) {
+  GatherShards sh;
+  memset(&sh, 0, sizeof(sh));
+  sh.n = n_shards;
+  for (int k = 0; k < n_shards; k++) { sh.ptr[k] = shard_ptr[k]; sh.start[k] = shard_start[k]; }
+  sh.start[n_shards] = total;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (count + 255) / 256;
+  const int64_t cap = (int64_t)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  switch (nl_dtype_size(dtype)) {
+    case 4: gather_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>((uint32_t *)out, (const long long *)idx, count, sh, (unsigned long long *)bad); break;
+    case 8: gather_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, st>>>((unsigned long long *)out, (const long long *)idx, count, sh, (unsigned long long *)bad); break;
+    case 1: gather_kernel<unsigned char><<<(unsigned)blocks, 256, 0, st>>>((unsigned char *)out, (const long long *)idx, count, sh, (unsigned long long *)bad); break;
+    default: set_error("nl_gather: bad dtype"); return NL_ERR_INVALID;
+  }
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return NL_OK;
+}
+
 static unsigned grid_for(int64_t work_items, int sm_count) {
   int64_t blocks = (work_items + 255) / 256;
   const int64_t cap = (int64_t)sm_count * 8;

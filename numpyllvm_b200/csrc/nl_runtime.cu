@@ -525,6 +525,17 @@ int nl_fill(int dev, int stream, void *dst, int dtype, int64_t first_index, int6
   return launch_fill(g_dev[dev].stream[stream], g_dev[dev].sm_count, dst, dtype, first_index, count, seed, kind);
 }
 
+int nl_gather(int dev, int stream, int dtype, void *out, const int64_t *idx, int64_t count, const void *const *shard_ptr,
+              const int64_t *shard_start, int n_shards, int64_t total, int64_t *bad) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (count < 0 || n_shards < 1 || n_shards > NL_MAX_DEVICES || total < 0 || !shard_ptr || !shard_start || !bad ||
+      (count > 0 && (!out || !idx))) { set_error("nl_gather: bad argument"); return NL_ERR_INVALID; }
+  if (count == 0) return NL_OK;
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_gather(g_dev[dev].stream[stream], g_dev[dev].sm_count, dtype, out, idx, count, shard_ptr, shard_start, n_shards, total, bad);
+}
+
 int nl_sort(int dev, int stream, int dtype, void *keys, void *tmp, int64_t count) {
   int rc = check_dev(dev, stream);
   if (rc) return rc;
@@ -600,6 +611,21 @@ static int setup_local_mailboxes() {
       cudaError_t err = cudaDeviceEnablePeerAccess(g_dev[e].id, 0);
       if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
       else if (err != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(err)); return NL_ERR_CUDA; }
+    }
+  }
+  // columns come from the stream-ordered pools: peers may read and write them too (gather reads
+  // remote shards with plain loads; cudaDeviceEnablePeerAccess alone does not cover pool memory)
+  for (int d = 0; d < g_ndev; d++) {
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, g_dev[d].id));
+    for (int e = 0; e < g_ndev; e++) {
+      if (d == e) continue;
+      cudaMemAccessDesc desc;
+      memset(&desc, 0, sizeof(desc));
+      desc.location.type = cudaMemLocationTypeDevice;
+      desc.location.id = g_dev[e].id;
+      desc.flags = cudaMemAccessFlagsProtReadWrite;
+      CUDA_TRY(cudaMemPoolSetAccess(pool, &desc, 1));
     }
   }
   unsigned long long *table[kMaxWorld] = {nullptr};

@@ -290,3 +290,39 @@ def test_results_can_stay_on_the_device():
     assert np.array_equal(got, a_n * 2 + 1)
     total = numpyllvm_b200.device_shards(jit.thunk(np.arange(1000, dtype=np.int64)).sum())
     assert len(total) == 1 and total[0].count == 1
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64], ids=lambda d: np.dtype(d).name)
+def test_integer_array_indexing_gathers_across_shards(dtype):
+    """a[idx] with an int64 index (declared but unimplemented in the reference): every GPU gathers the
+    elements its shard of idx names, from whichever GPU holds them."""
+    rng = np.random.default_rng(23)
+    n, m = 1_000_003, 700_001
+    a_n = (rng.random(n) * 1000).astype(dtype)
+    idx_n = rng.integers(-n, n, m)                               # negative indices wrap like NumPy's
+    a, idx = jit.thunk(a_n), jit.thunk(idx_n)
+    g = a[idx]
+    assert g.isevaluated() and len(g) == m
+    assert g.asnumpyarray().tobytes() == a_n[idx_n].tobytes()
+    assert (g * 2).asnumpyarray().tobytes() == (a_n[idx_n] * 2).tobytes()   # the result is an ordinary column
+    assert a[idx_n[:1000]].asnumpyarray().tobytes() == a_n[idx_n[:1000]].tobytes()   # ndarray index
+    perm = rng.permutation(n)
+    assert np.array_equal(a[jit.thunk(perm)].sort().asnumpyarray(), np.sort(a_n))
+    with pytest.raises(IndexError):
+        a[jit.thunk(np.array([0, 5, n], dtype=np.int64))]
+    with pytest.raises(IndexError):
+        a[jit.thunk(np.array([0, 1], dtype=np.int32))]
+
+
+def test_gather_by_a_filtered_index_and_of_a_filtered_column():
+    rng = np.random.default_rng(29)
+    n = 600_000
+    a_n = rng.integers(0, 1000, n)
+    idx_n = rng.integers(0, n, n)
+    a, idx = jit.thunk(a_n), jit.thunk(idx_n)
+    small = idx[idx < 1000]                                      # ragged index thunk
+    assert np.array_equal(a[small].asnumpyarray(), a_n[idx_n[idx_n < 1000]])
+    f = a[a >= 500]                                              # ragged column
+    k = len(f)
+    pick = rng.integers(0, k, 5000)
+    assert np.array_equal(f[jit.thunk(pick)].asnumpyarray(), a_n[a_n >= 500][pick])
