@@ -58,7 +58,9 @@ def test_error_behaviour():
     with pytest.raises(IndexError):
         a[jit.thunk(np.arange(3.0))]                      # indices must be integer or boolean
     with pytest.raises(IndexError):
-        a[jit.thunk(np.arange(3))]                        # integer gather: declared, not implemented
+        a[jit.thunk(np.arange(3, dtype=np.int32))]        # integer gather takes int64 indices
+    with pytest.raises(RuntimeError):
+        a[jit.thunk(np.arange(3))]                        # the gather is eager: without a GPU it fails loudly
     with pytest.raises(TypeError):
         a * jit.thunk(np.arange(7))                       # "Incompatible cardinality." (the check Q9 broke)
     with pytest.raises(TypeError):
