@@ -31,7 +31,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 NVCC_FLAGS += os.environ.get("NL_EXTRA_NVCC_FLAGS", "").split()   # tuning experiments (-DNL_PIPE_ROWS=8 ...); use with --force
 
 KERNEL_SOURCES = ["nl_plan.cpp", "nl_kernels.cu", "nl_runtime.cu", "nl_sort.cu",
-                  "nl_static_i32.cu", "nl_static_i64.cu", "nl_static_f32.cu", "nl_static_f64.cu"]
+                  "nl_dynamic_i32.cu", "nl_dynamic_i64.cu", "nl_dynamic_f32.cu", "nl_dynamic_f64.cu",
+                  "nl_static_i32.cu", "nl_static_i64.cu", "nl_static_f32.cu", "nl_static_f64.cu",
+                  "nl_static_i32_b.cu", "nl_static_i64_b.cu", "nl_static_f32_b.cu", "nl_static_f64_b.cu"]
 JIT_SOURCES = ["jitpackage.cpp", "device_sort.cpp", "thunk.cpp", "operation.cpp", "thunk_as_number.cpp", "thunk_as_mapping.cpp",
                "thunk_as_sequence.cpp", "thunk_methods.cpp", "parser.cpp", "optimizer.cpp", "scheduler.cpp",
                "debug_printer.cpp", "storage.cpp"]
@@ -73,7 +75,7 @@ def build_kernels(force: bool = False, verbose: bool = False, ptxas_info: bool =
             jobs.append(cmd)
     logs = []
     if jobs:
-        with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             logs = list(ex.map(lambda c: _run(c, verbose), jobs))
     if jobs or force or _stale(out, objs):
         _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-ldl", "-lpthread"], verbose)

@@ -122,31 +122,17 @@ __global__ void __launch_bounds__(256) fill_kernel(T *__restrict__ dst, int64_t 
 template <> struct TT<unsigned char> { static constexpr bool is_float = false; };
 
 // ------------------------------------------------------------------ host-side dispatch
-template <typename T, class Prog>
-static pipeline_fn pick_T(bool vec16, bool compact, bool reduce) {
-  constexpr int V16 = 16 / sizeof(T);
-  if (vec16) {
-    if (compact) return reduce ? pipeline_kernel<T, V16, kRows, true, true, Prog> : pipeline_kernel<T, V16, kRows, true, false, Prog>;
-    return reduce ? pipeline_kernel<T, V16, kRows, false, true, Prog> : pipeline_kernel<T, V16, kRows, false, false, Prog>;
-  }
-  if (compact) return reduce ? pipeline_kernel<T, 1, kRows, true, true, Prog> : pipeline_kernel<T, 1, kRows, true, false, Prog>;
-  return reduce ? pipeline_kernel<T, 1, kRows, false, true, Prog> : pipeline_kernel<T, 1, kRows, false, false, Prog>;
-}
-
-// the dynamic interpreter for (dtype, row width, mode); plans that never save a value temporary
-// take the light variant (fewer registers, one more resident CTA per SM: measured +10-17 %)
-template <class Prog>
-static pipeline_fn pick_dynamic_P(int dtype, bool vec16, bool compact, bool reduce) {
+// The interpreter-driven kernels are instantiated per dtype in nl_dynamic_<dtype>.cu (one translation
+// unit each, so the build spreads over the cores); plans that never save a value temporary take the
+// light variant (fewer registers, one more resident CTA per SM: measured +10-17 %).
+static pipeline_fn pick_dynamic(int dtype, bool vec16, bool compact, bool reduce, bool uses_temps) {
   switch (dtype) {
-    case NL_I32: return pick_T<int32_t, Prog>(vec16, compact, reduce);
-    case NL_I64: return pick_T<long long, Prog>(vec16, compact, reduce);
-    case NL_F32: return pick_T<float, Prog>(vec16, compact, reduce);
-    case NL_F64: return pick_T<double, Prog>(vec16, compact, reduce);
+    case NL_I32: return dynamic_kernel_i32(vec16, compact, reduce, uses_temps);
+    case NL_I64: return dynamic_kernel_i64(vec16, compact, reduce, uses_temps);
+    case NL_F32: return dynamic_kernel_f32(vec16, compact, reduce, uses_temps);
+    case NL_F64: return dynamic_kernel_f64(vec16, compact, reduce, uses_temps);
   }
   return nullptr;
-}
-static pipeline_fn pick_dynamic(int dtype, bool vec16, bool compact, bool reduce, bool uses_temps) {
-  return uses_temps ? pick_dynamic_P<DynProg>(dtype, vec16, compact, reduce) : pick_dynamic_P<DynProgLight>(dtype, vec16, compact, reduce);
 }
 
 // kernel-template selection: a build-time instantiation when the plan's step sequence is in
@@ -156,17 +142,19 @@ void set_static_kernels_enabled(int on) { g_static_enabled = on; }
 
 static const StaticEntry *find_static(const nl_plan *plan, bool vec16) {
   if (!g_static_enabled || !vec16) return nullptr;
-  int n = 0;
-  const StaticEntry *tab = nullptr;
-  switch (plan->dtype) {
-    case NL_I32: tab = static_table_i32(&n); break;
-    case NL_I64: tab = static_table_i64(&n); break;
-    case NL_F32: tab = static_table_f32(&n); break;
-    case NL_F64: tab = static_table_f64(&n); break;
-    default: return nullptr;
+  for (int half = 0; half < 2; half++) {          // the shape list is compiled in two halves per dtype
+    int n = 0;
+    const StaticEntry *tab = nullptr;
+    switch (plan->dtype) {
+      case NL_I32: tab = half ? static_table_i32_b(&n) : static_table_i32(&n); break;
+      case NL_I64: tab = half ? static_table_i64_b(&n) : static_table_i64(&n); break;
+      case NL_F32: tab = half ? static_table_f32_b(&n) : static_table_f32(&n); break;
+      case NL_F64: tab = half ? static_table_f64_b(&n) : static_table_f64(&n); break;
+      default: return nullptr;
+    }
+    for (int i = 0; i < n; i++)
+      if (tab[i].matches(plan->step, plan->n_steps)) return &tab[i];
   }
-  for (int i = 0; i < n; i++)
-    if (tab[i].matches(plan->step, plan->n_steps)) return &tab[i];
   return nullptr;
 }
 
@@ -194,20 +182,11 @@ static const char *dt_name(int d) {
 
 // the interpreter's staged compaction pipeline, one per dtype
 static pipeline_fn pick_dynamic_pipe(int dtype, int rows) {
-  if (rows == kPipeRowsNarrow) {
-    switch (dtype) {
-      case NL_I32: return compact_pipe_kernel<int32_t, 4, DynSplit, kPipeRowsNarrow>;
-      case NL_I64: return compact_pipe_kernel<long long, 2, DynSplit, kPipeRowsNarrow>;
-      case NL_F32: return compact_pipe_kernel<float, 4, DynSplit, kPipeRowsNarrow>;
-      case NL_F64: return compact_pipe_kernel<double, 2, DynSplit, kPipeRowsNarrow>;
-    }
-    return nullptr;
-  }
   switch (dtype) {
-    case NL_I32: return compact_pipe_kernel<int32_t, 4, DynSplit>;
-    case NL_I64: return compact_pipe_kernel<long long, 2, DynSplit>;
-    case NL_F32: return compact_pipe_kernel<float, 4, DynSplit>;
-    case NL_F64: return compact_pipe_kernel<double, 2, DynSplit>;
+    case NL_I32: return dynamic_pipe_i32(rows);
+    case NL_I64: return dynamic_pipe_i64(rows);
+    case NL_F32: return dynamic_pipe_f32(rows);
+    case NL_F64: return dynamic_pipe_f64(rows);
   }
   return nullptr;
 }
@@ -257,18 +236,12 @@ static int g_prefer_pipe = 0;      // tuning: staged pipeline before the super-t
 void set_compact_prefer_pipe(int on) { g_prefer_pipe = on; }
 
 // the interpreter's super-tile kernel
-template <typename T>
-static pipeline_fn pick_super_T(bool uses_temps) {
-  constexpr int V16 = 16 / sizeof(T);
-  return uses_temps ? compact_super_kernel<T, V16, kRows, DynSplit, true, kMinBlocks>
-                    : compact_super_kernel<T, V16, kRows, DynSplit, false, kMinBlocksLight>;
-}
 static pipeline_fn pick_dynamic_super(int dtype, bool uses_temps) {
   switch (dtype) {
-    case NL_I32: return pick_super_T<int32_t>(uses_temps);
-    case NL_I64: return pick_super_T<long long>(uses_temps);
-    case NL_F32: return pick_super_T<float>(uses_temps);
-    case NL_F64: return pick_super_T<double>(uses_temps);
+    case NL_I32: return dynamic_super_i32(uses_temps);
+    case NL_I64: return dynamic_super_i64(uses_temps);
+    case NL_F32: return dynamic_super_f32(uses_temps);
+    case NL_F64: return dynamic_super_f64(uses_temps);
   }
   return nullptr;
 }

@@ -1004,5 +1004,22 @@ const StaticEntry *static_table_i32(int *n);
 const StaticEntry *static_table_i64(int *n);
 const StaticEntry *static_table_f32(int *n);
 const StaticEntry *static_table_f64(int *n);
+// per-dtype interpreter-driven instantiations, defined in nl_dynamic_<dtype>.cu
+pipeline_fn dynamic_kernel_i32(bool vec16, bool compact, bool reduce, bool uses_temps);
+pipeline_fn dynamic_pipe_i32(int rows);
+pipeline_fn dynamic_super_i32(bool uses_temps);
+pipeline_fn dynamic_kernel_i64(bool vec16, bool compact, bool reduce, bool uses_temps);
+pipeline_fn dynamic_pipe_i64(int rows);
+pipeline_fn dynamic_super_i64(bool uses_temps);
+pipeline_fn dynamic_kernel_f32(bool vec16, bool compact, bool reduce, bool uses_temps);
+pipeline_fn dynamic_pipe_f32(int rows);
+pipeline_fn dynamic_super_f32(bool uses_temps);
+pipeline_fn dynamic_kernel_f64(bool vec16, bool compact, bool reduce, bool uses_temps);
+pipeline_fn dynamic_pipe_f64(int rows);
+pipeline_fn dynamic_super_f64(bool uses_temps);
+const StaticEntry *static_table_i32_b(int *n);
+const StaticEntry *static_table_i64_b(int *n);
+const StaticEntry *static_table_f32_b(int *n);
+const StaticEntry *static_table_f64_b(int *n);
 
 }  // namespace nl

@@ -119,7 +119,11 @@ template <uint32_t... S> constexpr int rows_for() {
   /* a[a * k >= s]   (Tests/filter.py:13 exactly) */                                                        \
   X(filter_mul_ge, sp::L(0), sp::SV(1), sp::B(V_MUL, 1), sp::C(C_GE, 2), sp::F(), sp::LT(1), sp::ST(0, sp::COMPACT)) \
   NL_CMP_SHAPES(X, ge, C_GE)                                                                                \
-  NL_CMP_SHAPES(X, gt, C_GT)                                                                                \
+  NL_CMP_SHAPES(X, gt, C_GT)
+
+// second half of the list: compiled in its own translation unit (nl_static_<dtype>_b.cu) so that the
+// build spreads over more cores
+#define NL_STATIC_SHAPES_B(X)                                                                               \
   NL_CMP_SHAPES(X, le, C_LE)                                                                                \
   NL_CMP_SHAPES(X, lt, C_LT)                                                                                \
   NL_CMP_SHAPES(X, eq, C_EQ)                                                                                \
@@ -141,9 +145,15 @@ template <uint32_t... S> constexpr int rows_for() {
    sp::SuperFor<NL_STATIC_T, (sp::has_compact<__VA_ARGS__>() && !sp::has_reduce<__VA_ARGS__>()), __VA_ARGS__>::fn, \
    sp::super_rows_for<__VA_ARGS__>()},
 
+#ifdef NL_STATIC_SECOND_HALF
+#define NL_STATIC_LIST NL_STATIC_SHAPES_B
+#else
+#define NL_STATIC_LIST NL_STATIC_SHAPES
+#endif
+
 #define NL_DEFINE_STATIC_TABLE(fn_name)                                                                     \
   const StaticEntry *fn_name(int *n) {                                                                      \
-    static const StaticEntry table[] = {NL_STATIC_SHAPES(NL_STATIC_ROW)};                                   \
+    static const StaticEntry table[] = {NL_STATIC_LIST(NL_STATIC_ROW)};                                     \
     *n = (int)(sizeof(table) / sizeof(table[0]));                                                           \
     return table;                                                                                           \
   }

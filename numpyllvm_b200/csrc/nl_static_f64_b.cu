@@ -1,0 +1,9 @@
+// nl_static_f64_b.cu — second half of the build-time shapes (nl_static.cuh: NL_STATIC_SHAPES_B) for double.
+#define NL_STATIC_T double
+#define NL_STATIC_DTYPE NL_F64
+#define NL_STATIC_SECOND_HALF
+#include "nl_static.cuh"
+
+namespace nl {
+NL_DEFINE_STATIC_TABLE(static_table_f64_b)
+}  // namespace nl
