@@ -100,6 +100,20 @@ Storage *regular_from_runs(int dtype, const std::vector<Buf> &runs, int64_t tota
 
 }  // namespace
 
+int storage_copy_range(Storage *src, int64_t lo, int64_t hi, int dst_dev, void *dst) {
+  std::vector<Buf> runs;
+  std::vector<int64_t> start;
+  int64_t run = 0;
+  for (const Shard &sh : src->shards) {
+    Buf b;
+    b.dev = sh.dev; b.ptr = sh.ptr; b.count = sh.count;
+    runs.push_back(b);
+    start.push_back(run);
+    run += sh.count;
+  }
+  return gather_range(runs, start, nl_dtype_size(src->dtype), lo, hi, dst_dev, dst);
+}
+
 Storage *storage_repartition(Storage *in) {
   if (nljit_ensure_runtime() < 0) return nullptr;
   int rc = sync_devices(nljit_device_count());

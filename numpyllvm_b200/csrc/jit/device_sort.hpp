@@ -14,4 +14,9 @@ Storage *device_sort(Storage *in);
 // an unfiltered column of the same length.  Order is preserved.
 Storage *storage_repartition(Storage *in);
 
+// Copy the global element range [lo, hi) of `src` (shards concatenated in order) to `dst` on local
+// device `dst_dev` with device-to-device / NVLink peer copies, ordered on dst_dev's compute stream.
+// The caller synchronises.  Returns an nl error code.
+int storage_copy_range(Storage *src, int64_t lo, int64_t hi, int dst_dev, void *dst);
+
 #endif

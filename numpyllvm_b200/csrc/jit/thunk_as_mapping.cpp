@@ -8,8 +8,11 @@
 #include "thunk.hpp"
 #include <vector>
 #include "scheduler.hpp"
+#include "device_sort.hpp"
 
 #include <algorithm>
+#include <utility>
+#include <vector>
 #include <cstring>
 
 static ssize_t subscript_cardinality_function(ssize_t *inputs) {
@@ -186,6 +189,59 @@ static int assign_run(PyThunkObject *self, int64_t lo, int64_t step, int64_t cou
     PyErr_SetString(PyExc_ValueError, "assignment into a filtered thunk sharded over several devices is not supported");
     return -1;
   }
+  // a column-valued thunk of the target's dtype stays on the GPUs: the pieces each target shard needs
+  // travel device-to-device (NVLink peer copies across GPUs), no host round trip
+  if (PyThunk_Check(value) && ((PyThunkObject *)value)->npy_type == self->npy_type) {
+    PyThunkObject *vt = (PyThunkObject *)value;
+    if (PyThunk_Evaluate(vt) == NULL) return -1;
+    if (vt->card.n > 1) {
+      if (PyThunk_EnsureDevice(vt) < 0) return -1;
+      Storage *vs = vt->storage;
+      if (vs == st) {
+        // a[...] = a: the whole column onto itself is a no-op; anything else goes through a host copy below
+        if (lo == 0 && step == 1 && count == vs->cardinality()) return 0;
+        goto host_path;
+      }
+      if (vs->cardinality() != count) {
+        PyErr_Format(PyExc_ValueError, "could not broadcast input array of size %lld into a selection of size %lld",
+                     (long long)vs->cardinality(), (long long)count);
+        return -1;
+      }
+      int rc = NL_OK;
+      Py_BEGIN_ALLOW_THREADS
+      for (int g = 0; g < nljit_device_count() && rc == NL_OK; g++) rc = nl_stream_sync(g, 0);   // the value is complete everywhere
+      Py_END_ALLOW_THREADS
+      std::vector<std::pair<int, void *>> temps;
+      int64_t gstart = 0;
+      for (Shard &sh : st->shards) {
+        if (rc != NL_OK) break;
+        const int64_t s0 = st->ragged ? gstart : sh.start, s1 = s0 + sh.count;
+        gstart += sh.count;
+        int64_t kmin, kmax;
+        if (!intersect_run(lo, step, count, s0, s1, &kmin, &kmax)) continue;
+        const int64_t llo = lo + kmin * step - s0, lcount = kmax - kmin + 1;
+        if (step == 1) {
+          rc = storage_copy_range(vs, kmin, kmax + 1, sh.dev, (char *)sh.ptr + (size_t)llo * es);   // straight into place
+        } else {
+          void *tmp = NULL;
+          rc = nl_malloc(sh.dev, (size_t)lcount * es, &tmp);
+          if (rc == NL_OK) temps.push_back(std::make_pair(sh.dev, tmp));
+          if (rc == NL_OK) rc = storage_copy_range(vs, kmin, kmax + 1, sh.dev, tmp);
+          if (rc == NL_OK) rc = nl_assign_copy(sh.dev, 0, sh.ptr, nl_type, llo, step, lcount, tmp);
+        }
+      }
+      Py_BEGIN_ALLOW_THREADS
+      for (int g = 0; g < nljit_device_count(); g++) {
+        const int r2 = nl_stream_sync(g, 0);
+        if (rc == NL_OK) rc = r2;
+      }
+      Py_END_ALLOW_THREADS
+      for (auto &t : temps) nl_free(t.first, t.second);
+      if (rc != NL_OK) { nljit_raise(rc, "jit: in-place assignment failed"); return -1; }
+      return 0;
+    }
+  }
+host_path:
   // scalar or array value?
   PyObject *varr = NULL;
   bool scalar = true;

@@ -326,3 +326,30 @@ def test_gather_by_a_filtered_index_and_of_a_filtered_column():
     k = len(f)
     pick = rng.integers(0, k, 5000)
     assert np.array_equal(f[jit.thunk(pick)].asnumpyarray(), a_n[a_n >= 500][pick])
+
+
+def test_slice_assignment_of_a_thunk_stays_on_the_device():
+    """a[lo:hi:step] = <column thunk>: the pieces go device-to-device (NVLink peer copies across GPUs)."""
+    rng = np.random.default_rng(31)
+    n = 900_001
+    a_n = rng.integers(0, 1000, n)
+    b_n = rng.integers(0, 1000, n)
+    for lo, hi, step in ((0, n, 1), (12_345, 700_000, 1), (5, n - 3, 7), (n - 1, 100, -3)):
+        a, b = jit.thunk(a_n), jit.thunk(b_n)
+        ref = a_n.copy()
+        m = len(range(lo, hi, step))
+        v_n = (b_n * 3 + 1)[:m]
+        v = (b * 3 + 1)
+        c = a * 2                                   # dependent of a: must see the old values
+        if m == n:
+            a[lo:hi:step] = v
+        else:
+            a[lo:hi:step] = jit.thunk(v_n)          # a value thunk of the selection's size
+        ref[lo:hi:step] = v_n
+        assert np.array_equal(a.asnumpyarray(), ref), (lo, hi, step)
+        assert np.array_equal(c.asnumpyarray(), a_n * 2)
+    a = jit.thunk(a_n)
+    a[:] = a                                        # onto itself: no-op
+    assert np.array_equal(a.asnumpyarray(), a_n)
+    with pytest.raises(ValueError):
+        a[0:10] = jit.thunk(np.arange(11))
