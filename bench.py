@@ -231,7 +231,10 @@ def run_gpu(args):
 
     # ---------------- the other BASELINE.json configs ----------------
     if not args.no_extra:
-        result["pipelines"] = run_extra(args, rt, lib, ranks, peak, timed)
+        try:
+            result["pipelines"] = run_extra(args, rt, lib, ranks, peak, timed)
+        except Exception as exc:                    # the extra configs must never cost the headline line
+            result["pipelines_error"] = f"{type(exc).__name__}: {exc}"
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     if ranks.rank == 0 and G == 1 and not args.no_cpu:
