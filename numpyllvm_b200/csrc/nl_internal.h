@@ -56,7 +56,10 @@ constexpr int kRows = 4;          // U: vectors per thread per tile
 #define NL_DESC_STRIDE 16          // 8-byte words between consecutive tile descriptors (16 = one per 128-byte line)
 #endif
 constexpr int kMinBlocksCompact = 4;  // resident CTAs per SM of the build-time compaction shapes
-constexpr int kRowsStream = 8;    // U of the build-time elementwise / reduction shapes
+#ifndef NL_ROWS_STREAM
+#define NL_ROWS_STREAM 8
+#endif
+constexpr int kRowsStream = NL_ROWS_STREAM;    // U of the build-time elementwise / reduction shapes
 constexpr int kRowsCompact = 8;   // U of the build-time compaction shapes
 #ifndef NL_MIN_BLOCKS
 #define NL_MIN_BLOCKS 2
