@@ -10,6 +10,7 @@ static ThunkOperation *make(OpClass klass, int arity, int opcode, HostFunction b
   op->operand[0] = a;
   op->operand[1] = b;
   op->name = name;
+  op->refs = 1;
   Py_XINCREF(a);
   Py_XINCREF(b);
   return op;
@@ -23,8 +24,13 @@ ThunkOperation *NewBinaryOperation(PyObject *left, PyObject *right, OpClass klas
   return make(klass, 2, opcode, NULL, name, left, right);
 }
 
+void RetainOperation(ThunkOperation *operation) {
+  if (operation) operation->refs++;
+}
+
 void DestroyOperation(ThunkOperation *operation) {
   if (!operation) return;
+  if (--operation->refs > 0) return;
   Py_XDECREF(operation->operand[0]);
   Py_XDECREF(operation->operand[1]);
   delete operation;

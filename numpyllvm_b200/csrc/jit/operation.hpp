@@ -29,12 +29,15 @@ struct ThunkOperation {
   HostFunction base;
   PyObject *operand[2];  // owned references (the reference INCREFs its parameters too, operation.cpp:15)
   std::string name;      // "*", ">=", "[]", "sum", ...
+  int refs;              // the owning thunk holds one; every parser node that runs the record holds one, so a
+                         // pipeline can still read it after the thunk was marked evaluated mid-evaluation
 
   bool is_breaker() const { return klass != OpClass::Vectorizable; }
 };
 
 ThunkOperation *NewUnaryOperation(PyObject *arg, OpClass klass, int opcode, HostFunction base, const char *name);
 ThunkOperation *NewBinaryOperation(PyObject *left, PyObject *right, OpClass klass, int opcode, const char *name);
-void DestroyOperation(ThunkOperation *operation);
+void RetainOperation(ThunkOperation *operation);
+void DestroyOperation(ThunkOperation *operation);   /* drops one reference; frees the record (and its operand references) at zero */
 
 #endif

@@ -8,6 +8,7 @@
 #define NLJIT_PARSER_H
 
 #include "thunk.hpp"
+#include <map>
 #include <set>
 #include <string>
 #include <vector>
@@ -30,11 +31,19 @@ struct Operation {
   Operation *lhs, *rhs;          // owned
   Pipeline *child;               // ChildResult: the pipeline that produces it
 
-  Operation(Kind k, PyThunkObject *t)
-      : kind(k), thunk(t), result_object(NULL), materialize(false), op(NULL), lhs(NULL), rhs(NULL), child(NULL) {}
+  // A node owns a reference to its thunk and to the operator record it runs: a child pipeline that
+  // finishes marks its thunks evaluated, which drops their operations (and with them whole operand
+  // sub-DAGs); later pipelines of the same tree still read both.  (The reference keeps raw pointers.)
+  Operation(Kind k, PyThunkObject *t, ThunkOperation *o = NULL)
+      : kind(k), thunk(t), result_object(NULL), materialize(false), op(o), lhs(NULL), rhs(NULL), child(NULL) {
+    Py_XINCREF((PyObject *)thunk);
+    RetainOperation(op);
+  }
   ~Operation() {
     delete lhs;
     delete rhs;
+    DestroyOperation(op);
+    Py_XDECREF((PyObject *)thunk);
   }
   bool is_leaf() const { return kind == Column || kind == ChildResult; }
 };

@@ -90,7 +90,21 @@ static int run_base_function(Pipeline *pipeline) {
 }
 
 static int execute_one(Pipeline *pipeline) {
+  if (pipeline->evaluated) return 0;
   if (nljit_ensure_runtime() < 0) return -1;
+  if (pipeline->root->thunk && pipeline->root->thunk->evaluated && pipeline->root->thunk->storage &&
+      pipeline->root->kind != Operation::Column && !pipeline->inplace_target) {
+    // the root was computed meanwhile (by an earlier pipeline of this tree): publish its storage to
+    // whoever reads this pipeline's result as a column and skip the work
+    for (Binding &e : pipeline->outputs)
+      if (e.source->object && e.source->object->storage && !e.source->storage) {
+        e.source->storage = e.source->object->storage;
+        storage_incref(e.source->storage);
+        e.source->size = (ssize_t)e.source->storage->cardinality();
+      }
+    pipeline->evaluated = true;
+    return 0;
+  }
   ThunkOperation *root_op = (pipeline->root)->op;
   if (root_op && root_op->opcode < 0) return run_base_function(pipeline);
 

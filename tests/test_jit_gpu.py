@@ -353,3 +353,31 @@ def test_slice_assignment_of_a_thunk_stays_on_the_device():
     assert np.array_equal(a.asnumpyarray(), a_n)
     with pytest.raises(ValueError):
         a[0:10] = jit.thunk(np.arange(11))
+
+
+@pytest.mark.parametrize("n", [100, (1 << 20) + 7])
+def test_a_breaker_result_used_twice_in_one_expression(n):
+    # a reduction / sort result reached twice through breakers in one evaluate()
+    rng = np.random.default_rng(7)
+    a_n = rng.integers(1, 100, n).astype(np.int64)
+    b_n = rng.integers(1, 100, n).astype(np.int64)
+    a, b = jit.thunk(a_n), jit.thunk(b_n)
+    m = a.max()
+    y = (a - m) * (b - m)
+    assert np.array_equal(y.asnumpyarray(), (a_n - a_n.max()) * (b_n - a_n.max()))
+    y2 = (a - a.max()) * (b - a.min())          # temporaries only
+    assert np.array_equal(y2.asnumpyarray(), (a_n - a_n.max()) * (b_n - a_n.min()))
+    s = (a * b).sum()
+    d = a - s
+    r = d * d
+    del d
+    assert np.array_equal(r.asnumpyarray(), (a_n - (a_n * b_n).sum()) ** 2)
+    x = a * b
+    z = x.sort() * x
+    assert np.array_equal(z.asnumpyarray(), np.sort(a_n * b_n) * (a_n * b_n))
+    assert x.isevaluated()
+    q = (a * 3).sort() * (a * 3)                # the two (a*3) are different thunks: two pipelines, same values
+    assert np.array_equal(q.asnumpyarray(), np.sort(a_n * 3) * (a_n * 3))
+    f = a[a >= 50]
+    t = f.sum() * f                             # the filter result feeds a reduction and its parent
+    assert np.array_equal(t.asnumpyarray(), a_n[a_n >= 50].sum() * a_n[a_n >= 50])

@@ -153,3 +153,36 @@ def test_children_do_not_dangle():
         del c
     d = a * b
     assert "static:mul2" in jit.plan(d)
+
+
+def test_a_thunk_reached_twice_through_breakers_gets_one_pipeline():
+    # every occurrence used to get a child pipeline of its own, and the second one ran
+    # on operator records the first had already released
+    a, b = (jit.thunk(v) for v in vec(k=2))
+    m = a.max()
+    y = (a - m) * (b - m)
+    lines = [l for l in plan_lines(y) if l.startswith("pipeline")]
+    assert len(lines) == 2 and "static:reduce_max" in lines[0]
+    x = a * b
+    z = x.sort() * x
+    lines = [l for l in plan_lines(z) if l.startswith("pipeline")]
+    assert len(lines) == 3                                 # x, sort(x), sort(x) * x
+    assert sum("base function sort" in l for l in lines) == 1
+    assert sum("static:mul2" in l for l in lines) == 1
+    s = (a * b).sum()
+    d = a - s
+    lines = [l for l in plan_lines(d * d) if l.startswith("pipeline")]
+    assert len(lines) == 2
+
+
+def test_materialisation_counts_references_from_outside_the_dag_only():
+    # the reference tests ob_refcnt > 1 (parser.cpp:66); a thunk used twice INSIDE one expression is
+    # not "held by somebody else"
+    a = jit.thunk(vec())
+    d = a - 1
+    r = d * d
+    assert "outputs=2" in jit.plan(r)          # `d` is still a Python variable
+    del d
+    assert "outputs=1" in jit.plan(r)          # both references are the expression's own
+    for _ in range(3):                         # parsing takes and drops its own references
+        assert "outputs=1" in jit.plan(r)
