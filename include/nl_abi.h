@@ -71,7 +71,10 @@ enum {
   NL_ERR_NO_DEVICE    = -4,  /* no CUDA device initialised (no CPU fallback)   */
   NL_ERR_CUDA         = -5,  /* a CUDA runtime call failed                     */
   NL_ERR_NCCL         = -6,  /* NCCL missing or a collective failed            */
-  NL_ERR_NOMEM        = -7
+  NL_ERR_NOMEM        = -7,
+  NL_ERR_SPLIT_FILTER = -8   /* a column is combined with the result of a filter of the same
+                                pipeline (a[m] * b[m], f[f < 10] with f = a[a > 5]): the host
+                                must give the filters below the root pipelines of their own */
 };
 
 /* ---- element types (subset of getLLVMType, compiler.cpp:156-182) ---------- */
@@ -190,8 +193,9 @@ NL_API size_t      nl_dtype_size(int dtype);
 
 /* Lower an operation tree to a plan ("CompilePipeline", compiler.cpp:309).
  * Pure host code; needs no device.  NL_ERR_SPLIT: too many inputs / temps /
- * steps — split the tree at a node and materialise it.  NL_ERR_UNSUPPORTED:
- * e.g. an array load after a filter, mixed array dtypes. */
+ * steps — split the tree at a node and materialise it.  NL_ERR_SPLIT_FILTER: an
+ * array load after a filter / a store between two filters — materialise the
+ * filter results first.  NL_ERR_UNSUPPORTED: e.g. mixed array dtypes. */
 NL_API int nl_plan_compile(const nl_expr_node *nodes, int n_nodes,
                     const nl_input_desc *inputs, int n_inputs,
                     nl_plan *plan_out);

@@ -25,6 +25,7 @@ NL_MAILBOX_HANDLE_BYTES = 64
 # error codes
 NL_OK, NL_ERR_INVALID, NL_ERR_UNSUPPORTED, NL_ERR_SPLIT = 0, -1, -2, -3
 NL_ERR_NO_DEVICE, NL_ERR_CUDA, NL_ERR_NCCL, NL_ERR_NOMEM = -4, -5, -6, -7
+NL_ERR_SPLIT_FILTER = -8
 
 # dtypes
 NL_BOOL, NL_I32, NL_I64, NL_F32, NL_F64 = 0, 1, 2, 3, 4

@@ -61,9 +61,9 @@ static void describe(Pipeline *p, std::string &out) {
     if (e.operation->kind == Operation::ChildResult) ready = false;
   if (!ready) { out += ": fused kernel over the results of its child pipelines\n"; return; }
   LoweredPipeline lp;
-  PyThunkObject *cut = NULL;
+  std::vector<PyThunkObject *> cut;
   int rc = LowerPipeline(p, &lp, &cut);
-  if (rc == 1) { out += ": too large for one fused kernel, will be split\n"; return; }
+  if (rc == 1) { out += ": cannot run as one fused kernel, will be split\n"; return; }
   if (rc < 0) { PyErr_Clear(); out += ": cannot be compiled\n"; return; }
   char buf[4096], kernel[160];
   int is_static = 0;

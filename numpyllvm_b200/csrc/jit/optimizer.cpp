@@ -127,7 +127,15 @@ static void pick_cut(Operation *op, Operation *root, int total, Operation **best
   }
 }
 
-int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, PyThunkObject **cut_out) {
+// every FILTER node below the root (their results become columns of a later pipeline)
+static void collect_filters(Operation *op, Operation *root, std::vector<PyThunkObject *> *out) {
+  if (op->kind != Operation::Apply1 && op->kind != Operation::Apply2) return;
+  if (op != root && op->op && op->op->opcode == NL_OP_FILTER && op->thunk) out->push_back(op->thunk);
+  if (op->lhs) collect_filters(op->lhs, root, out);
+  if (op->rhs) collect_filters(op->rhs, root, out);
+}
+
+int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, std::vector<PyThunkObject *> *cuts_out) {
   memset(out, 0, sizeof(*out));
   Lowering lw = {pipeline, out, false, false};
   lower_op(lw, pipeline->root);
@@ -173,6 +181,14 @@ int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, PyThunkObject **cut_
     }
     rc = nl_plan_compile(out->nodes, out->n_nodes, out->inputs, out->n_inputs, &out->plan);
     if (rc == NL_OK) return 0;
+    if (rc == NL_ERR_SPLIT_FILTER) {
+      // `a[m] * b[m]`, `f[f < 10]` with f = a[a > 5] still lazy: legal NumPy, but one loop cannot index a
+      // column by the loop counter and by the compaction counter at once (compiler.cpp:213-216 would read
+      // column[compacted index]).  The filters below the root get pipelines of their own; the root then
+      // runs over their (equally ragged) results.
+      collect_filters(pipeline->root, pipeline->root, cuts_out);
+      if (!cuts_out->empty()) return 1;
+    }
     if (rc != NL_ERR_SPLIT) {
       nljit_raise(rc, "jit: pipeline cannot be compiled");
       return -1;
@@ -186,6 +202,6 @@ int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, PyThunkObject **cut_
     nljit_raise(rc, "jit: pipeline cannot be split further");
     return -1;
   }
-  *cut_out = best->thunk;
+  cuts_out->push_back(best->thunk);
   return 1;
 }

@@ -8,6 +8,7 @@
 #define NLJIT_OPTIMIZER_H
 
 #include "parser.hpp"
+#include <vector>
 
 struct LoweredPipeline {
   nl_expr_node nodes[NL_MAX_NODES];
@@ -20,8 +21,10 @@ struct LoweredPipeline {
   nl_plan plan;
 };
 
-// 0: lowered and compiled.  1: the expression needs splitting, *cut_out is the thunk to
-// materialise in its own pipeline.  -1: error, Python exception set.
-int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, PyThunkObject **cut_out);
+// 0: lowered and compiled.  1: the expression needs splitting, `cuts_out` receives the thunk(s) to
+// materialise in pipelines of their own — one near the middle of an over-large expression, or every
+// filter below the root when a column meets a filter result inside one pipeline (a[m] * b[m]).
+// -1: error, Python exception set.
+int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, std::vector<PyThunkObject *> *cuts_out);
 
 #endif

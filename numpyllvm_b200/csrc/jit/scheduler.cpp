@@ -27,7 +27,7 @@ static int64_t *sizes_buffer(int dev) {
   return g_sizes[dev] + g_sizes_slot[dev] * NL_MAX_OUTPUTS;
 }
 
-static PyThunkObject *g_pending_cut = NULL;
+static std::vector<PyThunkObject *> g_pending_cuts;
 
 static int sync_devices() {
   int rc = NL_OK;
@@ -137,12 +137,12 @@ static int execute_one(Pipeline *pipeline) {
   }
 
   LoweredPipeline lp;
-  PyThunkObject *cut = NULL;
+  std::vector<PyThunkObject *> cut;
   int lrc = LowerPipeline(pipeline, &lp, &cut);
   if (lrc < 0) return -1;
   if (lrc == 1) {
-    // handled by EvaluateWithCuts: re-parse with `cut` as an extra breaker
-    g_pending_cut = cut;
+    // handled by EvaluateWithCuts: re-parse with the proposed thunks as extra breakers
+    g_pending_cuts = cut;
     return -2;
   }
   if (debug_plan_enabled()) PrintPlan(pipeline, &lp.plan);
@@ -329,12 +329,13 @@ static int EvaluateWithCuts(PyThunkObject *root, PyThunkObject *inplace_target) 
     if (debug_plan_enabled()) PrintPipeline(pipeline);
     int rc = ScheduleExecution(pipeline);
     DestroyPipeline(pipeline);
-    if (rc == -2 && g_pending_cut && !cuts.count(g_pending_cut)) {
-      cuts.insert(g_pending_cut);
-      g_pending_cut = NULL;
-      continue;
+    if (rc == -2) {
+      bool grew = false;
+      for (PyThunkObject *t : g_pending_cuts) grew |= cuts.insert(t).second;
+      g_pending_cuts.clear();
+      if (grew) continue;
+      break;
     }
-    if (rc == -2) break;
     return rc;
   }
   PyErr_SetString(PyExc_ValueError, "expression could not be split into fused pipelines");

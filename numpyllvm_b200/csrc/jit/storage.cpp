@@ -13,7 +13,7 @@ static int g_ndev = 0;
 
 void nljit_raise(int rc, const char *what) {
   PyObject *exc = PyExc_RuntimeError;
-  if (rc == NL_ERR_INVALID || rc == NL_ERR_UNSUPPORTED || rc == NL_ERR_SPLIT) exc = PyExc_ValueError;
+  if (rc == NL_ERR_INVALID || rc == NL_ERR_UNSUPPORTED || rc == NL_ERR_SPLIT || rc == NL_ERR_SPLIT_FILTER) exc = PyExc_ValueError;
   if (rc == NL_ERR_NOMEM) exc = PyExc_MemoryError;
   PyErr_Format(exc, "%s: %s", what, nl_last_error());
 }

@@ -96,7 +96,7 @@ struct Lower {
       // compiler.cpp:213-216 loads column[info.index]; once a filter has run that is the
       // compacted index, which is ill-defined for a full-length column
       if (in[nd.input].kind == NL_IN_ARRAY && cur_space == NL_IDX_COMPACT)
-        fail(NL_ERR_UNSUPPORTED, "array input %d is loaded after a filter in the same pipeline", nd.input);
+        fail(NL_ERR_SPLIT_FILTER, "array input %d is loaded after a filter in the same pipeline", nd.input);
     } else {
       if (nd.lhs < 0 || nd.lhs >= n) { fail(NL_ERR_INVALID, "node %d: bad lhs", n); return; }
       walk(nd.lhs);
@@ -112,7 +112,7 @@ struct Lower {
       if (nd.output >= NL_MAX_OUTPUTS) { fail(NL_ERR_SPLIT, "more than %d materialised outputs", NL_MAX_OUTPUTS); return; }
       int space = (nd.op == NL_OP_WHERE_STORE) ? NL_IDX_WHERE : cur_space;
       if (space == NL_IDX_COMPACT && !has_filter_below[n])
-        fail(NL_ERR_UNSUPPORTED, "node %d is stored at a compacted index but does not depend on the filter", n);
+        fail(NL_ERR_SPLIT_FILTER, "node %d is stored at a compacted index but does not depend on the filter", n);
       out_space[nd.output] = space;
       plan->out[nd.output].index_space = space;
       plan->out[nd.output].dtype = is_pred(n) ? NL_BOOL : plan->dtype;
@@ -359,7 +359,7 @@ int nl_plan_compile(const nl_expr_node *nodes, int n_nodes, const nl_input_desc 
     if (step_op(s) == S_FILTER) seen++;
     if ((step_op(s) == S_STORE || step_op(s) == S_PSTORE) && step_b(s) == NL_IDX_COMPACT) {
       plan->flags |= NL_PLAN_HAS_COMPACT;
-      if (seen != n_filters) { set_error("a filtered result is materialised between two filters: split the pipeline there"); return NL_ERR_UNSUPPORTED; }
+      if (seen != n_filters) { set_error("a filtered result is materialised between two filters: split the pipeline there"); return NL_ERR_SPLIT_FILTER; }
     }
   }
   // Dead saves: a column parked in a temporary "for later" whose later use found it still in the

@@ -114,7 +114,7 @@ def test_lowering_rejects_what_the_library_cannot_run():
     e.materialize(e.mul(e.filter(a, e.ge(e.ref(a), e.scalar(1))), b))
     with pytest.raises(abi.NLError) as ei:
         abi.compile_plan(e)
-    assert ei.value.code == abi.NL_ERR_UNSUPPORTED
+    assert ei.value.code == abi.NL_ERR_SPLIT_FILTER      # legal once the host gives the filter its own pipeline
     # mixed column dtypes
     e = Expr(np.int64)
     e.materialize(e.mul(e.array(np.int64), e.array(np.int32)))

@@ -381,3 +381,21 @@ def test_a_breaker_result_used_twice_in_one_expression(n):
     f = a[a >= 50]
     t = f.sum() * f                             # the filter result feeds a reduction and its parent
     assert np.array_equal(t.asnumpyarray(), a_n[a_n >= 50].sum() * a_n[a_n >= 50])
+
+
+@pytest.mark.parametrize("n", [100, (1 << 20) + 7])
+def test_columns_combined_after_a_filter_are_split_into_pipelines(n):
+    # these used to fail with "array input is loaded after a filter"
+    rng = np.random.default_rng(11)
+    a_n = rng.integers(1, 100, n).astype(np.int64)
+    b_n = rng.integers(1, 100, n).astype(np.int64)
+    a, b = jit.thunk(a_n), jit.thunk(b_n)
+    m = a > 40
+    assert np.array_equal((a[m] * b[m]).asnumpyarray(), a_n[a_n > 40] * b_n[a_n > 40])
+    assert np.array_equal((a[a > 40] + a[a > 40]).asnumpyarray(), 2 * a_n[a_n > 40])
+    f = a[a > 5]
+    g = f[f < 60]                               # f is still lazy here
+    assert np.array_equal(g.asnumpyarray(), a_n[(a_n > 5) & (a_n < 60)])
+    h = (a[a > 5] * 2)[b[a > 5] >= 50]          # filter, arithmetic, then a filter by another filtered column
+    assert np.array_equal(h.asnumpyarray(), (a_n[a_n > 5] * 2)[b_n[a_n > 5] >= 50])
+    assert (a[m] * b[m]).sum().asnumpyarray()[0] == (a_n[a_n > 40] * b_n[a_n > 40]).sum()

@@ -186,3 +186,13 @@ def test_materialisation_counts_references_from_outside_the_dag_only():
     assert "outputs=1" in jit.plan(r)          # both references are the expression's own
     for _ in range(3):                         # parsing takes and drops its own references
         assert "outputs=1" in jit.plan(r)
+
+
+def test_a_column_meeting_a_filter_result_is_split_not_rejected():
+    # a[m] * b[m] and chained lazy filters are legal NumPy; the plan compiler asks
+    # for the filters to get pipelines of their own (NL_ERR_SPLIT_FILTER) instead of failing
+    a, b = (jit.thunk(v) for v in vec(k=2))
+    m = a > 5
+    assert "will be split" in jit.plan(a[m] * b[m])
+    f = a[a > 5]
+    assert "will be split" in jit.plan(f[f < 10])
