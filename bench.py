@@ -8,9 +8,13 @@ Headline workload (BASELINE.json configs[1]): Tests/assignment.py at scale —
 `c = a * b` pending on 2^30-element f32 columns, `a[0] = 1000` forces it
 (thunk_as_mapping.cpp:80-86), one step = the forced fused pipeline (12 B/elem)
 plus the in-place update.  Weak scaling: every GPU owns a 2^30-element shard
-and there is no data-path collective.  The other BASELINE.json configs are
-reported in `pipelines` (N = 1: C1, C3, C4, C5; N > 1: C3/C4/C5 with their NCCL
-finish).  One JSON line is printed by rank 0.
+and there is no data-path collective.  `e2e` is the same step through the `jit`
+extension with HOST buffers (upload, kernel and download overlapped chunk by
+chunk).  The other BASELINE.json configs are reported in `pipelines` (C1, C3, C4,
+C5, sort), each with a full-size parity verdict against the oracle and, at
+N > 1, its efficiency against the same config run on one GPU in the same
+invocation.  One JSON line is printed by rank 0; its last key is a compact
+summary of every pipeline row.
 """
 from __future__ import annotations
 
@@ -23,6 +27,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -32,6 +37,7 @@ if ROOT not in sys.path:
 
 METRIC = "effective HBM GB/s per fused pipeline"
 FALLBACK_PEAK_GBS = 6650.0     # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+M64 = (1 << 64) - 1
 
 
 def measured_peak():
@@ -41,6 +47,14 @@ def measured_peak():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy_)"
     except Exception:
         return FALLBACK_PEAK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def headline_config(n, G):
+    """`config` of the JSON line — the SAME dict in both arms (the reference arm times the same step)."""
+    return {"workload": "Tests/assignment.py at scale: c = a*b forced by a[0] = 1000, then the in-place update",
+            "elements_per_gpu": n, "algorithmic_bytes_per_step_per_gpu": 12 * n + 4,
+            "l2": "inputs (12 GiB per GPU) are larger than L2; no flush needed",
+            "parallelism": f"{G} contiguous shards, one rank per GPU, no data-path collective"}
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -72,6 +86,7 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
 
     def summary(self, t0: float, t1: float):
         rows = [(t, l) for t, l in self.samples if t0 <= t <= t1 + 0.06]
@@ -97,6 +112,62 @@ class ClockSampler:
         return out
 
 
+# ------------------------------------------------------------------------------ host side of the parity checks
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def words_checksum(buf: np.ndarray):
+    """(n_words, sum, xor, position-weighted sum) of an array's bytes read as little-endian u64 words, a
+    trailing partial word zero-padded — the host twin of nl_checksum() (nl_abi.h)."""
+    raw = np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+    pad = (-raw.size) % 8
+    if pad:
+        raw = np.concatenate([raw, np.zeros(pad, np.uint8)])
+    w = raw.view(np.uint64)
+    if w.size == 0:
+        return 0, 0, 0, 0
+    k = np.arange(w.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return int(w.size), int(np.add.reduce(w)), int(np.bitwise_xor.reduce(w)), int(np.add.reduce(w * (2 * k + 1)))
+
+
+def combine_checksums(parts):
+    """Fold per-chunk (n_words, sum, xor, weighted) in order: a chunk starting at word b contributes
+    weighted + 2 b sum (see nl_checksum.cu)."""
+    base = s = x = p = 0
+    for nw, cs, cx, cp in parts:
+        s = (s + cs) & M64
+        x ^= cx
+        p = (p + cp + 2 * base * cs) & M64
+        base += nw
+    return base, s, x, p
+
+
+def oracle_stream(n, work, threads, chunk=1 << 22):
+    """work(first, count) over [0, n) in chunks on `threads` host threads (ctypes releases the GIL);
+    the partial results in chunk order."""
+    spans = [(s, min(chunk, n - s)) for s in range(0, n, chunk)]
+    if threads <= 1:
+        return [work(s, m) for s, m in spans]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(lambda sm: work(*sm), spans))
+
+
+def device_checksum(rt, lib, ptr, nbytes, scratch):
+    from numpyllvm_b200 import abi
+    abi.check(lib.nl_checksum(0, 0, C.c_void_p(ptr), nbytes, C.c_void_p(scratch.ptr)))
+    v = rt.download(scratch, 3)
+    return int(v[0]), int(v[1]), int(v[2])
+
+
+def verdict(ok, what):
+    return ("bit-exact vs oracle: " if ok else "MISMATCH vs oracle: ") + what
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     from numpyllvm_b200 import abi
@@ -104,9 +175,11 @@ def run_gpu(args):
     from numpyllvm_b200.device import Runtime
     from numpyllvm_b200.dist import Ranks
 
-    # the JSON line is the only thing this arm may print on stdout: keep NCCL's banner off it
-    os.environ["NCCL_DEBUG"] = os.environ.get("NL_NCCL_DEBUG", "WARN")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # the version banner must not precede the JSON line on stdout
+    # NCCL's own log stays on (the driver reads the ranks of the communicator from it) but goes to
+    # stderr: the JSON line is the only thing this arm may print on stdout
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
+    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ranks = Ranks(args.gpus)
     lib = abi.load_library()
     dev_ids = (C.c_int * 1)(ranks.local_rank)
@@ -117,14 +190,16 @@ def run_gpu(args):
     G = ranks.world
     n = 1 << args.log2n           # elements per GPU (weak scaling)
     K, W = args.steps, max(args.warmup, 3)
+    threads = max(1, host_threads() // G)       # host threads of this rank for the oracle side of the checks
 
-    def timed(step_fn, k, w, per_launch=None):
+    def timed(step_fn, k, w, per_launch=None, solo=False):
         """w warm-up + k timed steps, barrier + device sync on both sides, CUDA events on the
-        launching stream, max over ranks.  Returns (ms total, [per-launch ms])."""
+        launching stream, max over ranks (solo: rank 0 alone, no barrier).  Returns (ms total, [per-launch ms])."""
         for _ in range(w):
             step_fn(None)
         rt.sync()
-        ranks.barrier()
+        if not solo:
+            ranks.barrier()
         e0, e1 = rt.event(), rt.event()
         pairs = []
         rt.record(e0)
@@ -141,6 +216,8 @@ def run_gpu(args):
         launch_ms = [rt.elapsed_ms(a_, b_) for a_, b_ in pairs]
         for ev in [e0, e1] + [x for p in pairs for x in p]:
             lib.nl_event_destroy(ev)
+        if solo:
+            return ms, launch_ms
         ranks.barrier()
         return ranks.max(ms), launch_ms
 
@@ -150,6 +227,7 @@ def run_gpu(args):
     rt.fill(a, ranks.rank * n, 42, 2)
     rt.fill(b, ranks.rank * n, 43, 2)
     sizes = rt.empty(np.int64, 4)
+    csum = rt.empty(np.uint64, 4)
     e = Expr(f32)
     e.materialize(e.mul(e.array(), e.array()))
     plan = abi.compile_plan(e)
@@ -167,7 +245,6 @@ def run_gpu(args):
 
     sampler = ClockSampler(ranks.local_rank)
     time.sleep(0.12)
-    launches0 = lib.nl_launch_count()
     for _ in range(W):
         c2_step(None)
     rt.sync()
@@ -184,25 +261,31 @@ def run_gpu(args):
     achieved = 12 * n / (kern_ms * 1e-3) / 1e9
     kname, kgrid, kblock, kvec = rt.last_launch()
 
-    # spot-check parity on sampled windows against the oracle (outside the timed region)
+    # full-size parity (outside the timed region): 64-bit checksums of the whole result column against
+    # the oracle's compiled loop run chunk-streamed on regenerated inputs — every rank checks its shard
     parity = "unchecked"
-    if ranks.rank == 0 and not args.no_check:
+    if not args.no_check:
         import oracle
-        ok = True
-        for w0 in (0, n // 3 + 5, n - 4096):
-            wa = oracle.fill(f32, w0, 4096, 42, 2)
-            wb = oracle.fill(f32, w0, 4096, 43, 2)
-            if w0 == 0 and K + W > 1:
+        got = device_checksum(rt, lib, c.ptr, 4 * n, csum)
+        first = ranks.rank * n
+
+        def c2_chunk(s, m):
+            wa = oracle.fill(f32, first + s, m, 42, 2)
+            wb = oracle.fill(f32, first + s, m, 43, 2)
+            if s == 0 and ranks.rank == 0 and K + W > 1:
                 wa[0] = 1000.0            # every step after the first sees the updated a[0]
-            got = rt.download(c, 4096, offset_elems=w0)
-            ok &= bool(np.array_equal(got, wa * wb))
-        ok &= float(rt.download(a, 1)[0]) == 1000.0
-        parity = "bit-exact on sampled windows" if ok else "MISMATCH"
+            return words_checksum(oracle.fast_mul2_f32(wa, wb, np.empty_like(wa), 8, 1))
+        want = combine_checksums(oracle_stream(n, c2_chunk, threads))
+        ok = got == want[1:] and want[0] == n // 2
+        ok &= (ranks.rank != 0) or float(rt.download(a, 1)[0]) == 1000.0
+        ok = ranks.max(0.0 if ok else 1.0) == 0.0
+        parity = verdict(ok, f"sum/xor/position-weighted 64-bit checksums of all {n} elements of c on every rank")
 
     # ---------------- e2e: same step with HOST buffers, copies inside the timed region ------------
     e2e = e2e_streamed = None
     if not args.no_e2e:
-        e2e_streamed = run_e2e_cabi(args, rt, lib, ranks, plan, a, b, c, sizes, n, thousand)
+        if args.cabi_e2e:
+            e2e_streamed = run_e2e_cabi(args, rt, lib, ranks, plan, a, b, c, sizes, n, thousand)
         a.free(); b.free(); c.free()
         e2e = run_e2e_jit(args, ranks, n)
 
@@ -210,10 +293,7 @@ def run_gpu(args):
         "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": G, "steps": K, "warmup": W,
         "ms_per_step": round(ms_total / K, 5), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Tests/assignment.py at scale: c = a*b forced by a[0] = 1000, then the in-place update",
-                   "elements_per_gpu": n, "algorithmic_bytes_per_step_per_gpu": alg_bytes,
-                   "l2": "inputs (12 GiB per GPU) are larger than L2; no flush needed",
-                   "parallelism": f"{G} contiguous shards, one rank per GPU, no data-path collective"},
+        "config": headline_config(n, G),
         "elements_per_s": round(G * n * K / (ms_total * 1e-3), 1),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": load_traffic("c2"),
@@ -226,19 +306,27 @@ def run_gpu(args):
     }
     if e2e:
         result["e2e"] = e2e
+    if e2e_streamed:
         result["e2e_streamed_cabi"] = e2e_streamed
-    a.free(); b.free(); c.free()
-
-    # ---------------- the other BASELINE.json configs ----------------
-    if not args.no_extra:
-        try:
-            result["pipelines"] = run_extra(args, rt, lib, ranks, peak, timed)
-        except Exception as exc:                    # the extra configs must never cost the headline line
-            result["pipelines_error"] = f"{type(exc).__name__}: {exc}"
+    a.free(); b.free(); c.free(); csum.free()
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------
     if ranks.rank == 0 and G == 1 and not args.no_cpu:
         result["cpu_baseline"] = cpu_baseline(args)
+
+    # ---------------- the other BASELINE.json configs ----------------
+    if not args.no_extra:
+        try:
+            rows = run_extra(args, rt, lib, ranks, peak, timed, threads)
+            result["pipelines"] = rows
+            # last key of the line: one short entry per row, so that a tail of the output still shows every config
+            result["pipelines_summary"] = {r["id"]: [r.get("GB/s", r.get("Gkeys/s")), r.get("frac_of_measured_peak"),
+                                                     r.get("efficiency_vs_n1"), "ok" if str(r.get("parity", "")).startswith("bit-exact") or
+                                                     str(r.get("parity", "")).startswith("within") else r.get("parity", "unchecked")]
+                                           for r in rows}
+            result["pipelines_summary"]["_columns"] = ["GB/s (Gkeys/s for sort)", "frac_of_measured_peak", "efficiency_vs_n1", "parity"]
+        except Exception as exc:                    # the extra configs must never cost the headline line
+            result["pipelines_error"] = f"{type(exc).__name__}: {exc}"
     sampler.stop()
     if ranks.rank == 0:
         print(json.dumps(result), flush=True)
@@ -255,9 +343,9 @@ def load_traffic(key):
 
 
 def run_e2e_cabi(args, rt, lib, ranks, plan, a, b, c, sizes, n, thousand):
-    """Extra data point: the same step through the C-ABI with HOST (pinned) buffers: H2D of both inputs, the
-    fused pipeline, the in-place update and D2H of the result, chunked so the upload, the
-    kernel and the download overlap on the three streams of the device."""
+    """Extra data point (--cabi-e2e): the same step through the bare C-ABI with HOST (pinned) buffers: H2D of
+    both inputs, the fused pipeline, the in-place update and D2H of the result, chunked so the upload,
+    the kernel and the download overlap on the three streams of the device."""
     from numpyllvm_b200 import abi
     nbytes = 4 * n
     hp = [C.c_void_p() for _ in range(3)]
@@ -266,7 +354,6 @@ def run_e2e_cabi(args, rt, lib, ranks, plan, a, b, c, sizes, n, thousand):
     ha = np.ctypeslib.as_array(C.cast(hp[0], C.POINTER(C.c_float)), shape=(n,))
     hb = np.ctypeslib.as_array(C.cast(hp[1], C.POINTER(C.c_float)), shape=(n,))
     hc = np.ctypeslib.as_array(C.cast(hp[2], C.POINTER(C.c_float)), shape=(n,))
-    # host inputs: the same synthetic columns (fetched once from the device copy, untimed)
     rt.fill(a, ranks.rank * n, 42, 2)
     abi.check(lib.nl_memcpy_d2h(0, 0, hp[0], C.c_void_p(a.ptr), nbytes))
     abi.check(lib.nl_memcpy_d2h(0, 0, hp[1], C.c_void_p(b.ptr), nbytes))
@@ -275,7 +362,6 @@ def run_e2e_cabi(args, rt, lib, ranks, plan, a, b, c, sizes, n, thousand):
     nchunks = (n + chunk - 1) // chunk
 
     def step():
-        # the uploads overwrite a/b: they may not start before the previous step's kernels are done
         abi.check(lib.nl_stream_wait(0, 1, 0, 0))
         for i in range(nchunks):
             s, e_ = i * chunk, min(n, (i + 1) * chunk)
@@ -293,15 +379,11 @@ def run_e2e_cabi(args, rt, lib, ranks, plan, a, b, c, sizes, n, thousand):
     k = max(1, min(args.steps, args.e2e_steps))
     step(); rt.sync()
     ranks.barrier()
-    e0, e1 = rt.event(), rt.event()
     t0 = time.perf_counter()
-    rt.record(e0)
     for _ in range(k):
         step()
-    rt.record(e1)
     rt.sync()
-    wall = time.perf_counter() - t0
-    ms = ranks.max(max(rt.elapsed_ms(e0, e1), wall * 1e3))
+    ms = ranks.max((time.perf_counter() - t0) * 1e3)
     ok = bool(np.array_equal(hc[:4096], ha[:4096] * hb[:4096])) and bool(np.array_equal(hc[-4096:], ha[-4096:] * hb[-4096:]))
     for p in hp:
         lib.nl_host_free(p)
@@ -312,21 +394,43 @@ def run_e2e_cabi(args, rt, lib, ranks, plan, a, b, c, sizes, n, thousand):
             "parity": "bit-exact on sampled windows" if ok else "MISMATCH"}
 
 
+def mem_available_bytes():
+    try:
+        with open("/proc/meminfo") as fh:
+            for line in fh:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    return None
+
+
 def run_e2e_jit(args, ranks, n):
     """The headline end-to-end number: the step exactly as a user of the reference writes it
-    (Tests/assignment.py), through the `jit` extension, with HOST buffers.  Every step uploads
-    both columns from pinned host memory (jit.thunk copies on wrap), runs the forced pipeline and
-    the in-place update, and reads the result back into host memory (asnumpyarray)."""
+    (Tests/assignment.py), through the `jit` extension, with HOST buffers.  Every step hands both
+    columns to jit.thunk() from page-locked host memory, forces the pipeline with the in-place update
+    and reads the result back into host memory (asnumpyarray).  jit.thunk() returns while PCIe is
+    busy; the kernel follows the upload chunk by chunk and each chunk of the result leaves as soon as
+    it is computed, so the three legs overlap (storage.cpp, scheduler.cpp)."""
     import numpyllvm_b200
     jit = numpyllvm_b200.install_jit_alias()
     import oracle
-    n_e = n if ranks.world == 1 else min(n, 1 << 28)      # bound the pinned host memory of 8 ranks
+    G = ranks.world
+    # the same workload at every N: 2^30 elements per GPU (12 GiB of page-locked host memory per rank)
+    n_e, note = n, None
+    avail = mem_available_bytes()
+    while avail is not None and n_e > (1 << 20) and 12 * n_e * G * 1.3 > avail:
+        n_e //= 2
+        note = f"host memory ({avail >> 30} GiB available) bounds the page-locked buffers: {n_e} elements per GPU"
     ha, hb = jit.pinned_empty(n_e, np.float32), jit.pinned_empty(n_e, np.float32)
-    blk = 1 << 22
-    for s0 in range(0, n_e, blk):                          # synthetic columns, generated on the host
-        m = min(blk, n_e - s0)
-        ha[s0:s0 + m] = oracle.fill(np.float32, ranks.rank * n + s0, m, 42, 2)
-        hb[s0:s0 + m] = oracle.fill(np.float32, ranks.rank * n + s0, m, 43, 2)
+    threads = max(1, host_threads() // G)
+    first = ranks.rank * n
+
+    def gen(s, m):                                         # synthetic columns, generated on the host
+        ha[s:s + m] = oracle.fill(np.float32, first + s, m, 42, 2)
+        hb[s:s + m] = oracle.fill(np.float32, first + s, m, 43, 2)
+        return 0
+    oracle_stream(n_e, gen, threads)
 
     def step():
         a = jit.thunk(ha)
@@ -337,23 +441,33 @@ def run_e2e_jit(args, ranks, n):
         return c.asnumpyarray()
 
     out = step()                                           # warm-up: pins the result pool, loads kernels
-    ok = bool(np.array_equal(out[:4096], ha[:4096] * hb[:4096])) and bool(np.array_equal(out[-4096:], ha[-4096:] * hb[-4096:]))
+    # the whole host result against the oracle's loop on the host columns (the upload is part of what is checked)
+    def chk(s, m):
+        return bool(np.array_equal(out[s:s + m], oracle.fast_mul2_f32(ha[s:s + m], hb[s:s + m], np.empty(m, np.float32), 8, 1)))
+    ok = all(oracle_stream(n_e, chk, threads))
     del out
+    out = step(); del out                                  # second warm-up: every pool block exists now
     k = max(1, min(args.steps, args.e2e_steps))
+    jit.synchronize()
     ranks.barrier()
     t0 = time.perf_counter()
     for _ in range(k):
         out = step()
         del out
+    jit.synchronize()
     dt = ranks.max(time.perf_counter() - t0)
     ranks.barrier()
-    G = ranks.world
-    return {"value": round(G * (12 * n_e + 4) * k / dt / 1e9, 2), "unit": "GB/s",
-            "h2d_bytes_per_step": 8 * n_e, "d2h_bytes_per_step": 4 * n_e, "steps": k,
-            "ms_per_step": round(1e3 * dt / k, 3), "elements_per_gpu": n_e,
-            "api": "jit.thunk(pinned ndarray) x2 -> c = a*b -> a[0] = 1000 -> c.evaluate() -> c.asnumpyarray(); wall clock",
-            "bound": "PCIe: 12 bytes cross the host link per element for 12 algorithmic bytes",
-            "parity": "bit-exact on sampled windows" if ok else "MISMATCH"}
+    ok = ranks.max(0.0 if ok else 1.0) == 0.0
+    res = {"value": round(G * (12 * n_e + 4) * k / dt / 1e9, 2), "unit": "GB/s",
+           "h2d_bytes_per_step": 8 * n_e, "d2h_bytes_per_step": 4 * n_e, "steps": k,
+           "ms_per_step": round(1e3 * dt / k, 3), "elements_per_gpu": n_e,
+           "api": "jit.thunk(pinned ndarray) x2 -> c = a*b -> a[0] = 1000 -> c.evaluate() -> c.asnumpyarray(); wall clock, max over ranks",
+           "overlap": "upload (copy stream), kernel (compute stream) and download (copy-back stream) pipelined in 32 MiB chunks",
+           "bound": "PCIe: 8 bytes up and 4 bytes down per element for 12 algorithmic bytes",
+           "parity": verdict(ok, f"all {n_e} elements of the host result on every rank")}
+    if note:
+        res["note"] = note
+    return res
 
 
 def _reduce_device(rt, abi, Expr, op, dtype, ptr, n, sizes):
@@ -365,22 +479,6 @@ def _reduce_device(rt, abi, Expr, op, dtype, ptr, n, sizes):
     v = rt.download(res)[0]
     res.free()
     return v
-
-
-def filter_properties(rt, abi, Expr, x, y, n, cnt, thr, sizes):
-    """Size-independent checks of a[a > t] at full size: every survivor passes the predicate and the
-    survivors' sum equals the fused a[a > t].sum() pipeline's (same multiset)."""
-    dt = np.float64
-    ok_min = bool(cnt == 0 or _reduce_device(rt, abi, Expr, abi.OP_MIN, dt, y.ptr, cnt, sizes) > thr)
-    s_out = _reduce_device(rt, abi, Expr, abi.OP_SUM, dt, y.ptr, cnt, sizes) if cnt else 0.0
-    res = rt.empty(dt, 1)
-    e = Expr(dt)
-    xa = e.array()
-    e.materialize(e.sum(e.filter(xa, e.gt(e.ref(xa), e.scalar(thr)))))
-    rt.launch(abi.compile_plan(e), [res.ptr], [x.ptr, None], 0, n, sizes.ptr)
-    s_fused = rt.download(res)[0]
-    res.free()
-    return {"all_survivors_pass": ok_min, "sum_equals_fused_filter_sum": bool(abs(s_out - s_fused) <= 1e-9 * max(1.0, abs(s_fused)))}
 
 
 def sort_properties(rt, abi, Expr, lib, x, n, dt, sum_before, sizes):
@@ -400,32 +498,54 @@ def sort_properties(rt, abi, Expr, lib, x, n, dt, sum_before, sizes):
     return out
 
 
-def run_extra(args, rt, lib, ranks, peak, timed):
-    """C1, C3, C4, C5 of BASELINE.json: GB/s, elements/s and fraction of the HBM roofline."""
+def run_extra(args, rt, lib, ranks, peak, timed, threads):
+    """C1, C3, C4, C5 of BASELINE.json (+ the device sort): GB/s, elements/s, fraction of the HBM roofline, a
+    full-size parity verdict against the oracle and, at N > 1, the efficiency against one GPU."""
     from numpyllvm_b200 import abi
     from numpyllvm_b200.abi import Expr
+    import oracle
     G, rank = ranks.world, ranks.rank
     out = []
+    check = not args.no_check
     # the configs run 0.1-3 ms per step: a long warm-up keeps the allocation pause before each config
     # (clocks ramp down, the pool maps fresh pages) out of the 20 timed steps
     k, w = max(3, min(args.steps, 20)), 25
     sizes = rt.empty(np.int64, 4)
+    csum = rt.empty(np.uint64, 4)
     lib.nl_pool_trim(0)                         # columns of the earlier arms go back to the driver: fresh, large chunks for these
     fused = rt.peer_ready()                     # NVLink mailboxes exchanged: reductions finish inside their kernel
 
-    def report(name, dtype, n_per_gpu, bytes_per_gpu, ms, extra=None, k=k):
+    def all_ok(ok):
+        return ranks.max(0.0 if ok else 1.0) == 0.0
+
+    def report(rid, name, dtype, n_per_gpu, bytes_per_gpu, ms, extra=None, k=k, solo_ms=None, solo_bytes=None):
         gbs = G * bytes_per_gpu * k / (ms * 1e-3) / 1e9
-        row = {"config": name, "dtype": dtype, "elements_per_gpu": n_per_gpu, "ms_per_step": round(ms / k, 5),
+        row = {"id": rid, "config": name, "dtype": dtype, "elements_per_gpu": n_per_gpu, "ms_per_step": round(ms / k, 5),
                "GB/s": round(gbs, 2), "elements_per_s": round(G * n_per_gpu * k / (ms * 1e-3), 1),
                "frac_of_measured_peak": round(gbs / (G * peak), 4), "frac_of_nominal_8000": round(gbs / (G * 8000.0), 4)}
+        if solo_ms is not None:
+            # the same config on ONE GPU (rank 0 alone, same invocation): strong scaling unless noted
+            solo_gbs = solo_bytes * k / (solo_ms * 1e-3) / 1e9
+            row["GB/s_on_1_gpu"] = round(solo_gbs, 2)
+            row["efficiency_vs_n1"] = round(gbs / (G * solo_gbs), 4)
         if extra:
             row.update(extra)
         out.append(row)
 
+    def solo(fn_factory):
+        """rank 0 runs the N = 1 form of a config alone while the others wait; returns ms over k steps or None"""
+        ms = None
+        if G > 1:
+            if rank == 0:
+                ms = fn_factory()
+            ranks.barrier()
+            ms = ranks.max(ms if ms is not None else 0.0)
+        return ms
+
     # C1: (d*e*f)*(a*b*c), f64, 1e7 elements, 1 GPU; columns rotate through 3 buffer sets (1.7 GB)
     # so consecutive steps do not re-read L2-resident data
     if G == 1:
-        n1 = 10_000_000
+        n1 = args.n1
         sets = []
         for s in range(3):
             cols = [rt.empty(np.float64, n1) for _ in range(7)]
@@ -442,17 +562,55 @@ def run_extra(args, rt, lib, ranks, peak, timed):
             cols = sets[it[0] % 3]; it[0] += 1
             rt.launch(plan, [cols[6].ptr], [x.ptr for x in cols[:6]], 0, n1, sizes.ptr)
         ms, _ = timed(c1, 30, 6)
-        report("C1 Tests/multiplication.py (d*e*f)*(a*b*c)", "f64", n1, 56 * n1, ms,
-               {"l2": "3 rotating column sets (1.68 GB) > 126 MB L2"}, k=30)
+        extra = {"l2": "3 rotating column sets (1.68 GB) > 126 MB L2"}
+        if check:
+            ok = True
+            for s in range(3):
+                got = device_checksum(rt, lib, sets[s][6].ptr, 8 * n1, csum)
+
+                def c1_chunk(s0, m, s=s):
+                    cols = [oracle.fill(np.float64, s0, m, 100 + 10 * s + j, 2) for j in range(6)]
+                    # nlo_fast_mul6_f64: ((in0*in1)*in2) * ((in3*in4)*in5), the association of the plan above
+                    return words_checksum(oracle.fast_mul6_f64(cols, np.empty(m), 8, 1))
+                ok &= got == combine_checksums(oracle_stream(n1, c1_chunk, threads))[1:]
+            extra["parity"] = verdict(ok, f"64-bit checksums of all {n1} elements of all 3 result columns")
+        report("C1", "C1 Tests/multiplication.py (d*e*f)*(a*b*c)", "f64", n1, 56 * n1, ms, extra, k=30)
         for cols in sets:
             for x in cols:
                 x.free()
 
-    # C3: max over 2^31 f64 / int64 (sharded: 2^31 / G per GPU), NCCL allreduce of the partial
-    n3 = (1 << args.log2n_reduce) // G
+    # C3: max / sum over 2^31 f64 / int64 (sharded: 2^31 / G per GPU), partials exchanged over NVLink
+    n3_total = 1 << args.log2n_reduce
+    n3 = n3_total // G
     for dt, nm, nl_dt in ((np.float64, "f64", abi.NL_F64), (np.int64, "i64", abi.NL_I64)):
+        kind = 3 if dt == np.float64 else 1
+        want = {}
+        if check and rank == 0:
+            # the oracle's answer for the WHOLE column (every rank's shard), chunk-streamed on rank 0's host threads
+            def c3_chunk(s0, m):
+                xs = oracle.fill(dt, s0, m, 7, kind)
+                if dt == np.float64:
+                    return oracle.fast_max_f64(xs, 8, 1), float(np.add.reduce(xs))
+                return oracle.fast_max_i64(xs, 8, 1), oracle.fast_sum_i64(xs, 8, 1)
+            parts = oracle_stream(n3_total, c3_chunk, host_threads())
+            want["max"] = max(p[0] for p in parts)
+            want["sum"] = (float(np.add.reduce(np.array([p[1] for p in parts]))) if dt == np.float64
+                           else int(np.add.reduce(np.array([p[1] for p in parts], dtype=np.int64))))
+        solo_ms = {}
+        if G > 1 and rank == 0:
+            xs_ = rt.empty(dt, n3_total)
+            rt.fill(xs_, 0, 7, kind)
+            rs_ = rt.empty(dt, 1)
+            for op, opname in ((abi.OP_MAX, "max"), (abi.OP_SUM, "sum")):
+                e = Expr(dt)
+                e.materialize(e.unop(op, e.array()))
+                pl = abi.compile_plan(e)
+                solo_ms[opname], _ = timed(lambda _: rt.launch(pl, [rs_.ptr], [xs_.ptr], 0, n3_total, sizes.ptr), k, w, solo=True)
+            xs_.free(); rs_.free()
+            lib.nl_pool_trim(0)
+        ranks.barrier()
         x = rt.empty(dt, n3)
-        rt.fill(x, rank * n3, 7, 3 if dt == np.float64 else 1)
+        rt.fill(x, rank * n3, 7, kind)
         res = rt.empty(dt, 1)
         for op, opname in ((abi.OP_MAX, "max"), (abi.OP_SUM, "sum")):
             e = Expr(dt)
@@ -466,27 +624,78 @@ def run_extra(args, rt, lib, ranks, peak, timed):
 
             def c3_fused(_):
                 rt.launch_allreduce(plan, [res.ptr], [x.ptr], 0, n3, sizes.ptr)
+
+            def c3_local(_):
+                rt.launch(plan, [res.ptr], [x.ptr], 0, n3, sizes.ptr)
+
+            def par(v):
+                if not check:
+                    return {}
+                ok, fsum = True, opname == "sum" and dt == np.float64
+                if rank == 0:                    # rank 0 holds the oracle's answer; every rank holds the same device result
+                    if fsum:
+                        ok = abs(float(v) - want["sum"]) <= 1e-12 * abs(want["sum"])
+                    else:
+                        ok = (float(v) == want[opname]) if dt == np.float64 else (int(v) == want[opname])
+                ok = all_ok(ok)
+                if fsum:
+                    return {"parity": ("within rtol 1e-12 of the oracle: " if ok else "MISMATCH vs oracle: ") +
+                            f"sum over all {n3_total} elements = {float(v)!r}" + (f" (oracle {want['sum']!r})" if rank == 0 else "")}
+                return {"parity": verdict(ok, f"{opname} over all {n3_total} elements = {v!r}")}
+            sm = ranks.max(solo_ms.get(opname, 0.0)) if G > 1 else None
             if G > 1 and fused:
                 # the finish runs inside the reduction kernel over NVLink mailboxes; the NCCL finish is timed beside it
                 ms, _ = timed(c3_fused, k, w)
                 v_fused = rt.download(res)[0]
                 ms_nccl, _ = timed(c3, k, w)
-                same = bool(np.array_equal(v_fused, rt.download(res)[0])) if opname == "max" or nm == "i64" else None
-                report(f"C3 Tests/max.py a.{opname}() + NVLink mailbox finish (in-kernel)", nm, n3, 8 * n3, ms,
-                       {"ms_per_step_nccl_finish": round(ms_nccl / k, 5), "same_as_nccl": same})
+                v_nccl = rt.download(res)[0]
+                ms_local, _ = timed(c3_local, k, w)
+                same = bool(np.array_equal(v_fused, v_nccl)) if opname == "max" or nm == "i64" else bool(abs(v_fused - v_nccl) <= 1e-12 * abs(v_nccl))
+                extra = {"ms_per_step_nccl_finish": round(ms_nccl / k, 5), "ms_per_step_without_finish": round(ms_local / k, 5),
+                         "same_as_nccl": same}
+                extra.update(par(v_fused))
+                report(f"C3 {nm} {opname}", f"C3 Tests/max.py a.{opname}() + NVLink mailbox finish (in-kernel)", nm, n3, 8 * n3, ms,
+                       extra, solo_ms=sm, solo_bytes=8 * n3_total)
             else:
                 ms, _ = timed(c3, k, w)
-                report(f"C3 Tests/max.py a.{opname}()" + (" + NCCL allreduce" if G > 1 else ""), nm, n3, 8 * n3, ms)
+                extra = par(rt.download(res)[0])
+                report(f"C3 {nm} {opname}", f"C3 Tests/max.py a.{opname}()" + (" + NCCL allreduce" if G > 1 else ""), nm, n3, 8 * n3, ms,
+                       extra, solo_ms=sm if G > 1 else None, solo_bytes=8 * n3_total)
         x.free(); res.free()
         lib.nl_pool_trim(0)
 
     # C4: a[a > t] on 2^30 f64 at 1/10/50/90 % selectivity, counts scanned across shards
-    n4 = (1 << args.log2n) // G
+    n4_total = 1 << args.log2n
+    n4 = n4_total // G
+    sels = (0.01, 0.10, 0.50, 0.90)
+    want4 = None
+    if check:
+        # every rank: the oracle's compaction of ITS shard, all four thresholds in one pass over the data
+        def c4_chunk(s0, m):
+            xs = oracle.fill(np.float64, rank * n4 + s0, m, 9, 3)
+            buf = np.empty(m)
+            return [words_checksum(oracle.fast_filter_gt_f64(xs, 1.0 - sel, buf, 8, 1)) for sel in sels]
+        parts = oracle_stream(n4, c4_chunk, threads)
+        want4 = [combine_checksums([p[j] for p in parts]) for j in range(len(sels))]
+    solo4 = {}
+    if G > 1 and rank == 0:
+        xs_, ys_ = rt.empty(np.float64, n4_total), rt.empty(np.float64, n4_total)
+        rt.fill(xs_, 0, 9, 3)
+        for sel in sels:
+            e = Expr(np.float64)
+            xa = e.array()
+            e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(1.0 - sel))))
+            pl = abi.compile_plan(e)
+            ms1, _ = timed(lambda _: rt.launch(pl, [ys_.ptr], [xs_.ptr, None], 0, n4_total, sizes.ptr), k, w, solo=True)
+            solo4[sel] = (ms1, 8 * n4_total + 8 * int(rt.download(sizes, 1)[0]))
+        xs_.free(); ys_.free()
+        lib.nl_pool_trim(0)
+    ranks.barrier()
     x = rt.empty(np.float64, n4)
     rt.fill(x, rank * n4, 9, 3)
     y = rt.empty(np.float64, n4)
     offs = rt.empty(np.int64, G + 1)
-    for sel in (0.01, 0.10, 0.50, 0.90):
+    for j, sel in enumerate(sels):
         e = Expr(np.float64)
         xa = e.array()
         e.materialize(e.filter(xa, e.gt(e.ref(xa), e.scalar(1.0 - sel))))
@@ -497,31 +706,80 @@ def run_extra(args, rt, lib, ranks, peak, timed):
             rt.launch(plan, [y.ptr], [x.ptr, None], 0, n4, sizes.ptr)
             if G > 1:
                 abi.check(lib.nl_finish_filter(cptr, optr, 0))
+
         def c4_fused(_):
             rt.launch_allgather(plan, [y.ptr], [x.ptr, None], 0, n4, sizes.ptr, offs.ptr)
+
+        def c4_local(_):
+            rt.launch(plan, [y.ptr], [x.ptr, None], 0, n4, sizes.ptr)
+
+        def par4(cnt, offsets):
+            if not check:
+                return {}
+            got = device_checksum(rt, lib, y.ptr, 8 * cnt, csum)
+            ok = cnt == want4[j][0] and got == want4[j][1:]
+            what = f"count, values and ORDER of the {cnt} survivors of this rank's shard (64-bit checksums incl. position-weighted)"
+            if offsets is not None:
+                counts = ranks.all_gather_int(want4[j][0])
+                ex = [0]
+                for cval in counts:
+                    ex.append(ex[-1] + cval)
+                ok &= [int(v) for v in offsets] == ex
+                what += f"; offsets vector {ex} on every rank"
+            return {"parity": verdict(all_ok(ok), what)}
+        kname4 = None
         if G > 1 and fused:
             # the shard counts are exchanged and scanned inside the compaction kernel (NVLink mailboxes)
             ms, _ = timed(c4_fused, k, w)
             o_fused = rt.download(offs)
-            ms_nccl, _ = timed(c4, k, w)
             cnt = int(rt.download(sizes, 1)[0])
-            report(f"C4 Tests/filter.py a[a > t] sel={int(sel * 100)}% + NVLink mailbox count scan (in-kernel)", "f64", n4,
-                   8 * n4 + 8 * cnt, ms, {"kept": cnt, "selectivity": round(cnt / n4, 5),
-                                          "ms_per_step_nccl_finish": round(ms_nccl / k, 5),
-                                          "same_as_nccl": bool(np.array_equal(o_fused, rt.download(offs)))})
+            extra = par4(cnt, o_fused)
+            ms_nccl, _ = timed(c4, k, w)
+            o_nccl = rt.download(offs)
+            ms_local, _ = timed(c4_local, k, w)
+            total_kept = int(o_fused[G])
+            s1 = solo4.get(sel)
+            sm, sb = (ranks.max(s1[0] if s1 else 0.0), int(ranks.max(float(s1[1]) if s1 else 0.0)))
+            extra.update({"kept": cnt, "kept_total": total_kept, "selectivity": round(total_kept / n4_total, 5),
+                          "ms_per_step_nccl_finish": round(ms_nccl / k, 5), "ms_per_step_without_finish": round(ms_local / k, 5),
+                          "same_as_nccl": bool(np.array_equal(o_fused, o_nccl))})
+            # bytes: every rank reads its shard and writes its survivors; aggregate = 8 n_total + 8 kept_total
+            gb_per_gpu = (8 * n4_total + 8 * total_kept) / G
+            report(f"C4 {int(sel * 100)}%", f"C4 Tests/filter.py a[a > t] sel={int(sel * 100)}% + NVLink mailbox count scan (in-kernel)", "f64", n4,
+                   gb_per_gpu, ms, extra, solo_ms=sm, solo_bytes=sb)
         else:
             ms, _ = timed(c4, k, w)
+            kname4 = rt.last_launch()[0]
             cnt = int(rt.download(sizes, 1)[0])
-            extra = {"kept": cnt, "selectivity": round(cnt / n4, 5)}
-            if G == 1:
-                extra["properties_at_full_size"] = filter_properties(rt, abi, Expr, x, y, n4, cnt, 1.0 - sel, sizes)
-            report(f"C4 Tests/filter.py a[a > t] sel={int(sel * 100)}%" + (" + count scan" if G > 1 else ""), "f64", n4,
+            extra = {"kept": cnt, "selectivity": round(cnt / n4, 5), "kernel": kname4}
+            extra.update(par4(cnt, rt.download(offs) if G > 1 else None))
+            report(f"C4 {int(sel * 100)}%", f"C4 Tests/filter.py a[a > t] sel={int(sel * 100)}%" + (" + count scan" if G > 1 else ""), "f64", n4,
                    8 * n4 + 8 * cnt, ms, extra)
+    # a filter that has no build-time shape: (a*2+1)[a > t] runs the super-tile kernel under the step interpreter
+    if G == 1:
+        for sel in (0.10, 0.50):
+            e = Expr(np.float64)
+            xa = e.array()
+            val = e.add(e.mul(xa, e.scalar(2.0)), e.scalar(1.0))
+            e.materialize(e.filter(val, e.gt(e.ref(xa), e.scalar(1.0 - sel))))
+            plan = abi.compile_plan(e)
+            ms, _ = timed(lambda _: rt.launch(plan, [y.ptr], [x.ptr, None, None, None], 0, n4, sizes.ptr), k, w)
+            cnt = int(rt.download(sizes, 1)[0])
+            extra = {"kept": cnt, "kernel": rt.last_launch()[0]}
+            if check:
+                def c4d_chunk(s0, m, thr=1.0 - sel):
+                    xs = oracle.fill(np.float64, s0, m, 9, 3)
+                    return words_checksum(xs[xs > thr] * 2.0 + 1.0)
+                wantd = combine_checksums(oracle_stream(n4, c4d_chunk, threads))
+                got = device_checksum(rt, lib, y.ptr, 8 * cnt, csum)
+                extra["parity"] = verdict(cnt == wantd[0] and got == wantd[1:], f"count, values and order of the {cnt} survivors")
+            report(f"C4x {int(sel * 100)}%", f"filter off the static table: (a*2+1)[a > t] sel={int(sel * 100)}% (interpreter-driven compaction)", "f64",
+                   n4, 8 * n4 + 8 * cnt, ms, extra)
     x.free(); y.free(); offs.free()
     lib.nl_pool_trim(0)
 
     # C5: (a[a >= t] * k).max() over 4e9 f32 on 8 GPUs = 5e8 per GPU, single pass, no compaction
-    n5 = 500_000_000
+    n5 = args.n5
     x = rt.empty(np.float32, n5)
     rt.fill(x, rank * n5, 11, 3)
     res = rt.empty(np.float32, 1)
@@ -530,6 +788,12 @@ def run_extra(args, rt, lib, ranks, peak, timed):
     e.materialize(e.max(e.mul(e.filter(xa, e.ge(e.ref(xa), e.scalar(0.5))), e.scalar(3.0))))
     plan = abi.compile_plan(e)
     ptrs = abi.void_array([res.ptr])
+    want5 = None
+    if check:
+        def c5_chunk(s0, m):
+            return oracle.fast_filter_mul_max_f32(oracle.fill(np.float32, rank * n5 + s0, m, 11, 3), 0.5, 3.0, 8, 1)
+        mine = max(oracle_stream(n5, c5_chunk, threads))
+        want5 = max(float(v[0]) for v in ranks.all_gather_array(np.array([mine], dtype=np.float32)))
 
     def c5(_):
         rt.launch(plan, [res.ptr], [x.ptr, None, None], 0, n5, sizes.ptr)
@@ -537,30 +801,45 @@ def run_extra(args, rt, lib, ranks, peak, timed):
 
     def c5_fused(_):
         rt.launch_allreduce(plan, [res.ptr], [x.ptr, None, None], 0, n5, sizes.ptr)
+
+    def c5_local(_):
+        rt.launch(plan, [res.ptr], [x.ptr, None, None], 0, n5, sizes.ptr)
+
+    def par5(v):
+        return {"parity": verdict(all_ok(float(v) == want5), f"max over all {G * n5} elements = {float(v)!r}")} if check else {}
     if G > 1 and fused:
+        sm = solo(lambda: timed(c5_local, k, w, solo=True)[0])       # weak scaling: one GPU's share IS the N = 1 workload
         ms, _ = timed(c5_fused, k, w)
         v_fused = float(rt.download(res)[0])
         ms_nccl, _ = timed(c5, k, w)
-        report("C5 (a[a >= t] * k).max() fused + NVLink mailbox finish (in-kernel)", "f32", n5, 4 * n5, ms,
-               {"result": v_fused, "ms_per_step_nccl_finish": round(ms_nccl / k, 5),
-                "same_as_nccl": v_fused == float(rt.download(res)[0])})
+        v_nccl = float(rt.download(res)[0])
+        ms_local, _ = timed(c5_local, k, w)
+        extra = {"result": v_fused, "ms_per_step_nccl_finish": round(ms_nccl / k, 5), "ms_per_step_without_finish": round(ms_local / k, 5),
+                 "same_as_nccl": v_fused == v_nccl, "scaling": "weak (5e8 per GPU at every N)"}
+        extra.update(par5(v_fused))
+        report("C5", "C5 (a[a >= t] * k).max() fused + NVLink mailbox finish (in-kernel)", "f32", n5, 4 * n5, ms, extra,
+               solo_ms=sm, solo_bytes=4 * n5)
     else:
         ms, _ = timed(c5, k, w)
-        report("C5 (a[a >= t] * k).max() fused" + (" + NCCL allreduce" if G > 1 else ""), "f32", n5, 4 * n5, ms,
-               {"result": float(rt.download(res)[0])})
+        v = float(rt.download(res)[0])
+        extra = {"result": v}
+        extra.update(par5(v))
+        report("C5", "C5 (a[a >= t] * k).max() fused" + (" + NCCL allreduce" if G > 1 else ""), "f32", n5, 4 * n5, ms, extra)
     x.free(); res.free()
 
     # next row: the sort() full breaker as a device radix sort, one GPU's shard
-    if G == 1:
-        n6 = 1 << 28
-        for dt, kind, nm in ((np.int64, 1, "i64 full range"), (np.float64, 3, "f64 in [0,1)"), (np.int64, 0, "i64 in [1,100) like Tests/")):
+    if G == 1 and not args.no_sort:
+        n6 = 1 << args.log2n_sort
+        for dt, kind, nm, sid in ((np.int64, 1, "i64 full range", "sort i64"), (np.float64, 3, "f64 in [0,1)", "sort f64"),
+                                  (np.int64, 0, "i64 in [1,100) like Tests/", "sort i64 1..99")):
             x = rt.empty(dt, n6)
             tmp = rt.empty(dt, n6)
-            best, passes, sum_before = None, 0, None
+            best, passes, sum_before, before = None, 0, None, None
             for rep in range(3):
                 rt.fill(x, 0, 5 + rep, kind)
                 if np.dtype(dt).kind == "i":
                     sum_before = _reduce_device(rt, abi, Expr, abi.OP_SUM, dt, x.ptr, n6, sizes)
+                before = device_checksum(rt, lib, x.ptr, 8 * n6, csum)
                 rt.sync()
                 l0 = lib.nl_launch_count()
                 e0, e1 = rt.event(), rt.event()
@@ -570,76 +849,105 @@ def run_extra(args, rt, lib, ranks, peak, timed):
                 rt.sync()
                 ms1 = rt.elapsed_ms(e0, e1)
                 best = ms1 if best is None else min(best, ms1)
-                passes = (lib.nl_launch_count() - l0 - 1) // 3
-            head = rt.download(x, 1 << 16)
-            traffic = n6 * 8 * (1 + 3 * passes + (2 if passes % 2 else 0))     # histogram read + (count read, scatter read+write) per pass
-            out.append({"config": f"sort() device radix sort, {nm}", "dtype": np.dtype(dt).name, "elements_per_gpu": n6,
-                        "ms_per_step": round(best, 4), "Gkeys/s": round(n6 / best / 1e6, 2), "radix_passes": int(passes),
-                        "GB/s": round(traffic / best / 1e6, 1), "frac_of_measured_peak": round(traffic / best / 1e6 / peak, 4),
-                        "sorted": bool(np.all(head[:-1] <= head[1:])),
-                        "properties_at_full_size": sort_properties(rt, abi, Expr, lib, x, n6, dt, sum_before, sizes)})
+                passes = lib.nl_launch_count() - l0
+            after = device_checksum(rt, lib, x.ptr, 8 * n6, csum)
+            props = sort_properties(rt, abi, Expr, lib, x, n6, dt, sum_before, sizes)
+            props["same_multiset_checksums"] = before[:2] == after[:2]
+            good = props["inversions"] == 0 and props["same_multiset_checksums"] and props.get("sum_unchanged", True)
+            out.append({"id": sid, "config": f"sort() device radix sort, {nm}", "dtype": np.dtype(dt).name, "elements_per_gpu": n6,
+                        "ms_per_step": round(best, 4), "Gkeys/s": round(n6 / best / 1e6, 2), "kernel_launches": int(passes),
+                        "properties_at_full_size": props,
+                        "parity": ("bit-exact by properties: " if good else "MISMATCH: ") + "zero inversions over all keys and unchanged sum/xor checksums (sorted permutation of the input)"})
             x.free(); tmp.free()
+    sizes.free(); csum.free()
     return out
 
 
 # ------------------------------------------------------------------------------ CPU arms
-def host_threads():
-    try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except Exception:
-        return os.cpu_count() or 1
-
-
-def cpu_mul2(n, reps, threads):
-    """The oracle port of the headline pipeline (c = a*b, f32) on `threads` host threads, chunked
-    like the reference (scheduler.cpp:133-147 with thread_count = threads)."""
+def cpu_columns(n, threads):
     import oracle
-    a = oracle.fill(np.float32, 0, n, 42, 2)
-    b = oracle.fill(np.float32, 0, n, 43, 2)
-    c = np.empty_like(a)
-    chunks = max(8, threads)
-    oracle.fast_mul2_f32(a, b, c, chunks, threads)      # warm-up, page-faults the output
+    a, b = np.empty(n, np.float32), np.empty(n, np.float32)
+
+    def gen(s, m):
+        a[s:s + m] = oracle.fill(np.float32, s, m, 42, 2)
+        b[s:s + m] = oracle.fill(np.float32, s, m, 43, 2)
+        return 0
+    oracle_stream(n, gen, threads)
+    return a, b, np.empty(n, np.float32)
+
+
+def cpu_mul2(a, b, c, reps, chunks, workers):
+    """The oracle port of the headline pipeline (c = a*b, f32): the reference's chunking (scheduler.cpp:133-147)
+    with `chunks` ranges on `workers` pthreads; one step = the forced pipeline + the in-place update."""
+    import oracle
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        oracle.fast_mul2_f32(a, b, c, chunks, threads)
+        oracle.fast_mul2_f32(a, b, c, chunks, workers)
         a[0] = 1000.0                                    # the in-place update of the step
         times.append(time.perf_counter() - t0)
     return times
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(args):
+    """the reference's CPU path in its three forms, at the config's own size."""
     threads = host_threads()
-    n = 1 << min(args.log2n, 27)
-    times = cpu_mul2(n, 8, threads)
-    best = statistics.median(times)
-    return {"value": round(12 * n / best / 1e9, 2), "unit": "GB/s", "cores": threads, "kind": "port",
-            "sample": f"c = a*b on 2^{n.bit_length() - 1} f32 elements x 8 repetitions (median), gcc -O3 compiled loop, "
-                      f"{max(8, threads)} chunks on {threads} pthreads",
-            "elements_per_s": round(n / best, 1)}
+    n = 1 << args.log2n
+    a, b, c = cpu_columns(n, threads)
+    chunks = max(8, threads)
+    cpu_mul2(a, b, c, 1, chunks, threads)                                   # page-faults the output
+    intended = statistics.median(cpu_mul2(a, b, c, 5, chunks, threads))     # what the 8-chunk design is for
+    faithful = statistics.median(cpu_mul2(a, b, c, 2, 8, 1))                # what the reference does: ONE worker (scheduler.cpp:227-231)
+    t_np = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        np.multiply(a, b, out=c)
+        a[0] = 1000.0
+        t_np.append(time.perf_counter() - t0)
+    gbs = lambda t: round(12 * n / t / 1e9, 2)
+    return {"value": gbs(intended), "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"c = a*b on 2^{n.bit_length() - 1} f32 elements (the config's size) x 5 repetitions (median), gcc -O3 compiled loop, "
+                      f"{chunks} chunks on {threads} pthreads ('intended' form of the 8-chunk scheduler)",
+            "elements_per_s": round(n / intended, 1),
+            "faithful_one_worker": {"value": gbs(faithful), "unit": "GB/s", "cores": 1,
+                                    "sample": "8 chunks on the reference's single worker thread (scheduler.cpp:227-231), 2 repetitions"},
+            "numpy": {"value": gbs(statistics.median(t_np)), "unit": "GB/s", "cores": 1, "sample": "numpy.multiply(a, b, out=c), 2 repetitions"},
+            "cpu_model": cpu_model(), "nproc": os.cpu_count()}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference
     cannot be built here (CPython 2 + LLVM 3.9), so this is the oracle port with all host
-    threads; rank 0 alone runs it."""
+    threads on the config's own size; rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = host_threads()
-    n = 1 << min(args.log2n, 27)
-    K, W = args.steps, max(args.warmup, 1)
-    K = min(K, 50)
-    times = cpu_mul2(n, K + W, threads)[W:]
+    n = 1 << args.log2n
+    K, W = min(args.steps, 50), max(args.warmup, 1)
+    a, b, c = cpu_columns(n, threads)
+    chunks = max(8, threads)
+    times = cpu_mul2(a, b, c, K + W, chunks, threads)[W:]
     total = sum(times)
     value = 12 * n * len(times) / total / 1e9
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": args.gpus,
             "steps": len(times), "warmup": W, "ms_per_step": round(1e3 * total / len(times), 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Tests/assignment.py at scale: c = a*b forced by a[0] = 1000, then the in-place update",
-                       "elements_per_step": n, "note": "bounded sample of the 2^30-element workload"},
+            "config": headline_config(n, args.gpus),
             "cpu_baseline": {"value": round(value, 2), "unit": "GB/s", "cores": threads, "kind": "port",
-                             "sample": f"2^{n.bit_length() - 1} f32 elements per step, {max(8, threads)} chunks on {threads} pthreads"},
+                             "sample": f"one 2^{n.bit_length() - 1}-element shard (one GPU's share of the config) per step, {chunks} chunks on {threads} pthreads; "
+                                       "rank 0's host only", "cpu_model": cpu_model(), "nproc": os.cpu_count()},
             "e2e": {"value": round(value, 2), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "elements_per_s": round(n * len(times) / total, 1)}
     print(json.dumps(line), flush=True)
@@ -651,10 +959,15 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--log2n", type=int, default=30, help="log2 of elements per GPU for C2/C4")
+    ap.add_argument("--log2n", type=int, default=30, help="log2 of elements per GPU for C2 / of total elements for C4")
     ap.add_argument("--log2n-reduce", dest="log2n_reduce", type=int, default=31, help="log2 of total elements for C3")
-    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=3)
+    ap.add_argument("--log2n-sort", dest="log2n_sort", type=int, default=28)
+    ap.add_argument("--n1", type=int, default=10_000_000, help="elements of C1")
+    ap.add_argument("--n5", type=int, default=500_000_000, help="elements per GPU of C5")
+    ap.add_argument("--e2e-steps", dest="e2e_steps", type=int, default=5)
+    ap.add_argument("--cabi-e2e", dest="cabi_e2e", action="store_true", help="also time the chunk-streamed step through the bare C-ABI")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-sort", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true")

@@ -241,9 +241,19 @@ NL_API int nl_device_sync(int dev);
 /* make `waiter` stream wait for everything enqueued so far on `signaler` */
 NL_API int nl_stream_wait(int dev, int waiter, int signaler_dev, int signaler);
 
-/* CUDA-event timing on the launching stream */
+/* 1 when `ptr` is page-locked host memory the DMA engines can read directly (nl_host_alloc or any
+ * registered block), 0 for pageable memory.  Host-only query. */
+NL_API int nl_host_is_pinned(const void *ptr);
+
+/* CUDA events: timing on the launching stream, and the dependencies between the three streams of a
+ * device that replace the reference's task queue (a task becomes runnable when its children are
+ * done, scheduler.cpp:13-50) — e.g. the kernel over chunk i waits for the upload of chunk i only. */
 typedef struct nl_event_s *nl_event;
 NL_API int nl_event_create(int dev, nl_event *ev_out);
+NL_API int nl_event_create_sync(int dev, nl_event *ev_out);   /* ordering only (no timestamps): cheaper */
+NL_API int nl_event_query(nl_event ev);                       /* 1 complete, 0 still pending, < 0 error */
+/* make (dev, stream) wait for `ev` (recorded on any local device's stream) */
+NL_API int nl_stream_wait_event(int dev, int stream, nl_event ev);
 NL_API int nl_event_destroy(nl_event ev);
 NL_API int nl_event_record(nl_event ev, int stream);
 NL_API int nl_event_sync(nl_event ev);
@@ -321,6 +331,14 @@ NL_API int nl_assign_copy(int dev, int stream, void *dst, int dtype,
  * 3: floats in [0,1).   */
 NL_API int nl_fill(int dev, int stream, void *dst, int dtype, int64_t first_index,
             int64_t count, uint64_t seed, int kind);
+
+/* Three 64-bit checksums of `nbytes` of device memory read as little-endian 64-bit words w_i (a
+ * trailing partial word zero-padded; `ptr` 8-byte aligned):
+ *   out[0] = sum w_i,  out[1] = xor w_i,  out[2] = sum w_i * (2 i + 1)      (mod 2^64)
+ * `out`: DEVICE pointer to 3 uint64.  The device half of the full-size parity check: the host forms
+ * the same sums chunk by chunk from the oracle's output (bench.py).  Asynchronous on (dev, stream)
+ * unless nbytes is not a multiple of 8. */
+NL_API int nl_checksum(int dev, int stream, const void *ptr, size_t nbytes, uint64_t *out);
 
 /* Integer-array indexing (declared but never implemented in the reference: `a[idx]` with an int64
  * index has a cardinality function but no emitter, thunk_as_mapping.cpp:51-55):

@@ -210,7 +210,11 @@ _SIGNATURES = {
     "nl_stream_sync": (C.c_int, [C.c_int, C.c_int]),
     "nl_device_sync": (C.c_int, [C.c_int]),
     "nl_stream_wait": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nl_host_is_pinned": (C.c_int, [_VP]),
     "nl_event_create": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "nl_event_create_sync": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "nl_event_query": (C.c_int, [_VP]),
+    "nl_stream_wait_event": (C.c_int, [C.c_int, C.c_int, _VP]),
     "nl_event_destroy": (C.c_int, [_VP]),
     "nl_event_record": (C.c_int, [_VP, C.c_int]),
     "nl_event_sync": (C.c_int, [_VP]),
@@ -227,6 +231,7 @@ _SIGNATURES = {
     "nl_assign_fill": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_uint64]),
     "nl_assign_copy": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, C.c_int64, C.c_int64, C.c_int64, _VP]),
     "nl_fill": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_int]),
+    "nl_checksum": (C.c_int, [C.c_int, C.c_int, _VP, C.c_size_t, _VP]),
     "nl_sort": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int64]),
     "nl_gather": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int64, C.POINTER(_VP), C.POINTER(C.c_int64), C.c_int, C.c_int64, _VP]),
     "nl_comm_unique_id": (C.c_int, [_VP]),

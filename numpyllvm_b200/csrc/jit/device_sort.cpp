@@ -116,6 +116,7 @@ int storage_copy_range(Storage *src, int64_t lo, int64_t hi, int dst_dev, void *
 
 Storage *storage_repartition(Storage *in) {
   if (nljit_ensure_runtime() < 0) return nullptr;
+  if (storage_settle(in) < 0) return nullptr;
   int rc = sync_devices(nljit_device_count());
   if (rc != NL_OK) { nljit_raise(rc, "jit: device synchronisation failed"); return nullptr; }
   std::vector<Buf> runs;
@@ -135,6 +136,9 @@ Storage *device_sort(Storage *in) {
   const int64_t total = in->cardinality();
   int rc = NL_OK;
   auto fail = [&](int code, const char *what) -> Storage * { nljit_raise(code, what); return nullptr; };
+  if (storage_settle(in) < 0) return nullptr;
+  // evaluation no longer ends with idle devices: peers read these shards over NVLink below
+  if (G > 1 && (rc = sync_devices(G)) != NL_OK) return fail(rc, "jit: device synchronisation failed");
 
   // 1. a sorted copy of every shard
   std::vector<Buf> sorted((size_t)in->shards.size());

@@ -38,6 +38,27 @@ static PyObject *jit_device_count(PyObject *self, PyObject *unused) {
   return PyLong_FromLong(nljit_device_count());
 }
 
+// synchronize(): everything enqueued so far (uploads, kernels, downloads) has completed on return
+static PyObject *jit_synchronize(PyObject *self, PyObject *unused) {
+  (void)self; (void)unused;
+  if (nljit_ensure_runtime() < 0) return NULL;
+  int rc = NL_OK;
+  Py_BEGIN_ALLOW_THREADS
+  for (int g = 0; g < nljit_device_count() && rc == NL_OK; g++) rc = nl_device_sync(g);
+  Py_END_ALLOW_THREADS
+  if (rc != NL_OK) { nljit_raise(rc, "jit: device synchronisation failed"); return NULL; }
+  nljit_reap_uploads(true);
+  Py_RETURN_NONE;
+}
+
+static PyObject *jit_set_chunk_bytes(PyObject *self, PyObject *arg) {
+  (void)self;
+  const long long b = PyLong_AsLongLong(arg);
+  if (b == -1 && PyErr_Occurred()) return NULL;
+  nljit_set_chunk_bytes((int64_t)b);
+  Py_RETURN_NONE;
+}
+
 static PyObject *jit_launch_count(PyObject *self, PyObject *unused) {
   (void)self; (void)unused;
   return PyLong_FromUnsignedLongLong(nl_launch_count());
@@ -92,6 +113,8 @@ static PyMethodDef module_methods[] = {
     {"thunk", PyThunk_FromArray, METH_O, thunk_docstring},
     {"pinned_empty", jit_pinned_empty, METH_VARARGS, "pinned_empty(n, dtype) => 1-D ndarray in page-locked host memory (full-rate DMA)."},
     {"device_count", jit_device_count, METH_NOARGS, "device_count() => number of GPUs the arrays are sharded over."},
+    {"synchronize", jit_synchronize, METH_NOARGS, "synchronize() => waits for every upload, kernel and download enqueued so far (evaluation is stream-ordered)."},
+    {"set_chunk_bytes", jit_set_chunk_bytes, METH_O, "set_chunk_bytes(n) => size of the upload / chunked-evaluation / download chunks (0: default, 32 MiB)."},
     {"launch_count", jit_launch_count, METH_NOARGS, "launch_count() => kernels launched by the engine so far."},
     {"plan", jit_plan, METH_O, "plan(thunk) => text description of the fused pipelines and kernels."},
     {NULL, NULL, 0, NULL}};

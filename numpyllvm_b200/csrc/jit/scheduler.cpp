@@ -9,6 +9,7 @@
 #include "debug_printer.hpp"
 #include "device_sort.hpp"
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -29,15 +30,8 @@ static int64_t *sizes_buffer(int dev) {
 
 static std::vector<PyThunkObject *> g_pending_cuts;
 
-static int sync_devices() {
-  int rc = NL_OK;
-  const int G = nljit_device_count();
-  Py_BEGIN_ALLOW_THREADS     // the reference blocks on a semaphore while holding the GIL (thunk.cpp:106)
-  for (int g = 0; g < G && rc == NL_OK; g++) rc = nl_stream_sync(g, 0);
-  Py_END_ALLOW_THREADS
-  if (rc != NL_OK) { nljit_raise(rc, "jit: device synchronisation failed"); return -1; }
-  return 0;
-}
+// the reference blocks on a semaphore while holding the GIL (thunk.cpp:106); here the GIL is released
+static int sync_devices() { return nljit_sync_devices(); }
 
 // the full pipeline breaker: materialise the child, run the NumPy base function on the host,
 // upload the result (compiler.cpp:93-122)
@@ -139,6 +133,16 @@ static int execute_one(Pipeline *pipeline) {
   LoweredPipeline lp;
   std::vector<PyThunkObject *> cut;
   int lrc = LowerPipeline(pipeline, &lp, &cut);
+  if (lrc == 0) {
+    // A purely elementwise pipeline can follow an upload that is still in flight chunk by chunk;
+    // everything else (and every column on another layout) first orders the compute stream behind it.
+    const bool chunkable = !(lp.plan.flags & (NL_PLAN_HAS_FILTER | NL_PLAN_HAS_COMPACT | NL_PLAN_HAS_REDUCE | NL_PLAN_HAS_WHERE));
+    for (int k = 0; k < lp.n_inputs; k++) {
+      Storage *s = lp.input_sources[k]->storage;
+      if (!s || s->producer < 0) continue;
+      if (!chunkable || lp.inputs[k].kind != NL_IN_ARRAY || s->ragged) { if (storage_settle(s) < 0) return -1; }
+    }
+  }
   if (lrc < 0) return -1;
   if (lrc == 1) {
     // handled by EvaluateWithCuts: re-parse with the proposed thunks as extra breakers
@@ -248,11 +252,56 @@ static int execute_one(Pipeline *pipeline) {
     }
     sizes[g] = sizes_buffer(g);
     if (!sizes[g]) { nljit_raise(NL_ERR_NOMEM, "jit: scratch allocation failed"); return fail(); }
+    // Inputs whose upload is still in flight (jit.thunk() returns before PCIe is done): the kernel runs
+    // chunk by chunk, each launch waiting for the upload of its own chunk only, and leaves marks on the
+    // outputs so that asnumpyarray() can send chunk i home while chunk i + 1 is computed.
+    std::vector<int64_t> bounds;
+    for (int k = 0; k < lp.n_inputs; k++) {
+      Storage *s = lp.input_sources[k]->storage;
+      if (lp.inputs[k].kind != NL_IN_ARRAY || s->producer != NL_STREAM_H2D) continue;
+      std::vector<ReadyMark> &marks = s->shards[g].marks;
+      if (!marks.empty() && nl_event_query(marks.back().ev) == 1) continue;      // landed meanwhile
+      for (const ReadyMark &m : marks) bounds.push_back(m.end);
+    }
+    const int64_t count = shape->shards[g].count;
+    if (!bounds.empty()) {
+      std::sort(bounds.begin(), bounds.end());
+      bounds.erase(std::unique(bounds.begin(), bounds.end()), bounds.end());
+      while (!bounds.empty() && bounds.back() >= count) bounds.pop_back();
+      bounds.push_back(count);
+      int64_t prev = 0;
+      int rc = NL_OK;
+      for (int64_t e : bounds) {
+        if (e <= prev) continue;
+        for (int k = 0; k < lp.n_inputs && rc == NL_OK; k++) {
+          Storage *s = lp.input_sources[k]->storage;
+          if (lp.inputs[k].kind != NL_IN_ARRAY || s->producer != NL_STREAM_H2D) continue;
+          for (const ReadyMark &m : s->shards[g].marks)
+            if (m.end >= e || &m == &s->shards[g].marks.back()) { rc = nl_stream_wait_event(g, NL_STREAM_COMPUTE, m.ev); break; }
+        }
+        if (rc == NL_OK) rc = nl_launch_pipeline(&lp.plan, out_ptrs, in_ptrs, prev, e, sizes[g], 0, g, NL_STREAM_COMPUTE);
+        for (int k = 0; k < lp.n_outputs && rc == NL_OK; k++) {
+          nl_event ev = NULL;
+          rc = nl_event_create_sync(g, &ev);
+          if (rc == NL_OK) rc = nl_event_record(ev, NL_STREAM_COMPUTE);
+          if (ev) outs[k]->shards[g].marks.push_back(ReadyMark{e, ev});
+          outs[k]->producer = NL_STREAM_COMPUTE;
+        }
+        if (rc != NL_OK) { nljit_raise(rc, "jit: pipeline launch failed"); return fail(); }
+        prev = e;
+      }
+      continue;
+    }
+    for (int k = 0; k < lp.n_inputs; k++) {
+      // the upload landed before we looked (or there never was one): plain stream order from here on
+      Storage *s = lp.input_sources[k]->storage;
+      if (lp.inputs[k].kind == NL_IN_ARRAY && s->producer == NL_STREAM_H2D && g == G - 1) storage_drop_marks(s);
+    }
     // a reduction over several GPUs finishes inside its kernel: the partials travel through the
     // peers' NVLink mailboxes, no collective launch follows
     int rc = fused_finish
-                 ? nl_launch_pipeline_allreduce(&lp.plan, out_ptrs, in_ptrs, 0, shape->shards[g].count, sizes[g], g)
-                 : nl_launch_pipeline(&lp.plan, out_ptrs, in_ptrs, 0, shape->shards[g].count, sizes[g], 0, g, 0);
+                 ? nl_launch_pipeline_allreduce(&lp.plan, out_ptrs, in_ptrs, 0, count, sizes[g], g)
+                 : nl_launch_pipeline(&lp.plan, out_ptrs, in_ptrs, 0, count, sizes[g], 0, g, 0);
     if (rc != NL_OK) { nljit_raise(rc, "jit: pipeline launch failed"); return fail(); }
   }
 
@@ -311,11 +360,16 @@ static int execute_tree(Pipeline *pipeline) {
   return execute_one(pipeline);
 }
 
+// Evaluation is stream-ordered: the launches are enqueued and this returns.  The data is waited for
+// where it is read on the host (asnumpyarray / str / device_shards, the counts of a filter) — the
+// reference's caller blocks on a semaphore here (thunk.cpp:106) because its results live in host
+// memory; ours live behind a stream, and not waiting is what lets the upload, the kernel and the
+// download of one expression overlap.
 int ScheduleExecution(Pipeline *pipeline) {
   int rc = execute_tree(pipeline);
   if (rc == -2) return -2;
   if (rc < 0) return -1;
-  return sync_devices();
+  return 0;
 }
 
 // parse -> execute, re-parsing with an extra breaker whenever the optimiser reports that an

@@ -78,14 +78,41 @@ Storage *storage_new(int dtype, int64_t bound) {
   s->host_scalar = false;
   s->scalar_bits = 0;
   s->refs = 1;
+  s->producer = -1;
   return s;
 }
 
 void storage_incref(Storage *s) { if (s) s->refs++; }
 
+void storage_drop_marks(Storage *s) {
+  for (Shard &sh : s->shards) {
+    for (ReadyMark &m : sh.marks) nl_event_destroy(m.ev);
+    sh.marks.clear();
+  }
+  s->producer = -1;
+}
+
+static int settle_rc(Storage *s) {
+  int rc = NL_OK;
+  if (s->producer == NL_STREAM_H2D)
+    for (Shard &sh : s->shards)
+      if (!sh.marks.empty() && rc == NL_OK) rc = nl_stream_wait_event(sh.dev, NL_STREAM_COMPUTE, sh.marks.back().ev);
+  storage_drop_marks(s);
+  return rc;
+}
+
+int storage_settle(Storage *s) {
+  if (!s || s->producer < 0) return 0;
+  int rc = settle_rc(s);
+  if (rc != NL_OK) { nljit_raise(rc, "jit: stream ordering failed"); return -1; }
+  return 0;
+}
+
 void storage_decref(Storage *s) {
   if (!s) return;
   if (--s->refs > 0) return;
+  // buffers go back to the pool in compute-stream order: an upload still in flight must land first
+  settle_rc(s);
   for (Shard &sh : s->shards)
     if (sh.ptr) nl_free(sh.dev, sh.ptr);
   delete s;
@@ -128,21 +155,115 @@ static int sync_all(int stream) {
   return rc;
 }
 
+int nljit_sync_devices() {
+  int rc = sync_all(NL_STREAM_COMPUTE);
+  if (rc != NL_OK) { nljit_raise(rc, "jit: device synchronisation failed"); return -1; }
+  nljit_reap_uploads(false);
+  return 0;
+}
+
+static int64_t g_chunk_bytes = 0;
+
+void nljit_set_chunk_bytes(int64_t b) { g_chunk_bytes = b > 0 ? b : 0; }
+
+int64_t nljit_chunk_elems(size_t itemsize) {
+  int64_t &bytes = g_chunk_bytes;
+  if (!bytes) {
+    bytes = (int64_t)32 << 20;            // 32 MiB: 0.6 ms of PCIe Gen5, 5 us of HBM
+    if (const char *env = getenv("NL_CHUNK_MB")) { const long mb = atol(env); if (mb > 0) bytes = (int64_t)mb << 20; }
+  }
+  int64_t n = (bytes / (int64_t)(itemsize ? itemsize : 1)) & ~(int64_t)1023;
+  return n < 1024 ? 1024 : n;
+}
+
+// ---- uploads in flight from page-locked sources ------------------------------------------
+// The DMA engine reads such a source directly while jit.thunk() has already returned.  Until the
+// last chunk has landed the source ndarray is kept alive and marked read-only (NumPy refuses writes
+// through it), which is what keeps the reference's copy-on-wrap contract (thunk.cpp:30) observable.
+struct Inflight {
+  PyObject *source;
+  bool restore_writeable;
+  std::vector<nl_event> done;     // one per device that received a piece, recorded after its last chunk
+};
+static std::vector<Inflight> g_inflight;
+
+void nljit_reap_uploads(bool block) {
+  size_t w = 0;
+  for (size_t i = 0; i < g_inflight.size(); i++) {
+    Inflight &f = g_inflight[i];
+    bool complete = true;
+    for (nl_event ev : f.done) {
+      if (block) { Py_BEGIN_ALLOW_THREADS nl_event_sync(ev); Py_END_ALLOW_THREADS }
+      else if (nl_event_query(ev) == 0) { complete = false; break; }
+    }
+    if (!complete) { if (w != i) g_inflight[w] = f; w++; continue; }
+    for (nl_event ev : f.done) nl_event_destroy(ev);
+    if (f.restore_writeable) {
+      // the same array may be on its way up a second time: the last upload to finish lifts the guard
+      bool handed_on = false;
+      for (size_t j = 0; j < g_inflight.size() && !handed_on; j++) {
+        const bool alive = (j < i) ? (j < w) : (j > i);      // kept entries [0, w) and the not yet visited ones
+        if (alive && g_inflight[j].source == f.source) { g_inflight[j].restore_writeable = true; handed_on = true; }
+      }
+      if (!handed_on) PyArray_ENABLEFLAGS((PyArrayObject *)f.source, NPY_ARRAY_WRITEABLE);
+    }
+    Py_DECREF(f.source);
+  }
+  g_inflight.resize(w);
+}
+
 Storage *storage_from_host(PyArrayObject *arr) {
+  nljit_reap_uploads(false);
   const int dtype = nljit_npy_to_nl(PyArray_TYPE(arr));
   const int64_t n = (int64_t)PyArray_SIZE(arr);
   Storage *s = storage_new(dtype, n);
   if (storage_alloc_shards(s) < 0) { storage_decref(s); return nullptr; }
   const size_t es = nl_dtype_size(dtype);
   const char *src = (const char *)PyArray_DATA(arr);
+  const bool pinned = nl_host_is_pinned(src) == 1;
+  const int64_t chunk = nljit_chunk_elems(es);
+  Inflight guard;
+  guard.source = (PyObject *)arr;
+  guard.restore_writeable = false;
+  int rc = NL_OK;
+  s->producer = NL_STREAM_H2D;
+  Py_BEGIN_ALLOW_THREADS            // a pageable source is staged by the driver inside the call: do not hold the GIL for it
   for (Shard &sh : s->shards) {
-    if (!sh.capacity) continue;
-    int rc = nl_memcpy_h2d(sh.dev, 0, sh.ptr, src + (size_t)sh.start * es, (size_t)sh.capacity * es);
-    if (rc != NL_OK) { nljit_raise(rc, "jit: host to device copy failed"); storage_decref(s); return nullptr; }
+    if (!sh.capacity || rc != NL_OK) continue;
+    // the block may be recycled pool memory that work already enqueued on the compute stream still uses
+    rc = nl_stream_wait(sh.dev, NL_STREAM_H2D, sh.dev, NL_STREAM_COMPUTE);
+    for (int64_t off = 0; off < sh.capacity && rc == NL_OK; off += chunk) {
+      const int64_t m = sh.capacity - off < chunk ? sh.capacity - off : chunk;
+      rc = nl_memcpy_h2d(sh.dev, NL_STREAM_H2D, (char *)sh.ptr + (size_t)off * es, src + (size_t)(sh.start + off) * es, (size_t)m * es);
+      nl_event ev = nullptr;
+      if (rc == NL_OK) rc = nl_event_create_sync(sh.dev, &ev);
+      if (rc == NL_OK) rc = nl_event_record(ev, NL_STREAM_H2D);
+      if (ev) sh.marks.push_back(ReadyMark{off + m, ev});
+    }
+    if (pinned && rc == NL_OK) {
+      nl_event ev = nullptr;
+      rc = nl_event_create_sync(sh.dev, &ev);
+      if (rc == NL_OK) rc = nl_event_record(ev, NL_STREAM_H2D);
+      if (ev) guard.done.push_back(ev);
+    }
   }
-  // copy-on-wrap (thunk.cpp:30): the caller may change its array as soon as thunk() returns
-  int rc = sync_all(0);
-  if (rc != NL_OK) { nljit_raise(rc, "jit: host to device copy failed"); storage_decref(s); return nullptr; }
+  Py_END_ALLOW_THREADS
+  if (rc != NL_OK) {
+    nljit_raise(rc, "jit: host to device copy failed");
+    for (nl_event ev : guard.done) { nl_event_sync(ev); nl_event_destroy(ev); }
+    sync_all(NL_STREAM_H2D);
+    storage_decref(s);
+    return nullptr;
+  }
+  if (pinned && !guard.done.empty()) {
+    // copy-on-wrap (thunk.cpp:30) without waiting for PCIe: the source is guarded instead of copied
+    if (PyArray_FLAGS(arr) & NPY_ARRAY_WRITEABLE) {
+      PyArray_CLEARFLAGS(arr, NPY_ARRAY_WRITEABLE);
+      guard.restore_writeable = true;
+    }
+    Py_INCREF(guard.source);
+    g_inflight.push_back(guard);
+  }
   return s;
 }
 
@@ -249,15 +370,31 @@ PyObject *storage_to_host(Storage *s) {
   if (!arr) return nullptr;
   char *dst = (char *)PyArray_DATA((PyArrayObject *)arr);
   int64_t off = 0;
+  int rc = NL_OK;
   for (Shard &sh : s->shards) {
-    if (sh.count > 0) {
+    if (sh.count > 0 && rc == NL_OK) {
       // the exclusive scan of the shard counts is where each shard's run lands (compiler.cpp:36-48)
-      int rc = nl_memcpy_d2h(sh.dev, 0, dst + (size_t)off * es, sh.ptr, (size_t)sh.count * es);
-      if (rc != NL_OK) { nljit_raise(rc, "jit: device to host copy failed"); Py_DECREF(arr); return nullptr; }
+      char *to = dst + (size_t)off * es;
+      if (sh.marks.empty()) {
+        rc = nl_stream_wait(sh.dev, NL_STREAM_D2H, sh.dev, NL_STREAM_COMPUTE);
+        if (rc == NL_OK) rc = nl_memcpy_d2h(sh.dev, NL_STREAM_D2H, to, sh.ptr, (size_t)sh.count * es);
+      } else {
+        // the column is still being produced chunk by chunk: each chunk leaves as soon as it is there
+        int64_t prev = 0;
+        for (const ReadyMark &m : sh.marks) {
+          const int64_t end = m.end < sh.count ? m.end : sh.count;
+          if (end <= prev || rc != NL_OK) continue;
+          rc = nl_stream_wait_event(sh.dev, NL_STREAM_D2H, m.ev);
+          if (rc == NL_OK) rc = nl_memcpy_d2h(sh.dev, NL_STREAM_D2H, to + (size_t)prev * es, (const char *)sh.ptr + (size_t)prev * es, (size_t)(end - prev) * es);
+          prev = end;
+        }
+      }
     }
     off += sh.count;
   }
-  int rc = sync_all(0);
+  if (rc == NL_OK) rc = sync_all(NL_STREAM_D2H);
   if (rc != NL_OK) { nljit_raise(rc, "jit: device to host copy failed"); Py_DECREF(arr); return nullptr; }
+  storage_drop_marks(s);          // every chunk has been waited for and copied: the marks have all fired
+  nljit_reap_uploads(false);
   return arr;
 }

@@ -190,6 +190,10 @@ PyObject *PyThunk_AsArray(PyObject *obj) {
   if (!thunk->host) {
     thunk->host = storage_to_host(thunk->storage);
     if (!thunk->host) return NULL;
+    // The reference hands out its storage itself (thunk.cpp:115-124); this is a host COPY of device
+    // storage, cached until the thunk is assigned to.  Read-only, so that a write meant for the thunk
+    // fails loudly instead of silently diverging from the device data.
+    PyArray_CLEARFLAGS((PyArrayObject *)thunk->host, NPY_ARRAY_WRITEABLE);
   }
   return thunk->host;
 }

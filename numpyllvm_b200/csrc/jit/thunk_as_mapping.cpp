@@ -33,6 +33,9 @@ static PyObject *thunk_gather(PyThunkObject *self, PyThunkObject *index) {
     return NULL;
   }
   if (nljit_ensure_runtime() < 0) return NULL;
+  if (storage_settle(col) < 0 || storage_settle(idx) < 0) return NULL;
+  // peers read `col` with plain loads over NVLink: what other GPUs' streams still owe it must be done
+  if (nljit_device_count() > 1 && nljit_sync_devices() < 0) return NULL;
   const int64_t total = col->cardinality();
   const void *ptrs[NL_MAX_DEVICES];
   int64_t starts[NL_MAX_DEVICES];
@@ -197,6 +200,7 @@ static int assign_run(PyThunkObject *self, int64_t lo, int64_t step, int64_t cou
     if (vt->card.n > 1) {
       if (PyThunk_EnsureDevice(vt) < 0) return -1;
       Storage *vs = vt->storage;
+      if (storage_settle(vs) < 0) return -1;
       if (vs == st) {
         // a[...] = a: the whole column onto itself is a no-op; anything else goes through a host copy below
         if (lo == 0 && step == 1 && count == vs->cardinality()) return 0;
@@ -372,6 +376,9 @@ static int thunk_assign_subscript(PyObject *self_o, PyObject *ind, PyObject *val
   if (!r) { Py_XDECREF(where); return -1; }
   Py_DECREF(r);
   if (PyThunk_EnsureDevice(self) < 0) { Py_XDECREF(where); return -1; }
+  // the update runs on the compute stream: behind the target's upload, and nobody may go on following
+  // readiness marks that do not know about the write
+  if (storage_settle(self->storage) < 0) { Py_XDECREF(where); return -1; }
 
   int rc = -1;
   if (where) {

@@ -85,11 +85,7 @@ static PyObject *_thunk_device_shards(PyThunkObject *self, PyObject *args) {
   }
   const char *typestr = s->dtype == NL_I32 ? "<i4" : s->dtype == NL_I64 ? "<i8" : s->dtype == NL_F32 ? "<f4"
                         : s->dtype == NL_F64 ? "<f8" : "|b1";
-  int rc = NL_OK;
-  Py_BEGIN_ALLOW_THREADS
-  for (int g = 0; g < nljit_device_count() && rc == NL_OK; g++) rc = nl_stream_sync(g, 0);
-  Py_END_ALLOW_THREADS
-  if (rc != NL_OK) { nljit_raise(rc, "jit: device synchronisation failed"); return NULL; }
+  if (storage_settle(s) < 0 || nljit_sync_devices() < 0) return NULL;
   PyObject *list = PyList_New(0);
   if (!list) return NULL;
   for (const Shard &sh : s->shards) {

@@ -86,6 +86,8 @@ int launch_fill(void *stream, int sm_count, void *dst, int dtype, int64_t first_
 int launch_empty_range(void *stream, const nl_plan *plan, const KParams &kp);
 int launch_gather(void *stream, int sm_count, int dtype, void *out, const int64_t *idx, int64_t count, const void *const *shard_ptr,
                   const int64_t *shard_start, int n_shards, int64_t total, int64_t *bad);
+// nl_checksum.cu
+int launch_checksum(void *stream, int sm_count, const void *ptr, size_t nbytes, unsigned long long *out);
 // nl_sort.cu
 int launch_sort(void *stream, int sm_count, int dtype, void *keys, void *tmp, int64_t n);
 int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t name_len, int *is_static);

@@ -294,6 +294,13 @@ int nl_host_free(void *ptr) {
   return NL_OK;
 }
 
+int nl_host_is_pinned(const void *ptr) {
+  if (g_ndev == 0 || !ptr) return 0;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return attr.type == cudaMemoryTypeHost ? 1 : 0;
+}
+
 static int copy_async(int dev, int stream, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
   int rc = check_dev(dev, stream);
   if (rc) return rc;
@@ -361,6 +368,34 @@ int nl_event_create(int dev, nl_event *ev_out) {
   cudaError_t ce = cudaEventCreate(&e->ev);
   if (ce != cudaSuccess) { delete e; CUDA_TRY(ce); }
   *ev_out = e;
+  return NL_OK;
+}
+int nl_event_create_sync(int dev, nl_event *ev_out) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  if (!ev_out) { set_error("nl_event_create_sync: null"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  nl_event_s *e = new nl_event_s;
+  e->dev = dev;
+  cudaError_t ce = cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming);
+  if (ce != cudaSuccess) { delete e; CUDA_TRY(ce); }
+  *ev_out = e;
+  return NL_OK;
+}
+int nl_event_query(nl_event ev) {
+  if (!ev) { set_error("null event"); return NL_ERR_INVALID; }
+  cudaError_t ce = cudaEventQuery(ev->ev);
+  if (ce == cudaSuccess) return 1;
+  if (ce == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+  CUDA_TRY(ce);
+  return 0;
+}
+int nl_stream_wait_event(int dev, int stream, nl_event ev) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (!ev) { set_error("null event"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  CUDA_TRY(cudaStreamWaitEvent(g_dev[dev].stream[stream], ev->ev, 0));
   return NL_OK;
 }
 int nl_event_destroy(nl_event ev) {
@@ -534,6 +569,15 @@ int nl_gather(int dev, int stream, int dtype, void *out, const int64_t *idx, int
   if (count == 0) return NL_OK;
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
   return launch_gather(g_dev[dev].stream[stream], g_dev[dev].sm_count, dtype, out, idx, count, shard_ptr, shard_start, n_shards, total, bad);
+}
+
+int nl_checksum(int dev, int stream, const void *ptr, size_t nbytes, uint64_t *out) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (!out || (nbytes > 0 && !ptr)) { set_error("nl_checksum: bad argument"); return NL_ERR_INVALID; }
+  if (((uintptr_t)ptr & 7) != 0) { set_error("nl_checksum: the buffer must be 8-byte aligned"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_checksum(g_dev[dev].stream[stream], g_dev[dev].sm_count, ptr, nbytes, (unsigned long long *)out);
 }
 
 int nl_sort(int dev, int stream, int dtype, void *keys, void *tmp, int64_t count) {

@@ -4,6 +4,8 @@ Bar: bit-exact for integer ops, masks, filters (values, order, count), max/min a
 float elementwise (the kernels are built with -fmad=false); float sums within
 rtol 1e-12 (f64) / 1e-6 (f32) of the oracle.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -461,3 +463,18 @@ def test_true_division(rt, dtype):
     xa = e.array()
     e.materialize(e.filter(e.div(e.scalar(np.dtype(dtype).type(1)), xa), e.gt(e.ref(xa), e.scalar(np.dtype(dtype).type(0)))))
     assert_same_up_to_nan_payload(*both(rt, e, [a, None, None], n))          # 1/a where a > 0: division before a compaction
+
+
+@pytest.mark.parametrize("nbytes", [0, 8, 24, 4096 + 8, (1 << 22) + 16, (1 << 22) + 12, 1001])
+@pytest.mark.parametrize("misalign", [0, 8])
+def test_checksum_kernel_matches_its_host_definition(nl, nbytes, misalign):
+    """nl_checksum (the device half of bench.py's full-size parity checks) against the NumPy restatement."""
+    import bench
+    rt = Runtime.get()
+    rng = np.random.default_rng(nbytes + misalign)
+    host = rng.integers(0, 256, nbytes + misalign, dtype=np.uint8)
+    d = rt.upload(host) if host.size else rt.empty(np.uint8, 16)
+    out = rt.empty(np.uint64, 3)
+    abi.check(nl.nl_checksum(0, 0, C.c_void_p(d.ptr + misalign), nbytes, C.c_void_p(out.ptr)))
+    got = tuple(int(v) for v in rt.download(out))
+    assert got == bench.words_checksum(host[misalign:])[1:]

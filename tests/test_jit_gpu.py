@@ -399,3 +399,82 @@ def test_columns_combined_after_a_filter_are_split_into_pipelines(n):
     h = (a[a > 5] * 2)[b[a > 5] >= 50]          # filter, arithmetic, then a filter by another filtered column
     assert np.array_equal(h.asnumpyarray(), (a_n[a_n > 5] * 2)[b_n[a_n > 5] >= 50])
     assert (a[m] * b[m]).sum().asnumpyarray()[0] == (a_n[a_n > 40] * b_n[a_n > 40]).sum()
+
+
+# ---- the asynchronous host edge -----------------------------------------------
+@pytest.fixture
+def small_chunks():
+    jit.set_chunk_bytes(1 << 20)       # 1 MiB chunks: a few dozen per column at the sizes below
+    yield
+    jit.set_chunk_bytes(0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.int64])
+@pytest.mark.parametrize("n", [1000, (1 << 22) + 13, 3 * (1 << 22)])
+def test_pipelined_upload_compute_download(small_chunks, dtype, n):
+    rng = np.random.default_rng(3)
+    ha, hb = jit.pinned_empty(n, dtype), jit.pinned_empty(n, dtype)
+    ha[:] = rng.integers(1, 100, n).astype(dtype)
+    hb[:] = rng.integers(1, 100, n).astype(dtype)
+    want = ha * hb
+    for _ in range(3):                              # buffers and pinned blocks are recycled between rounds
+        a, b = jit.thunk(ha), jit.thunk(hb)         # returns while PCIe is still busy
+        c = a * b
+        a[0] = 1000                                 # forces c chunk by chunk behind the uploads, then writes a
+        c.evaluate()
+        out = c.asnumpyarray()                      # chunks leave as they are computed
+        assert np.array_equal(out, want)
+        assert a.asnumpyarray()[0] == 1000 and np.array_equal(a.asnumpyarray()[1:], ha[1:])
+        del a, b, c, out
+    jit.synchronize()
+    assert ha.flags.writeable and hb.flags.writeable     # the write guard is lifted once the DMA is done
+    ha[0] = 5                                            # and the caller's buffer is its own again
+
+
+def test_copy_on_wrap_holds_for_pageable_and_pinned_sources(small_chunks):
+    n = (1 << 22) + 5
+    x = np.arange(n, dtype=np.int64)                 # pageable: consumed when thunk() returns
+    t = jit.thunk(x)
+    x[:] = -1
+    assert np.array_equal(t.asnumpyarray(), np.arange(n, dtype=np.int64))
+    p = jit.pinned_empty(n, np.int64)
+    p[:] = np.arange(n)
+    u = jit.thunk(p)                                 # page-locked: read by the DMA engine after thunk() returned
+    try:
+        p[:] = -1                                    # either the guard refuses the write ...
+    except ValueError:
+        pass
+    got = u.asnumpyarray()                           # ... or the upload had landed already: never a torn column
+    assert np.array_equal(got, np.arange(n)) or np.array_equal(got, np.full(n, -1))
+    jit.synchronize()
+    assert p.flags.writeable
+
+
+def test_consumers_that_are_not_chunk_aware_wait_for_the_upload(small_chunks):
+    n = (1 << 22) + 77
+    rng = np.random.default_rng(5)
+    hx = jit.pinned_empty(n, np.float64)
+    hx[:] = rng.random(n)
+    x_n = hx.copy()
+    assert jit.thunk(hx).sum().asnumpyarray()[0] == pytest.approx(x_n.sum(), rel=1e-12)      # reduction
+    assert np.array_equal(jit.thunk(hx)[jit.thunk(hx) > 0.5].asnumpyarray(), x_n[x_n > 0.5])  # compaction
+    assert np.array_equal(jit.thunk(hx).sort().asnumpyarray(), np.sort(x_n))                  # full breaker
+    idx = rng.integers(0, n, 1000)
+    assert np.array_equal(jit.thunk(hx)[idx].asnumpyarray(), x_n[idx])                         # gather
+    t = jit.thunk(hx)
+    t[10:20] = 3.0                                                                             # in-place write
+    x_n[10:20] = 3.0
+    assert np.array_equal(t.asnumpyarray(), x_n)
+    u = jit.thunk(hx)
+    del u                                                                                      # dropped mid-upload
+    y = (jit.thunk(hx) * 2 + 1) * jit.thunk(hx)                                                # chain of chunked pipelines
+    assert np.array_equal(y.asnumpyarray(), (hx * 2 + 1) * hx)
+    jit.synchronize()
+    assert hx.flags.writeable
+
+
+def test_the_cached_host_copy_is_read_only():
+    t = jit.thunk(np.arange(10))
+    arr = t.asnumpyarray()
+    with pytest.raises(ValueError):
+        arr[0] = 1
