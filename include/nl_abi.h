@@ -386,8 +386,20 @@ NL_API uint64_t nl_launch_count(void);
  * would run — a build-time instantiated shape ("static:<shape>") or the dynamic
  * interpreter.  Host-only.  vec16: rows of 128 bits (aligned operands) or scalar rows. */
 NL_API int nl_plan_kernel(const nl_plan *plan, int vec16, char *name, size_t name_len, int *is_static);
-/* Testing hook: 0 forces every launch through the dynamic interpreter. */
-NL_API int nl_set_static_kernels(int enabled);
+/* Which tiers of kernel-template selection a launch may use (tests run every tier on the same
+ * programs): 1 (default) exact build-time shapes, then shape families, then the step interpreter;
+ * 2 families and interpreter; 0 interpreter only. */
+NL_API int nl_set_static_kernels(int mode);
+/* Named tuning knobs (benchmarking / tests; the defaults are what the measurements in DESIGN.md use):
+ *   "compact_kernel"     0 chosen by size: super-tile kernel, staged TMA pipeline, plain kernel (default);
+ *                        1 plain kernel only; 2 staged pipeline before the super-tile kernel
+ *   "pipe_dynamic"       1: the staged pipeline may also run under the step interpreter (default 0)
+ *   "pipe_side_buffers"  0: no side buffers in the staged pipeline (default 1)
+ *   "pipe_lag"           tiles between count and store phase of the staged pipeline (0: half the ring)
+ *   "max_ctas_per_sm"    cap on resident CTAs per SM of the streaming kernels (0: by occupancy)
+ *   "reset"              all of the above back to their defaults (value ignored)
+ * Unknown keys and out-of-range values return NL_ERR_INVALID. */
+NL_API int nl_tune(const char *key, int value);
 /* Name and grid of the most recent pipeline launch (for logs / tests). */
 NL_API int nl_last_launch_info(char *kernel_name, size_t name_len, int *grid, int *block, int *vec_elems);
 

@@ -243,6 +243,7 @@ _SIGNATURES = {
     "nl_comm_peer_ready": (C.c_int, []),
     "nl_plan_kernel": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]),
     "nl_set_static_kernels": (C.c_int, [C.c_int]),
+    "nl_tune": (C.c_int, [C.c_char_p, C.c_int]),
     "nl_launch_count": (C.c_uint64, []),
     "nl_last_launch_info": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
 }

@@ -33,7 +33,9 @@ NVCC_FLAGS += os.environ.get("NL_EXTRA_NVCC_FLAGS", "").split()   # tuning exper
 KERNEL_SOURCES = ["nl_plan.cpp", "nl_kernels.cu", "nl_runtime.cu", "nl_sort.cu", "nl_checksum.cu",
                   "nl_dynamic_i32.cu", "nl_dynamic_i64.cu", "nl_dynamic_f32.cu", "nl_dynamic_f64.cu",
                   "nl_static_i32.cu", "nl_static_i64.cu", "nl_static_f32.cu", "nl_static_f64.cu",
-                  "nl_static_i32_b.cu", "nl_static_i64_b.cu", "nl_static_f32_b.cu", "nl_static_f64_b.cu"]
+                  "nl_static_i32_b.cu", "nl_static_i64_b.cu", "nl_static_f32_b.cu", "nl_static_f64_b.cu",
+                  "nl_family_i32.cu", "nl_family_i64.cu", "nl_family_f32.cu", "nl_family_f64.cu",
+                  "nl_family_i32_b.cu", "nl_family_i64_b.cu", "nl_family_f32_b.cu", "nl_family_f64_b.cu"]
 JIT_SOURCES = ["jitpackage.cpp", "device_sort.cpp", "thunk.cpp", "operation.cpp", "thunk_as_number.cpp", "thunk_as_mapping.cpp",
                "thunk_as_sequence.cpp", "thunk_methods.cpp", "parser.cpp", "optimizer.cpp", "scheduler.cpp",
                "debug_printer.cpp", "storage.cpp"]

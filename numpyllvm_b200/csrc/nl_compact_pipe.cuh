@@ -170,6 +170,8 @@ struct DynSplit {
       sparse_step<T>(p, step_op(s), step_a(s), step_b(s), v, pos);
     }
   }
+  // store pass of the super-tile kernel: do the steps before the filter have to run again? (host: store_pass_needs_prefix)
+  static __device__ __forceinline__ bool needs_prefix(const KParams &p) { return p.store_prefix != 0; }
 };
 
 template <uint32_t... S>
@@ -210,6 +212,42 @@ struct StaticSplit {
   static __device__ __forceinline__ void after_sparse(const KParams &p, T v, long long pos) {
     run_sparse<T, filter_index() + 1>(p, v, pos, std::make_index_sequence<N - filter_index() - 1>{});
   }
+  NL_HD static constexpr bool needs_prefix_c() {
+    constexpr uint32_t st[] = {S...};
+    return store_pass_needs_prefix(st, N, filter_index());
+  }
+  static __device__ __forceinline__ bool needs_prefix(const KParams &) { return needs_prefix_c(); }
+};
+
+// The same split for a shape family (FamilyProg): the step kinds on either side of the filter are
+// build-time, operators and inputs come from the launch.
+template <uint32_t... K>
+struct FamilySplit {
+  using Prog = FamilyProg<K...>;
+  static constexpr int N = sizeof...(K);
+  NL_HD static constexpr int filter_index() {
+    constexpr uint32_t st[] = {K...};
+    for (int i = 0; i < N; i++)
+      if (step_op(st[i]) == S_FILTER) return i;
+    return N;
+  }
+  template <bool kValuesOnly, class TileT, int I0, size_t... I>
+  static __device__ __forceinline__ void run_seq(TileT &t, const KParams &p, TileShared &sh, int lane, int warp, std::index_sequence<I...>) {
+    (Prog::template step<I0 + (int)I, kValuesOnly>(t, p, sh, lane, warp), ...);
+  }
+  template <bool kValuesOnly, class TileT>
+  static __device__ __forceinline__ void before(TileT &t, const KParams &p, TileShared &sh, int lane, int warp) {
+    run_seq<kValuesOnly, TileT, 0>(t, p, sh, lane, warp, std::make_index_sequence<filter_index()>{});
+  }
+  template <class TileT>
+  static __device__ __forceinline__ void after(TileT &t, const KParams &p, TileShared &sh, int lane, int warp) {
+    run_seq<false, TileT, filter_index() + 1>(t, p, sh, lane, warp, std::make_index_sequence<N - filter_index() - 1>{});
+  }
+  NL_HD static constexpr bool needs_prefix_c() {
+    constexpr uint32_t st[] = {K...};
+    return store_pass_needs_prefix(st, N, filter_index());
+  }
+  static __device__ __forceinline__ bool needs_prefix(const KParams &) { return needs_prefix_c(); }
 };
 
 // Optional per-role time breakdown (cycles), printed by CTA 0 when built with -DNL_PIPE_STATS.

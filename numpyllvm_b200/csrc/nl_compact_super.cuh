@@ -40,6 +40,16 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) compact_super_kernel(const _
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long n_sub = (p.end - p.start + TileT::TILE - 1) / TileT::TILE;
 
+  // which CTA of its SM is this?  (the kernel is persistent: all CTAs are resident from the start)
+  if (tid == 0) {
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    sh.last = (int)atomicAdd(&p.sm_rank[smid & 255u], 1u);
+  }
+  __syncthreads();
+  const bool may_retire = sh.last >= p.super_keep_ctas;
+  __syncthreads();
+
   if (blockIdx.x == 0 && tid == 0) {
     for (int o = 0; o < p.n_outputs; o++)
       if (p.out_space[o] == NL_IDX_LOOP) p.out_sizes[o] = p.end;
@@ -127,7 +137,8 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) compact_super_kernel(const _
       if (wtot[k][warp] == 0) continue;             // warp-uniform
       const long long sub = super * K + k;
       t.begin_tile(p, sub, tid);
-      if (keepm[k]) Split::template before<true>(t, p, sh, lane, warp);
+      // (only when a value from before the filter is still needed: `(a*2+1)[a > t]` reloads its column after it)
+      if (keepm[k] && Split::needs_prefix(p)) Split::template before<true>(t, p, sh, lane, warp);
       t.keep = keepm[k];
       t.rank_rows(lane);
       t.cbase = base_out + (long long)woff[k][warp];
@@ -137,10 +148,10 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) compact_super_kernel(const _
     __syncthreads();                                // sh.tile / wtot are rewritten by the next round
     // The rows of K tiles per resident CTA wait in L2 between the two passes.  When most elements
     // survive, the survivors written meanwhile push that window (4 CTAs/SM x 128 KB = 76 MB) out of
-    // L2 and the store pass re-reads from HBM (measured +36 % DRAM reads at 90 %).  The CTAs of the
-    // fourth wave then retire: three per SM keep the window at 57 MB (0.85 -> 0.94 of the roofline
-    // at 90 %), while sparse inputs keep all four (0.90 vs 0.80 at 1 %).
-    if (dense && (int)blockIdx.x >= p.super_drop_from) break;
+    // L2 and the store pass re-reads from HBM (measured +36 % DRAM reads at 90 %).  The CTA that
+    // started fourth on its SM then retires: three per SM keep the window at 57 MB (0.85 -> 0.94 of
+    // the roofline at 90 %), while sparse inputs keep all four (0.90 vs 0.80 at 1 %).
+    if (dense && may_retire) break;
   }
 }
 

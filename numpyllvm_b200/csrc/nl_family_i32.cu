@@ -1,0 +1,8 @@
+// nl_family_i32.cu — build-time instantiations of the shape families of nl_family.cuh for int32_t (first half).
+#define NL_STATIC_T int32_t
+#define NL_STATIC_DTYPE NL_I32
+#include "nl_family.cuh"
+
+namespace nl {
+NL_DEFINE_FAMILY_TABLE(family_table_i32)
+}  // namespace nl

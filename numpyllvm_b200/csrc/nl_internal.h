@@ -20,6 +20,7 @@ struct KParams {
   // scratch (per device+stream arena)
   unsigned long long *tile_desc;  // decoupled look-back descriptors, n_tiles entries, zeroed
   unsigned int *tile_ticket;      // dynamic tile counter, zeroed
+  unsigned int *sm_rank;          // per SM (%smid): CTAs of this launch that have started there, zeroed (compaction)
   unsigned long long *red_partials;  // one 8-byte partial per CTA
   unsigned int *red_ticket;       // self-resetting
   uint32_t step[NL_MAX_STEPS];
@@ -41,7 +42,8 @@ struct KParams {
   int32_t pipe_rows;                  // 16-byte rows per consumer thread and tile of the chosen instantiation
   int32_t super_k;                    // > 0: super-tile compaction kernel (nl_compact_super.cuh), tiles per super-tile
   int32_t super_rows;                 // ... and its rows per thread
-  int32_t super_drop_from;            // CTAs with blockIdx >= this retire when they meet a dense super-tile
+  int32_t super_keep_ctas;            // a CTA that was not among the first `super_keep_ctas` on its SM retires when it meets a dense super-tile
+  int32_t store_prefix;               // the store pass re-runs the value steps before the filter (nl_step.h: store_pass_needs_prefix)
   // fused multi-GPU finish of a reduction over peer memory (NVLink mailboxes, nl_pipeline.cuh)
   unsigned long long *const *peer_box;   // device array: mailbox of every rank, mapped here (NULL: no fused finish)
   int32_t peer_world, peer_rank;
@@ -77,7 +79,7 @@ int launch_pipeline_kernel(const nl_plan *plan, const KParams &kp, bool vec16, i
                            void *stream /*cudaStream_t*/, LaunchInfo *info);
 // elements per tile of the kernel that nl_launch_pipeline would select for this plan and size;
 // fills the staged-pipeline fields of *kp when that kernel is chosen
-int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp);
+int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp, int sm_count);
 int launch_finalize_partials(void *stream, int rop, int dtype, const void *partials, int n, void *out);
 int launch_assign_fill(void *stream, int sm_count, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, uint64_t bits);
 int launch_assign_copy(void *stream, int sm_count, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, const void *src);

@@ -140,20 +140,34 @@ static pipeline_fn pick_dynamic(int dtype, bool vec16, bool compact, bool reduce
 static int g_static_enabled = 1;
 void set_static_kernels_enabled(int on) { g_static_enabled = on; }
 
+// three tiers: an exact build-time shape (nl_static.cuh), a shape family (nl_family.cuh: operators and
+// inputs are run-time fields), else the step interpreter.  g_static_enabled: 1 all tiers, 2 families and
+// interpreter only, 0 interpreter only (tests run every tier on the same programs).
 static const StaticEntry *find_static(const nl_plan *plan, bool vec16) {
   if (!g_static_enabled || !vec16) return nullptr;
-  for (int half = 0; half < 2; half++) {          // the shape list is compiled in two halves per dtype
+  for (int tier = (g_static_enabled == 2 ? 2 : 0); tier < 4; tier++) {          // each list is compiled in two halves per dtype
     int n = 0;
     const StaticEntry *tab = nullptr;
-    switch (plan->dtype) {
-      case NL_I32: tab = half ? static_table_i32_b(&n) : static_table_i32(&n); break;
-      case NL_I64: tab = half ? static_table_i64_b(&n) : static_table_i64(&n); break;
-      case NL_F32: tab = half ? static_table_f32_b(&n) : static_table_f32(&n); break;
-      case NL_F64: tab = half ? static_table_f64_b(&n) : static_table_f64(&n); break;
-      default: return nullptr;
+    const int half = tier & 1;
+    if (tier < 2) {
+      switch (plan->dtype) {
+        case NL_I32: tab = half ? static_table_i32_b(&n) : static_table_i32(&n); break;
+        case NL_I64: tab = half ? static_table_i64_b(&n) : static_table_i64(&n); break;
+        case NL_F32: tab = half ? static_table_f32_b(&n) : static_table_f32(&n); break;
+        case NL_F64: tab = half ? static_table_f64_b(&n) : static_table_f64(&n); break;
+        default: return nullptr;
+      }
+    } else {
+      switch (plan->dtype) {
+        case NL_I32: tab = half ? family_table_i32_b(&n) : family_table_i32(&n); break;
+        case NL_I64: tab = half ? family_table_i64_b(&n) : family_table_i64(&n); break;
+        case NL_F32: tab = half ? family_table_f32_b(&n) : family_table_f32(&n); break;
+        case NL_F64: tab = half ? family_table_f64_b(&n) : family_table_f64(&n); break;
+        default: return nullptr;
+      }
     }
     for (int i = 0; i < n; i++)
-      if (tab[i].matches(plan->step, plan->n_steps)) return &tab[i];
+      if (tab[i].matches(plan)) return &tab[i];
   }
   return nullptr;
 }
@@ -247,24 +261,25 @@ static pipeline_fn pick_dynamic_super(int dtype, bool uses_temps) {
 }
 
 // super-tile compaction kernel for this plan?  Fills kp->super_k / super_rows / filter_step.
-static bool super_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
+static bool super_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp, int sm_count) {
   if (!g_pipe_enabled || !vec16) return false;        // "plain kernel only" switches both off
   const int filter = split_point(plan);
   if (filter < 0) return false;
   const StaticEntry *se = find_static(plan, true);
   const int rows = (se && se->super) ? se->super_rows : kRows;
   const int64_t tile = (int64_t)kBlock * rows * (int64_t)(16 / nl_dtype_size(plan->dtype));
-  if (n_elems < tile * kSuperK * 148) return false;      // at least one super-tile per SM
+  if (n_elems < tile * kSuperK * sm_count) return false;      // at least one super-tile per SM
   if (kp) {
     kp->super_k = kSuperK;
     kp->super_rows = rows;
     kp->filter_step = filter;
     kp->n_inputs = plan->n_inputs;
+    kp->store_prefix = store_pass_needs_prefix(plan->step, plan->n_steps, filter) ? 1 : 0;
   }
   return true;
 }
 
-static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
+static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp, int sm_count) {
   if (!g_pipe_enabled || !vec16) return false;
   const int filter = split_point(plan);
   if (filter < 0) return false;
@@ -289,7 +304,7 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
   const int rows = (cols == 1) ? kPipeRows : kPipeRowsNarrow;
   if (has_static_pipe && se->pipe_rows != rows) return false;   // e.g. a scalar slot of the shape bound to a column
   const int64_t tile = (int64_t)kPipeConsumers * rows * (int64_t)(16 / es);
-  if (n_elems < tile * 2 * 148) return false;
+  if (n_elems < tile * 2 * sm_count) return false;
   // the side buffer can take a survivor only if everything after the filter works on a bare
   // value: scalar operands and compacted stores
   bool sparse_ok = true;
@@ -327,15 +342,16 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
   return true;
 }
 
-int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp) {
+int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp, int sm_count) {
+  if (sm_count < 1) sm_count = 148;        // host-only callers (plan descriptions): a B200
   const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
   KParams local;
   KParams *q = kp ? kp : &local;
   q->super_k = 0;
   q->n_slots = 0;
-  if (g_prefer_pipe && pipe_eligible(plan, vec16, n_elems, q)) return (int64_t)kPipeConsumers * q->pipe_rows * v;
-  if (super_eligible(plan, vec16, n_elems, q)) return (int64_t)kBlock * q->super_rows * v * q->super_k;
-  if (!g_prefer_pipe && pipe_eligible(plan, vec16, n_elems, q)) return (int64_t)kPipeConsumers * q->pipe_rows * v;
+  if (g_prefer_pipe && pipe_eligible(plan, vec16, n_elems, q, sm_count)) return (int64_t)kPipeConsumers * q->pipe_rows * v;
+  if (super_eligible(plan, vec16, n_elems, q, sm_count)) return (int64_t)kBlock * q->super_rows * v * q->super_k;
+  if (!g_prefer_pipe && pipe_eligible(plan, vec16, n_elems, q, sm_count)) return (int64_t)kPipeConsumers * q->pipe_rows * v;
   const StaticEntry *e = find_static(plan, vec16);
   const int rows = e ? e->rows : kRows;
   return (int64_t)kBlock * rows * v;
@@ -349,7 +365,7 @@ int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t
   const bool reduce = (plan->flags & NL_PLAN_HAS_REDUCE) != 0;
   const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
   if (name && name_len) {
-    if (sname) snprintf(name, name_len, "pipeline_kernel<%s,V=%d,static:%s>", dt_name(plan->dtype), v, sname);
+    if (sname) snprintf(name, name_len, "pipeline_kernel<%s,V=%d,%s%s>", dt_name(plan->dtype), v, strncmp(sname, "family:", 7) ? "static:" : "", sname);
     else snprintf(name, name_len, "pipeline_kernel<%s,V=%d,compact=%d,reduce=%d,dynamic%s>", dt_name(plan->dtype), v, (int)compact, (int)reduce,
                   plan->n_temps > 0 ? "" : "-light");
   }
@@ -392,15 +408,16 @@ static int launch_compact_super(const nl_plan *plan, const KParams &kp, int sm_c
   if (grid > kp.n_tiles) grid = kp.n_tiles;
   if (grid < 1) grid = 1;
   KParams kq = kp;
-  // the fourth wave of CTAs (hardware places CTA b on SM b mod #SMs) may retire on dense input
-  kq.super_drop_from = (bps >= 4 && grid == (int64_t)sm_count * bps) ? 3 * sm_count : 0x7fffffff;
+  // on dense input every SM keeps three resident CTAs: whichever started fourth on its SM (counted per %smid by
+  // the kernel itself — no assumption about how the hardware places CTAs) retires
+  kq.super_keep_ctas = (bps >= 4 && grid == (int64_t)sm_count * bps) ? 3 : 0x7fffffff;
   fn<<<(unsigned)grid, kBlock, 0, (cudaStream_t)stream>>>(kq);
   CUDA_TRY(cudaGetLastError());
   count_launch();
   if (info) {
     const int v = (int)(16 / nl_dtype_size(plan->dtype));
     snprintf(info->kernel, sizeof(info->kernel), "compact_super_kernel<%s,V=%d,U=%d,K=%d,%s%s>", dt_name(plan->dtype), v, kp.super_rows, kp.super_k,
-             is_static ? "static:" : (plan->n_temps > 0 ? "dynamic" : "dynamic-light"), is_static ? e->name : "");
+             is_static ? (strncmp(e->name, "family:", 7) ? "static:" : "") : (plan->n_temps > 0 ? "dynamic" : "dynamic-light"), is_static ? e->name : "");
     info->grid = (int)grid;
     info->block = kBlock;
     info->vec_elems = v;

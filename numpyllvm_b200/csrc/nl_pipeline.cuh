@@ -37,6 +37,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "nl_internal.h"
 #include "nl_step.h"
 
@@ -533,8 +535,39 @@ struct Tile {
   __device__ __forceinline__ T scalar_of(const KParams &p, uint32_t src) const {
     return (p.in_kind[src] == NL_IN_SCALAR_IMM) ? from_bits<T>(p.imm[src]) : *reinterpret_cast<const T *>(p.in[src]);
   }
-  template <class X>
+  // kInlineOnly (shape families): the operator is a run-time field, floor division never reaches here
+  // (family_step_ok) — its out-of-line sequence would cost every family kernel registers for nothing
+  template <bool kInlineOnly = false, class X>
   __device__ __forceinline__ void bin_apply(uint32_t vop, X x) {
+    if constexpr (kInlineOnly) {
+      switch (vop) {
+        case V_MUL:
+#pragma unroll
+          for (int e = 0; e < E; e++) acc[e] = op_mul<T>(acc[e], x(e));
+          break;
+        case V_ADD:
+#pragma unroll
+          for (int e = 0; e < E; e++) acc[e] = op_add<T>(acc[e], x(e));
+          break;
+        case V_SUB:
+#pragma unroll
+          for (int e = 0; e < E; e++) acc[e] = op_sub<T>(acc[e], x(e));
+          break;
+        case V_RSUB:
+#pragma unroll
+          for (int e = 0; e < E; e++) acc[e] = op_sub<T>(x(e), acc[e]);
+          break;
+        case V_DIV:
+#pragma unroll
+          for (int e = 0; e < E; e++) acc[e] = op_div<T>(acc[e], x(e));
+          break;
+        default:
+#pragma unroll
+          for (int e = 0; e < E; e++) acc[e] = op_div<T>(x(e), acc[e]);
+          break;
+      }
+      return;
+    }
     switch (vop) {
       case V_MUL:
 #pragma unroll
@@ -606,7 +639,10 @@ struct Tile {
   // StaticProg driver — everything but the selected case folds away.
   // kValuesOnly (phase B of the staged compaction pipeline): the keep mask is already known, so
   // steps that only produce predicates are skipped.
-  template <bool kValuesOnly = false>
+  // kOperand (shape families): the BIN / CMP operand is known to be a scalar (FK_SCALAR) or a column
+  // (FK_COLUMN) at build time — a scalar-only step then carries no second register set; FK_EITHER decides
+  // at run time like the interpreter
+  template <bool kValuesOnly = false, bool kInlineOnly = false, uint32_t kOperand = FK_EITHER>
   __device__ __forceinline__ void exec(const KParams &p, TileShared &sh, uint32_t op, uint32_t a, uint32_t b,
                                        int lane, int warp) {
     switch (op) {
@@ -636,18 +672,18 @@ struct Tile {
       case S_BIN:
         // a scalar operand is used straight from its (uniform) register: broadcasting it into E
         // registers first cost 16 moves per step
-        if (is_scalar(p, b)) {
+        if (kOperand == FK_SCALAR || (kOperand == FK_EITHER && is_scalar(p, b))) {
           const T sc = scalar_of(p, b);
-          bin_apply(a, [&](int) { return sc; });
+          bin_apply<kInlineOnly>(a, [&](int) { return sc; });
         } else {
           T x[E];
           fetch(p, b, x);
-          bin_apply(a, [&](int e) { return x[e]; });
+          bin_apply<kInlineOnly>(a, [&](int e) { return x[e]; });
         }
         break;
       case S_CMP:
         if constexpr (!kValuesOnly) {
-          if (is_scalar(p, b)) {
+          if (kOperand == FK_SCALAR || (kOperand == FK_EITHER && is_scalar(p, b))) {
             const T sc = scalar_of(p, b);
             pacc = cmp_apply(a, [&](int) { return sc; });
           } else {
@@ -826,6 +862,7 @@ struct Tile {
 template <bool kUsesTemps>
 struct DynProgT {
   static constexpr bool is_static = false;
+  static constexpr int min_blocks_stream = 1;
   static constexpr bool uses_temps = kUsesTemps;
   template <class TileT>
   static __device__ __forceinline__ void run(TileT &t, const KParams &p, TileShared &sh, int lane, int warp) {
@@ -843,23 +880,75 @@ template <uint32_t... S>
 struct StaticProg {
   static constexpr bool is_static = true;
   static constexpr bool uses_temps = true;
+  static constexpr int min_blocks_stream = 1;        // resident CTAs per SM the register allocation must allow (non-compaction)
   static constexpr int n_steps = sizeof...(S);
   template <class TileT>
   static __device__ __forceinline__ void run(TileT &t, const KParams &p, TileShared &sh, int lane, int warp) {
     (t.exec(p, sh, step_op(S), step_a(S), step_b(S), lane, warp), ...);
   }
-  static bool matches(const uint32_t *steps, int n) {
+  static bool matches(const nl_plan *plan) {
     constexpr uint32_t mine[] = {S...};
-    if (n != n_steps) return false;
-    for (int i = 0; i < n; i++)
-      if (steps[i] != mine[i]) return false;
+    if (plan->n_steps != n_steps) return false;
+    for (int i = 0; i < n_steps; i++)
+      if (plan->step[i] != mine[i]) return false;
+    return true;
+  }
+};
+
+// A shape FAMILY (nl_step.h: family_key): the step kinds, temporaries and stores are template
+// arguments like StaticProg's, while operators and input indices are read from the launch's own step
+// words — one build-time kernel for every expression of the same shape.
+template <uint32_t... K>
+struct FamilyProg {
+  static constexpr bool is_static = true;
+  // an "either" operand keeps a column-sized register set in reserve at every step: cap the allocation so that
+  // two CTAs stay resident (the exact shapes need 84 registers for the same rows)
+  static constexpr int min_blocks_stream = 2;
+  static constexpr int n_steps = sizeof...(K);
+  static constexpr bool uses_temps = ((step_op(K) == S_SAVE) || ...);
+  NL_HD static constexpr uint32_t key_at(int i) {
+    constexpr uint32_t k[] = {K...};
+    return k[i];
+  }
+  template <int I, bool kValuesOnly, class TileT>
+  static __device__ __forceinline__ void step(TileT &t, const KParams &p, TileShared &sh, int lane, int warp) {
+    constexpr uint32_t k = key_at(I);
+    constexpr uint32_t op = step_op(k);
+    const uint32_t s = p.step[I];                    // this launch's operators and inputs
+    uint32_t a = step_a(k), b = step_b(k);
+    if constexpr (op == S_LOAD || op == S_PLOAD || op == S_REDUCE || op == S_PBIN) a = step_a(s);
+    if constexpr ((op == S_BIN || op == S_CMP) && !(step_b(k) & SRC_TEMP)) {
+      a = step_a(s);
+      b = step_b(s);
+      t.template exec<kValuesOnly, true, step_b(k)>(p, sh, op, a, b, lane, warp);      // scalar / column / either: from the key
+    } else {
+      if constexpr (op == S_BIN || op == S_CMP) a = step_a(s);
+      t.template exec<kValuesOnly, true>(p, sh, op, a, b, lane, warp);
+    }
+  }
+  template <class TileT, size_t... I>
+  static __device__ __forceinline__ void run_seq(TileT &t, const KParams &p, TileShared &sh, int lane, int warp, std::index_sequence<I...>) {
+    (step<(int)I, false>(t, p, sh, lane, warp), ...);
+  }
+  template <class TileT>
+  static __device__ __forceinline__ void run(TileT &t, const KParams &p, TileShared &sh, int lane, int warp) {
+    run_seq(t, p, sh, lane, warp, std::make_index_sequence<n_steps>{});
+  }
+  static bool matches(const nl_plan *plan) {
+    constexpr uint32_t mine[] = {K...};
+    if (plan->n_steps != n_steps) return false;
+    for (int i = 0; i < n_steps; i++) {
+      const uint32_t s = plan->step[i], op = step_op(s);
+      const bool column = (op == S_BIN || op == S_CMP) && !(step_b(s) & SRC_TEMP) && plan->in[step_b(s)].kind == NL_IN_ARRAY;
+      if (!family_key_fits(family_key(s, column), mine[i]) || !family_step_ok(s)) return false;
+    }
     return true;
   }
 };
 
 // ------------------------------------------------------------------ the kernel
 template <typename T, int V, int U, bool kCompact, bool kReduce, class Prog>
-__global__ void __launch_bounds__(kBlock, Prog::is_static ? (kCompact ? kMinBlocksCompact : 1) : (Prog::uses_temps ? kMinBlocks : kMinBlocksLight))
+__global__ void __launch_bounds__(kBlock, Prog::is_static ? (kCompact ? kMinBlocksCompact : Prog::min_blocks_stream) : (Prog::uses_temps ? kMinBlocks : kMinBlocksLight))
 pipeline_kernel(const __grid_constant__ KParams p) {
   using TileT = Tile<T, V, U, kCompact, kReduce, kBlock, false, Prog::uses_temps>;
   using Tr = TT<T>;
@@ -988,7 +1077,7 @@ typedef void (*pipeline_fn)(const KParams);
 
 struct StaticEntry {
   const char *name;
-  bool (*matches)(const uint32_t *steps, int n);
+  bool (*matches)(const nl_plan *plan);
   int dtype;
   bool vec16;
   int rows;            // U of the instantiation: rows per thread per tile
@@ -1021,5 +1110,14 @@ const StaticEntry *static_table_i32_b(int *n);
 const StaticEntry *static_table_i64_b(int *n);
 const StaticEntry *static_table_f32_b(int *n);
 const StaticEntry *static_table_f64_b(int *n);
+// shape families (nl_family.cuh), two halves per dtype, defined in nl_family_<dtype>[_b].cu
+const StaticEntry *family_table_i32(int *n);
+const StaticEntry *family_table_i64(int *n);
+const StaticEntry *family_table_f32(int *n);
+const StaticEntry *family_table_f64(int *n);
+const StaticEntry *family_table_i32_b(int *n);
+const StaticEntry *family_table_i64_b(int *n);
+const StaticEntry *family_table_f32_b(int *n);
+const StaticEntry *family_table_f64_b(int *n);
 
 }  // namespace nl

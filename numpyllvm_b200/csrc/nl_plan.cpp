@@ -344,10 +344,11 @@ int nl_plan_compile(const nl_expr_node *nodes, int n_nodes, const nl_input_desc 
   if (lw.rc != NL_OK) return lw.rc;
   if (nodes[root].output < 0) { set_error("pipeline root is not materialised"); return NL_ERR_INVALID; }
   lw.cache_budget = NL_MAX_TEMPS - lw.temps_needed(root);
-  // A plan that needs no value temporary for its own evaluation and has no filter runs on the
-  // light interpreter (three CTAs per SM): caching a twice-read column would be its only
-  // temporary and would cost that.  The second read of a row hits L1/L2.
-  if (lw.temps_needed(root) == 0 && !lw.has_filter_below[root]) lw.cache_budget = 0;
+  // A plan that needs no value temporary for its own evaluation stays without one: caching a
+  // twice-read column would be its only temporary, which costs the interpreter a resident CTA per SM
+  // and every compaction kernel half its rows per thread, while the second read of a row hits L1/L2
+  // (and the super-tile compaction kernel reads its rows a second time from L2 by design).
+  if (lw.temps_needed(root) == 0) lw.cache_budget = 0;
   if (lw.is_pred(root)) lw.gen_pred(root); else lw.gen_value(root);
   if (lw.rc != NL_OK) return lw.rc;
 

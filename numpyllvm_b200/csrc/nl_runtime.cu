@@ -32,7 +32,8 @@ constexpr size_t kRedTicketOff = 0;            // u32, self-resetting
 constexpr size_t kRedPartialsOff = 256;        // 8 B x kMaxGrid
 constexpr size_t kMaxGrid = 8192;
 constexpr size_t kTileTicketOff = kRedPartialsOff + 8 * kMaxGrid;   // u32, zeroed per compact launch
-constexpr size_t kTileDescOff = kTileTicketOff + 256;               // 8 B x n_tiles, zeroed per compact launch
+constexpr size_t kSmRankOff = kTileTicketOff + 256;                 // u32 x 256: CTAs that have started on each SM, zeroed per compact launch
+constexpr size_t kTileDescOff = kSmRankOff + 1024;                  // 8 B x n_tiles, zeroed per compact launch
 
 struct Scratch {
   char *base = nullptr;
@@ -485,7 +486,7 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
   }
   if (end == start) return launch_empty_range(d.stream[stream], plan, kp);
 
-  const int64_t tile = pipeline_tile_elems(plan, vec16, end - start, &kp);   // also selects the staged compaction pipeline
+  const int64_t tile = pipeline_tile_elems(plan, vec16, end - start, &kp, d.sm_count);   // also selects the staged compaction pipeline
   kp.n_tiles = (end - start + tile - 1) / tile;
   const bool compact = (plan->flags & NL_PLAN_HAS_COMPACT) != 0;
   const size_t need = kTileDescOff + (compact ? (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE : 0);
@@ -495,6 +496,7 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
   kp.red_ticket = (unsigned int *)(sb + kRedTicketOff);
   kp.red_partials = (unsigned long long *)(sb + kRedPartialsOff);
   kp.tile_ticket = (unsigned int *)(sb + kTileTicketOff);
+  kp.sm_rank = (unsigned int *)(sb + kSmRankOff);
   kp.tile_desc = (unsigned long long *)(sb + kTileDescOff);
   if (compact)
     CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE, d.stream[stream]));
@@ -807,14 +809,37 @@ int nl_plan_kernel(const nl_plan *plan, int vec16, char *name, size_t name_len, 
   return describe_pipeline_kernel(plan, vec16 != 0, name, name_len, is_static);
 }
 
-int nl_set_static_kernels(int enabled) {
-  set_static_kernels_enabled(enabled & 1);
-  set_compact_pipe_enabled((enabled & 2) ? 0 : 1);      // bit 1 set: keep compaction on the plain kernel
-  set_max_ctas_per_sm((enabled >> 8) & 0xf);                                 // bits 8..11: cap on CTAs per SM (tuning)
-  set_compact_pipe_side((enabled & 4) ? 0 : 1);
-  set_compact_pipe_dynamic((enabled & 8) ? 1 : 0);
-  set_compact_prefer_pipe((enabled & 16) ? 1 : 0);                           // bit 4 set: staged pipeline before the super-tile kernel (tuning/tests)                           // bit 3 set: interpreter-driven staged pipeline allowed (tests)                              // bit 2 set: no side buffers (tuning)
-  set_compact_pipe_lag((enabled >> 12) & 0xf);                              // bits 12..15: lag override (tuning)
+int nl_set_static_kernels(int mode) {
+  if (mode < 0 || mode > 2) { set_error("nl_set_static_kernels: mode must be 0 (interpreter only), 1 (all tiers) or 2 (families + interpreter)"); return NL_ERR_INVALID; }
+  set_static_kernels_enabled(mode);
+  return NL_OK;
+}
+
+int nl_tune(const char *key, int value) {
+  if (!key) { set_error("nl_tune: null key"); return NL_ERR_INVALID; }
+  if (!strcmp(key, "compact_kernel")) {
+    // 0: by size (super-tile kernel, then staged pipeline, then plain); 1: plain kernel only;
+    // 2: staged pipeline before the super-tile kernel
+    if (value < 0 || value > 2) { set_error("nl_tune(compact_kernel): 0, 1 or 2"); return NL_ERR_INVALID; }
+    set_compact_pipe_enabled(value == 1 ? 0 : 1);
+    set_compact_prefer_pipe(value == 2 ? 1 : 0);
+  } else if (!strcmp(key, "pipe_dynamic")) {
+    set_compact_pipe_dynamic(value ? 1 : 0);
+  } else if (!strcmp(key, "pipe_side_buffers")) {
+    set_compact_pipe_side(value ? 1 : 0);
+  } else if (!strcmp(key, "pipe_lag")) {
+    if (value < 0 || value > 15) { set_error("nl_tune(pipe_lag): 0 (default) .. 15"); return NL_ERR_INVALID; }
+    set_compact_pipe_lag(value);
+  } else if (!strcmp(key, "max_ctas_per_sm")) {
+    if (value < 0 || value > 32) { set_error("nl_tune(max_ctas_per_sm): 0 (occupancy) .. 32"); return NL_ERR_INVALID; }
+    set_max_ctas_per_sm(value);
+  } else if (!strcmp(key, "reset")) {
+    set_compact_pipe_enabled(1); set_compact_prefer_pipe(0); set_compact_pipe_dynamic(0); set_compact_pipe_side(1);
+    set_compact_pipe_lag(0); set_max_ctas_per_sm(0);
+  } else {
+    set_error("nl_tune: unknown key '%s'", key);
+    return NL_ERR_INVALID;
+  }
   return NL_OK;
 }
 

@@ -117,7 +117,7 @@ template <uint32_t... S> constexpr int rows_for() {
   X(reduce_min, sp::L(0), sp::R(R_MIN, 0))                                                                   \
   X(reduce_sum, sp::L(0), sp::R(R_SUM, 0))                                                                   \
   /* a[a * k >= s]   (Tests/filter.py:13 exactly) */                                                        \
-  X(filter_mul_ge, sp::L(0), sp::SV(1), sp::B(V_MUL, 1), sp::C(C_GE, 2), sp::F(), sp::LT(1), sp::ST(0, sp::COMPACT)) \
+  X(filter_mul_ge, sp::L(0), sp::B(V_MUL, 1), sp::C(C_GE, 2), sp::F(), sp::L(0), sp::ST(0, sp::COMPACT)) \
   NL_CMP_SHAPES(X, ge, C_GE)                                                                                \
   NL_CMP_SHAPES(X, gt, C_GT)
 

@@ -57,4 +57,56 @@ NL_HD constexpr inline uint32_t step_a(uint32_t s) { return (s >> 8) & 0xff; }
 NL_HD constexpr inline uint32_t step_b(uint32_t s) { return (s >> 16) & 0xff; }
 NL_HD constexpr inline uint32_t step_c(uint32_t s) { return (s >> 24) & 0xff; }
 
+// ---- shape families -------------------------------------------------------------------------
+// A build-time instantiated kernel does not have to fix WHICH operator a step applies or WHICH input
+// it reads — only what kind of step it is: the operator is a warp-uniform switch outside the element
+// loop and the input an index into the parameter block, neither costs anything at HBM rate.  The
+// family key of a step keeps the fields that shape the code (step kind, temporaries, output slot and
+// index space) and drops the ones that stay run-time parameters:
+//   LOAD / PLOAD     which input
+//   BIN / CMP        which operator; which input when the operand is not a temporary — but whether that
+//                    input is a scalar or a column IS part of the shape where registers are tight (a
+//                    column operand needs a second register set): FK_SCALAR / FK_COLUMN / FK_EITHER
+//   PBIN             and / or / xor
+//   REDUCE           max / min / sum
+// One family therefore serves `a[a > t]`, `a[a <= 3]`, ... and `(a*2+1)[a > t]`, `(a/3-1)[a != 0]`, ...
+enum FamilyOperand : uint32_t { FK_SCALAR = 0, FK_COLUMN = 1, FK_EITHER = 2 };
+// key of a plan's step; operand_is_column: the step's input operand (BIN / CMP, not a temporary) is an array
+NL_HD constexpr inline uint32_t family_key(uint32_t s, bool operand_is_column) {
+  switch (step_op(s)) {
+    case S_LOAD: case S_PLOAD: return make_step(step_op(s));
+    case S_BIN: case S_CMP:
+      return (step_b(s) & SRC_TEMP) ? make_step(step_op(s), 0, step_b(s)) : make_step(step_op(s), 0, operand_is_column ? FK_COLUMN : FK_SCALAR);
+    case S_PBIN: return make_step(S_PBIN, 0, step_b(s));
+    case S_REDUCE: return make_step(S_REDUCE, 0, step_b(s));
+    default: return s;
+  }
+}
+// does a plan step with key `have` fit the family's key `want`?
+NL_HD constexpr inline bool family_key_fits(uint32_t have, uint32_t want) {
+  if (have == want) return true;
+  const uint32_t op = step_op(want);
+  return (op == S_BIN || op == S_CMP) && step_op(have) == op && !(step_b(want) & SRC_TEMP) && !(step_b(have) & SRC_TEMP) &&
+         step_b(want) == FK_EITHER;
+}
+// operators a family kernel carries inline (floor division is a long out-of-line sequence: interpreter only)
+NL_HD constexpr inline bool family_step_ok(uint32_t s) {
+  return !(step_op(s) == S_BIN && (step_a(s) == V_FDIV || step_a(s) == V_RFDIV));
+}
+
+// Splitting a compaction plan at its filter into a count pass and a store pass (super-tile kernel): do
+// the steps BEFORE the filter have to run again in the store pass?  Only if a value they produce is
+// still used after it: the accumulator (the first step after the filter is not a load) or a temporary.
+NL_HD constexpr inline bool store_pass_needs_prefix(const uint32_t *steps, int n, int filter) {
+  if (filter + 1 >= n) return false;
+  const uint32_t first = step_op(steps[filter + 1]);
+  if (first != S_LOAD && first != S_LOADT) return true;
+  for (int i = filter + 1; i < n; i++) {
+    const uint32_t op = step_op(steps[i]);
+    if (op == S_LOADT) return true;
+    if ((op == S_BIN || op == S_CMP) && (step_b(steps[i]) & SRC_TEMP)) return true;
+  }
+  return false;
+}
+
 }  // namespace nl

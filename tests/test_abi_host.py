@@ -76,16 +76,28 @@ def steps_of(plan):
     return abi.dump_plan(plan).splitlines()
 
 
-def test_lowering_filter_caches_the_column():
-    # Tests/filter.py: a[a*2 >= 50] reads column a once and keeps it in a temporary
+def test_lowering_filter_takes_no_temporary_for_a_reread_column():
+    # Tests/filter.py: a[a*2 >= 50].  The column is needed before and after the filter; a plan that needs no
+    # value temporary for the expression itself does not take one to park the column (the re-read is an
+    # L1/L2 hit, and the super-tile compaction kernel re-reads its rows from L2 by design)
     e = Expr(np.int64)
     a = e.array()
     e.materialize(e.filter(a, e.ge(e.mul(e.ref(a), e.scalar(2)), e.scalar(50))))
     plan = abi.compile_plan(e)
     text = abi.dump_plan(plan)
     assert plan.flags == abi.PLAN_HAS_FILTER | abi.PLAN_HAS_COMPACT
-    assert text.count("acc = in0") == 1 and "out0[compact] = acc" in text
+    assert plan.n_temps == 0 and text.count("acc = in0") == 2 and "out0[compact] = acc" in text
     assert plan.out[0].index_space == abi.IDX_COMPACT
+    # a[a > t]: the accumulator still holds the column when the filter has run — one load
+    e = Expr(np.float64)
+    a = e.array()
+    e.materialize(e.filter(a, e.gt(e.ref(a), e.scalar(0.5))))
+    assert abi.dump_plan(abi.compile_plan(e)).count("acc = in0") == 1
+    # an expression that needs a temporary anyway may park a column in the other one
+    e = Expr(np.int64)
+    a, b = e.array(), e.array()
+    e.materialize(e.filter(e.add(e.mul(e.ref(a), b), e.mul(e.ref(a), e.ref(a))), e.gt(a, e.scalar(3))))
+    assert abi.compile_plan(e).n_temps >= 1
 
 
 def test_lowering_six_way_product_uses_one_temp():
@@ -204,15 +216,40 @@ def test_benchmark_shapes_resolve_to_build_time_kernels():
     assert kernel(e)[0].endswith("static:filter_mul_ge>")                               # Tests/filter.py
     e = Expr(np.int64); xa = e.array(); e.materialize(e.sum(e.filter(xa, e.ge(e.ref(xa), e.scalar(50)))))
     assert kernel(e)[0].endswith("static:filter_ge_sum>")                               # Tests/max.py
+    # second tier: shape FAMILIES (nl_family.cuh) — the step kinds are build-time, operators and inputs run-time
     e = Expr(np.int64); xa = e.array(); e.materialize(e.add(e.mul(xa, e.scalar(3)), e.scalar(1)))
+    assert kernel(e) == ("pipeline_kernel<i64,V=2,family:ew2>", True)                     # a*3 + 1
+    e = Expr(np.float64); xa, xb = e.array(), e.array(); e.materialize(e.sub(e.div(xa, xb), e.scalar(0.5)))
+    assert kernel(e)[0].endswith("family:ew2>")                                          # a/b - 0.5: same family, other operators
+    e = Expr(np.float32); a, b, c, d = (e.array() for _ in range(4)); e.materialize(e.add(e.mul(a, b), e.mul(c, d)))
+    assert kernel(e) == ("pipeline_kernel<f32,V=4,family:ew1x1>", True)                   # a*b + c*d
+    e = Expr(np.float64); xa = e.array()
+    e.materialize(e.filter(e.add(e.mul(xa, e.scalar(2.0)), e.scalar(1.0)), e.gt(e.ref(xa), e.scalar(0.9))))
+    assert kernel(e)[0].endswith("family:fc_v2>")                                        # (a*2+1)[a > t]: the accumulator still holds a
+    e = Expr(np.float64); xa, xb, xc = e.array(), e.array(), e.array()
+    e.materialize(e.filter(e.sub(xa, xb), e.ne(xc, e.scalar(0.0))))
+    assert kernel(e)[0].endswith("family:fc_l_v1c>")                                     # (a-b)[c != 0]: a COLUMN operand is part of the shape
+    e = Expr(np.int32); xa, xb = e.array(), e.array(); e.materialize(e.sum(e.mul(xa, xb)))
+    assert kernel(e)[0].endswith("family:red1>")                                         # (a*b).sum()
+    e = Expr(np.float32); xa = e.array()
+    e.materialize(e.min(e.add(e.filter(xa, e.lt(e.ref(xa), e.scalar(0.5))), e.scalar(1.0))))
+    assert kernel(e)[0].endswith("family:fr_v1>")                                        # (a[a < t] + 1).min()
+    # third tier, the step interpreter: floor division (a long out-of-line sequence no family carries) ...
+    e = Expr(np.int64); xa = e.array(); e.materialize(e.floordiv(xa, e.scalar(3)))
     name, is_static = kernel(e)
     assert not is_static and "dynamic" in name
-    # scalar rows (misaligned operands) always use the interpreter
+    # ... shapes outside the lists ...
+    e = Expr(np.float32); cols = [e.array() for _ in range(8)]
+    acc = cols[0]
+    for c in cols[1:]:
+        acc = e.add(acc, c)
+    e.materialize(acc)
+    assert kernel(e) == ("pipeline_kernel<f32,V=4,compact=0,reduce=0,dynamic-light>", False)
+    # ... and scalar rows (misaligned operands): the light variant when the plan has no value temporary, the general one otherwise
     e = Expr(np.float32); e.materialize(e.mul(e.array(), e.array()))
-    # ... the light variant when the plan has no value temporary, the general one otherwise
     assert abi.plan_kernel(abi.compile_plan(e), vec16=False) == ("pipeline_kernel<f32,V=1,compact=0,reduce=0,dynamic-light>", False)
     e = Expr(np.float32); a, b, c, d = (e.array() for _ in range(4)); e.materialize(e.add(e.mul(a, b), e.mul(c, d)))
-    assert abi.plan_kernel(abi.compile_plan(e), vec16=True) == ("pipeline_kernel<f32,V=4,compact=0,reduce=0,dynamic>", False)
+    assert abi.plan_kernel(abi.compile_plan(e), vec16=False) == ("pipeline_kernel<f32,V=1,compact=0,reduce=0,dynamic>", False)
     # a column read twice is not parked in a temporary when that would be the plan's only one
     e = Expr(np.float32); x = e.array(); e.materialize(e.mul(e.add(e.ref(x), e.scalar(np.float32(1))), e.ref(x)))
     assert abi.compile_plan(e).n_temps == 0

@@ -11,11 +11,10 @@ from numpyllvm_b200.device import Runtime, run_pipeline
 
 pytestmark = pytest.mark.gpu
 
-# flags of nl_set_static_kernels(): bit 0 = build-time shapes, bit 1 = keep compaction on the plain kernel
-# bit 0: build-time shapes, bit 1: plain kernel only, bit 3: interpreter-driven pipeline allowed,
-# bit 4: staged pipeline before the super-tile kernel
-MODES = {"pipe-static": 1 | 8 | 16, "pipe-dynamic": 0 | 8 | 16, "super-static": 1, "super-dynamic": 0,
-         "plain-static": 3, "plain-dynamic": 2}
+# (nl_set_static_kernels mode, nl_tune "compact_kernel", nl_tune "pipe_dynamic"): every compaction kernel under
+# exact build-time shapes (1), shape families (2) and the step interpreter (0)
+MODES = {"pipe-static": (1, 2, 1), "pipe-dynamic": (0, 2, 1), "super-static": (1, 0, 0), "super-family": (2, 0, 0),
+         "super-dynamic": (0, 0, 0), "plain-static": (1, 1, 0), "plain-family": (2, 1, 0), "plain-dynamic": (0, 1, 0)}
 
 
 @pytest.fixture(scope="module")
@@ -25,9 +24,13 @@ def rt(nl):
 
 @pytest.fixture(params=list(MODES))
 def mode(request, nl):
-    nl.nl_set_static_kernels(MODES[request.param])
+    tier, which, dyn_pipe = MODES[request.param]
+    nl.nl_set_static_kernels(tier)
+    nl.nl_tune(b"compact_kernel", which)
+    nl.nl_tune(b"pipe_dynamic", dyn_pipe)
     yield request.param
     nl.nl_set_static_kernels(1)
+    nl.nl_tune(b"reset", 0)
 
 
 def tile_elems(dtype):

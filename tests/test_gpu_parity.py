@@ -27,11 +27,12 @@ def rt(nl):
     return Runtime.get()
 
 
-@pytest.fixture(autouse=True, params=["static", "dynamic"])
+@pytest.fixture(autouse=True, params=["static", "family", "dynamic"])
 def driver(request, nl):
-    """Every case runs twice: with the build-time instantiated shapes (nl_static.cuh) where the
-    plan matches one, and with everything forced through the dynamic interpreter."""
-    nl.nl_set_static_kernels(1 if request.param == "static" else 0)
+    """Every case runs three times: with the build-time instantiated shapes (nl_static.cuh) where the
+    plan matches one, with the shape families (nl_family.cuh) where it matches one of those, and with
+    everything forced through the dynamic interpreter."""
+    nl.nl_set_static_kernels({"static": 1, "family": 2, "dynamic": 0}[request.param])
     yield request.param
     nl.nl_set_static_kernels(1)
 

@@ -89,10 +89,14 @@ def main():
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
-    ap.add_argument("--kernel-flags", type=int, default=1, help="nl_set_static_kernels() argument (tuning)")
+    ap.add_argument("--tier", type=int, default=1, help="nl_set_static_kernels(): 1 all tiers, 2 families + interpreter, 0 interpreter")
+    ap.add_argument("--tune", action="append", default=[], help="nl_tune key=value (repeatable), e.g. compact_kernel=1")
     args = ap.parse_args()
     rt = Runtime.get(1)
-    rt.lib.nl_set_static_kernels(args.kernel_flags)
+    rt.lib.nl_set_static_kernels(args.tier)
+    for kv in args.tune:
+        key, val = kv.split("=")
+        abi.check(rt.lib.nl_tune(key.encode(), int(val)))
     n = args.n or (1 << args.log2n)
     plan, outs, ins, nbytes, keep = build(args.config, rt, n)
     sizes = keep[-1]
