@@ -175,11 +175,14 @@ def run_gpu(args):
     from numpyllvm_b200.device import Runtime
     from numpyllvm_b200.dist import Ranks
 
-    # NCCL's own log stays on (the driver reads the ranks of the communicator from it) but goes to
-    # stderr: the JSON line is the only thing this arm may print on stdout
+    # NCCL's own log stays on (the driver reads the ranks of the communicator from it).  NCCL prints to
+    # the process's stdout, and the JSON line is the only thing this arm may print there: file descriptor 1
+    # is pointed at stderr for everything native, the line itself goes out through a private copy.
     os.environ.setdefault("NCCL_DEBUG", "INFO")
     os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ranks = Ranks(args.gpus)
     lib = abi.load_library()
     dev_ids = (C.c_int * 1)(ranks.local_rank)
@@ -329,7 +332,7 @@ def run_gpu(args):
             result["pipelines_error"] = f"{type(exc).__name__}: {exc}"
     sampler.stop()
     if ranks.rank == 0:
-        print(json.dumps(result), flush=True)
+        print(json.dumps(result), file=json_out, flush=True)
     ranks.finish()
 
 

@@ -378,6 +378,12 @@ NL_API int nl_comm_destroy(void);
 NL_API int nl_comm_mailbox_export(int dev, void *handle_out /*NL_MAILBOX_HANDLE_BYTES*/);
 NL_API int nl_comm_mailbox_import(const void *handles /*world_size x NL_MAILBOX_HANDLE_BYTES*/);
 NL_API int nl_comm_peer_ready(void);               /* 1 when the fused finish can be used */
+/* The rank on local device `dev` cannot take part in the next fused finish (its own error path): post an
+ * abort for that epoch into every peer's mailbox, so that kernels already waiting for this rank stop at
+ * once instead of running into the peer timeout; their next synchronisation returns NL_ERR_NCCL.  The
+ * library does the same by itself when a fused launch fails after its epoch was committed.  The
+ * communicator is unusable afterwards (nl_comm_destroy + nl_comm_init). */
+NL_API int nl_comm_abort(int dev);
 
 /* ======================= introspection ==================================== */
 /* Kernels launched by this library since load (the bench's gpu_launches). */
@@ -397,6 +403,8 @@ NL_API int nl_set_static_kernels(int mode);
  *   "pipe_side_buffers"  0: no side buffers in the staged pipeline (default 1)
  *   "pipe_lag"           tiles between count and store phase of the staged pipeline (0: half the ring)
  *   "max_ctas_per_sm"    cap on resident CTAs per SM of the streaming kernels (0: by occupancy)
+ *   "peer_timeout_ms"    how long a fused multi-GPU finish waits for a peer's mailbox slot before it gives up
+ *                        and the next synchronisation returns NL_ERR_NCCL (default 10000; 0: default)
  *   "reset"              all of the above back to their defaults (value ignored)
  * Unknown keys and out-of-range values return NL_ERR_INVALID. */
 NL_API int nl_tune(const char *key, int value);

@@ -241,6 +241,7 @@ _SIGNATURES = {
     "nl_comm_mailbox_export": (C.c_int, [C.c_int, _VP]),
     "nl_comm_mailbox_import": (C.c_int, [_VP]),
     "nl_comm_peer_ready": (C.c_int, []),
+    "nl_comm_abort": (C.c_int, [C.c_int]),
     "nl_plan_kernel": (C.c_int, [C.POINTER(Plan), C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]),
     "nl_set_static_kernels": (C.c_int, [C.c_int]),
     "nl_tune": (C.c_int, [C.c_char_p, C.c_int]),

@@ -28,6 +28,20 @@ static int64_t *sizes_buffer(int dev) {
   return g_sizes[dev] + g_sizes_slot[dev] * NL_MAX_OUTPUTS;
 }
 
+// per-device scratch for the exclusive scan of the shard counts a fused filter leaves behind (world + 1 entries)
+static int64_t *g_offsets[NL_MAX_DEVICES];
+static int g_offsets_slot[NL_MAX_DEVICES];
+
+static int64_t *offsets_buffer(int dev) {
+  if (!g_offsets[dev]) {
+    void *p = NULL;
+    if (nl_malloc(dev, sizeof(int64_t) * (NL_MAX_DEVICES + 1) * kSizeSlots, &p) != NL_OK) return NULL;
+    g_offsets[dev] = (int64_t *)p;
+  }
+  g_offsets_slot[dev] = (g_offsets_slot[dev] + 1) % kSizeSlots;
+  return g_offsets[dev] + g_offsets_slot[dev] * (NL_MAX_DEVICES + 1);
+}
+
 static std::vector<PyThunkObject *> g_pending_cuts;
 
 // the reference blocks on a semaphore while holding the GIL (thunk.cpp:106); here the GIL is released
@@ -236,7 +250,12 @@ static int execute_one(Pipeline *pipeline) {
 
   // one launch per device shard (the reference's 8 range tasks, scheduler.cpp:133-147)
   const bool fused_finish = G > 1 && (lp.plan.flags & NL_PLAN_HAS_REDUCE) && nl_comm_peer_ready();
+  // a filter over several GPUs exchanges its shard counts inside the kernel too: every device ends up with
+  // the exclusive scan of all counts (the memmove gather of compiler.cpp:36-48 as offsets), so the host reads
+  // ONE small vector from ONE device instead of a count from each
+  const bool fused_counts = G > 1 && (lp.plan.flags & NL_PLAN_HAS_COMPACT) && !(lp.plan.flags & NL_PLAN_HAS_REDUCE) && nl_comm_peer_ready();
   std::vector<int64_t *> sizes(G, (int64_t *)NULL);
+  std::vector<int64_t *> offsets(G, (int64_t *)NULL);
   for (int g = 0; g < G; g++) {
     void *out_ptrs[NL_MAX_OUTPUTS] = {0};
     const void *in_ptrs[NL_MAX_INPUTS] = {0};
@@ -299,9 +318,13 @@ static int execute_one(Pipeline *pipeline) {
     }
     // a reduction over several GPUs finishes inside its kernel: the partials travel through the
     // peers' NVLink mailboxes, no collective launch follows
-    int rc = fused_finish
-                 ? nl_launch_pipeline_allreduce(&lp.plan, out_ptrs, in_ptrs, 0, count, sizes[g], g)
-                 : nl_launch_pipeline(&lp.plan, out_ptrs, in_ptrs, 0, count, sizes[g], 0, g, 0);
+    if (fused_counts) {
+      offsets[g] = offsets_buffer(g);
+      if (!offsets[g]) { nljit_raise(NL_ERR_NOMEM, "jit: scratch allocation failed"); return fail(); }
+    }
+    int rc = fused_finish   ? nl_launch_pipeline_allreduce(&lp.plan, out_ptrs, in_ptrs, 0, count, sizes[g], g)
+             : fused_counts ? nl_launch_pipeline_allgather(&lp.plan, out_ptrs, in_ptrs, 0, count, sizes[g], offsets[g], g)
+                            : nl_launch_pipeline(&lp.plan, out_ptrs, in_ptrs, 0, count, sizes[g], 0, g, 0);
     if (rc != NL_OK) { nljit_raise(rc, "jit: pipeline launch failed"); return fail(); }
   }
 
@@ -319,7 +342,16 @@ static int execute_one(Pipeline *pipeline) {
       need_counts = true;
     }
   }
-  if (need_counts) {
+  if (need_counts && fused_counts) {
+    // the kernels exchanged the counts among themselves: device 0 holds the scan of all of them
+    int64_t host[NL_MAX_DEVICES + 1] = {0};
+    int rc = nl_memcpy_d2h(0, 0, host, offsets[0], sizeof(int64_t) * (size_t)(G + 1));
+    if (rc == NL_OK) { Py_BEGIN_ALLOW_THREADS rc = nl_stream_sync(0, 0); Py_END_ALLOW_THREADS }
+    if (rc != NL_OK) { nljit_raise(rc, "jit: count read-back failed"); return fail(); }
+    for (int k = 0; k < lp.n_outputs; k++)
+      if (lp.plan.out[k].index_space == NL_IDX_COMPACT)
+        for (int g = 0; g < G; g++) outs[k]->shards[g].count = host[g + 1] - host[g];
+  } else if (need_counts) {
     // the shard counts are what the memmove gather of compiler.cpp:36-48 becomes: each shard's
     // run starts at the exclusive scan of the counts before it
     std::vector<int64_t> host((size_t)G * NL_MAX_OUTPUTS, 0);

@@ -49,6 +49,8 @@ struct KParams {
   int32_t peer_world, peer_rank;
   unsigned long long peer_epoch;      // > 0, the same on every rank for one reduction
   long long *peer_offsets;            // filters: exclusive scan of every rank's count, peer_world + 1 entries (or NULL)
+  unsigned long long peer_timeout_ns; // bound on every wait for a peer's slot
+  unsigned long long *peer_status;    // pinned host word of this device, raised when an exchange was given up
 };
 
 // geometry of the pipeline kernel

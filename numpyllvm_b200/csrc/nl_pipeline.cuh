@@ -216,6 +216,42 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
   return v;
 }
 
+// A wait on a peer is BOUNDED: a rank whose launch failed (or never came) must not hang the other
+// seven kernels.  Every mailbox ends in an abort word; the waiter gives up when it reads an abort for
+// this epoch (or an earlier one) or when peer_timeout_ns have passed, posts the abort to every peer
+// itself — so they stop, too — and raises the device's status word in pinned host memory, which the
+// host turns into NL_ERR_NCCL at its next synchronisation (nl_runtime.cu: check_peer_status).
+constexpr int kMailboxAbortIdx = 2 * 256 * 2;       // u64 index of the abort word: behind [2 parities][256 ranks][value, epoch]
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void peer_give_up(const KParams &p, int waiting_for) {
+  for (int dst = 0; dst < p.peer_world; dst++) st_release_sys_u64(p.peer_box[dst] + kMailboxAbortIdx, p.peer_epoch);
+  if (p.peer_status) {
+    st_relaxed_sys_u64(p.peer_status, (p.peer_epoch & 0xffffffffffffull) | ((unsigned long long)(waiting_for + 1) << 48));
+    __threadfence_system();
+  }
+}
+// lane 0 of the exchanging warp: wait until `flag` carries this launch's epoch; false: aborted / timed out
+__device__ __forceinline__ bool peer_wait(const KParams &p, const unsigned long long *flag, int src) {
+  unsigned int spins = 0;
+  unsigned long long t0 = 0;
+  while (ld_acquire_sys_u64(flag) != p.peer_epoch) {
+    if ((++spins & 255u) == 0) {
+      const unsigned long long ab = ld_relaxed_sys_u64(p.peer_box[p.peer_rank] + kMailboxAbortIdx);
+      const unsigned long long now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      if ((ab != 0 && ab <= p.peer_epoch) || now - t0 > p.peer_timeout_ns) {
+        peer_give_up(p, src);
+        return false;
+      }
+    }
+  }
+  return true;
+}
+
 // Called by ONE warp (all 32 lanes); `mine` = this GPU's result as accumulator bits (Acc for
 // sums, T for max/min).  Returns the global result bits in every lane.
 template <typename T>
@@ -235,11 +271,12 @@ __device__ __forceinline__ unsigned long long peer_allreduce(const KParams &p, u
   T ev = (rop == R_MIN) ? Tr::highest() : Tr::lowest();
   for (int src = 0; src < W; src++) {                     // rank order: deterministic, identical everywhere
     unsigned long long bits = 0;
+    int ok = 1;
     if (lane == 0) {
-      while (ld_acquire_sys_u64(own + (size_t)src * 2 + 1) != epoch) {
-      }
+      ok = peer_wait(p, own + (size_t)src * 2 + 1, src) ? 1 : 0;
       bits = ld_relaxed_sys_u64(own + (size_t)src * 2);
     }
+    if (!__shfl_sync(0xffffffffu, ok, 0)) break;           // aborted: the host reports NL_ERR_NCCL, the value is void
     bits = __shfl_sync(0xffffffffu, bits, 0);
     if (rop == R_SUM) sv = acc_add(sv, from_bits<Acc>(bits));
     else if (rop == R_MAX) ev = op_max<T>(ev, from_bits<T>(bits));
@@ -264,8 +301,7 @@ __device__ __forceinline__ void peer_scan_counts(const KParams &p, unsigned long
     const unsigned long long *own = p.peer_box[r] + par_off;
     long long run = 0;
     for (int src = 0; src < W; src++) {
-      while (ld_acquire_sys_u64(own + (size_t)src * 2 + 1) != epoch) {
-      }
+      if (!peer_wait(p, own + (size_t)src * 2 + 1, src)) break;      // aborted: the host reports NL_ERR_NCCL
       p.peer_offsets[src] = run;
       run += (long long)ld_relaxed_sys_u64(own + (size_t)src * 2);
     }

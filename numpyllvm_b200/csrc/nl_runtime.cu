@@ -51,10 +51,14 @@ struct Device {
   unsigned long long *box = nullptr;          // cudaMalloc (IPC-exportable), kMailboxBytes, zeroed
   unsigned long long **box_table = nullptr;   // device array [world]
   unsigned long long epoch = 0;               // fused reductions launched on this device so far
+  unsigned long long *box_host_table[256] = {nullptr};   // host copy of box_table (to post an abort from the host)
+  unsigned long long *status = nullptr;       // pinned host word (device-mapped): raised by a kernel that gave up on a peer
 };
 
 constexpr int kMaxWorld = 256;
-constexpr size_t kMailboxBytes = 2 * (size_t)kMaxWorld * 16;   // [2 parities][world][value, epoch]
+constexpr size_t kMailboxBytes = 2 * (size_t)kMaxWorld * 16 + 64;   // [2 parities][world][value, epoch] + the abort word (nl_pipeline.cuh: kMailboxAbortIdx)
+static unsigned long long g_peer_timeout_ns = 10ull * 1000 * 1000 * 1000;   // bound on a kernel's wait for a peer (nl_tune "peer_timeout_ms")
+void set_peer_timeout_ms(int ms) { g_peer_timeout_ns = (unsigned long long)(ms > 0 ? ms : 10000) * 1000ull * 1000ull; }
 static bool g_peer_ready = false;
 static void *g_ipc_mapped[NL_MAX_DEVICES][kMaxWorld];          // IPC mappings to close at destroy
 
@@ -72,6 +76,17 @@ static int check_dev(int dev, int stream) {
   if (dev < 0 || dev >= g_ndev) { set_error("device index %d out of range (0..%d)", dev, g_ndev - 1); return NL_ERR_INVALID; }
   if (stream < 0 || stream >= NL_N_STREAMS) { set_error("stream index %d out of range", stream); return NL_ERR_INVALID; }
   return NL_OK;
+}
+
+// a kernel that gave up waiting for a peer's mailbox slot (peer_give_up) left a note: report it once
+static int check_peer_status(Device &d) {
+  if (!d.status || *(volatile unsigned long long *)d.status == 0) return NL_OK;
+  const unsigned long long v = *(volatile unsigned long long *)d.status;
+  *(volatile unsigned long long *)d.status = 0;
+  set_error("fused multi-GPU finish given up on device %d: epoch %llu, rank %d did not post its slot (its launch failed, it aborted, or it "
+            "took longer than the peer timeout); the result of that launch is void — destroy and re-create the communicator",
+            d.id, v & 0xffffffffffffull, (int)(v >> 48) - 1);
+  return NL_ERR_NCCL;
 }
 
 static int ensure_scratch(Device &d, int stream, size_t need) {
@@ -194,6 +209,7 @@ int nl_init(int n_devices, const int *device_ids) {
 
 int nl_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
+  nl_comm_destroy();          // communicator, IPC mappings, mailboxes and epochs: nothing stale survives into a later nl_init
   for (int d = 0; d < g_ndev; d++) {
     Device &dv = g_dev[d];
     cudaSetDevice(dv.id);
@@ -329,7 +345,7 @@ int nl_stream_sync(int dev, int stream) {
   int rc = check_dev(dev, stream);
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(g_dev[dev].stream[stream]));
-  return NL_OK;
+  return check_peer_status(g_dev[dev]);
 }
 
 int nl_device_sync(int dev) {
@@ -337,7 +353,7 @@ int nl_device_sync(int dev) {
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
   CUDA_TRY(cudaDeviceSynchronize());
-  return NL_OK;
+  return check_peer_status(g_dev[dev]);
 }
 
 int nl_stream_wait(int dev, int waiter, int signaler_dev, int signaler) {
@@ -425,6 +441,16 @@ int nl_event_elapsed_ms(nl_event start, nl_event stop, float *ms_out) {
 }
 
 // ======================================================================= hot path
+// this rank cannot take part in epoch `epoch` after all: tell every peer's mailbox (their kernels poll the word)
+static void post_abort(Device &d, unsigned long long epoch) {
+  cudaSetDevice(d.id);
+  for (int r = 0; r < g_world; r++)
+    if (d.box_host_table[r])
+      cudaMemcpyAsync(d.box_host_table[r] + 2 * kMaxWorld * 2, &epoch, sizeof(epoch), cudaMemcpyHostToDevice, d.stream[2]);
+  cudaStreamSynchronize(d.stream[2]);
+  cudaGetLastError();
+}
+
 static int launch_impl(const nl_plan *plan, void *const *outputs, const void *const *inputs, int64_t start, int64_t end,
                        int64_t *output_sizes, int thread_nr, int dev, int stream, bool fuse_finish, int64_t *peer_offsets = nullptr) {
   int rc = check_dev(dev, stream);
@@ -477,14 +503,23 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
     if (step_op(plan->step[i]) == S_REDUCE) { kp.reduce_rop = (int32_t)step_a(plan->step[i]); kp.reduce_out = (int32_t)step_b(plan->step[i]); }
 
   if (fuse_finish) {
-    // every rank launches the same sequence of fused reductions: the per-device counter is the epoch
+    // every rank launches the same sequence of fused reductions: the per-device counter is the epoch.  It is
+    // committed (d.epoch) only when the launch is certain — scratch allocated, kernel selected —, and a launch that
+    // still fails after that posts an abort for the epoch so that the peers' kernels stop waiting for this rank.
     kp.peer_box = d.box_table;
     kp.peer_world = g_world;
     kp.peer_rank = g_first_rank + dev;
-    kp.peer_epoch = ++d.epoch;
+    kp.peer_epoch = d.epoch + 1;
     kp.peer_offsets = (long long *)peer_offsets;
+    kp.peer_timeout_ns = g_peer_timeout_ns;
+    kp.peer_status = d.status;
   }
-  if (end == start) return launch_empty_range(d.stream[stream], plan, kp);
+  if (end == start) {
+    if (fuse_finish) d.epoch++;
+    rc = launch_empty_range(d.stream[stream], plan, kp);
+    if (rc != NL_OK && fuse_finish) post_abort(d, kp.peer_epoch);
+    return rc;
+  }
 
   const int64_t tile = pipeline_tile_elems(plan, vec16, end - start, &kp, d.sm_count);   // also selects the staged compaction pipeline
   kp.n_tiles = (end - start + tile - 1) / tile;
@@ -502,8 +537,10 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
     CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE, d.stream[stream]));
 
   LaunchInfo info;
+  if (fuse_finish) d.epoch++;
   rc = launch_pipeline_kernel(plan, kp, vec16, d.sm_count, d.stream[stream], &info);
   if (rc == NL_OK) g_last_info = info;
+  else if (fuse_finish) post_abort(d, kp.peer_epoch);
   return rc;
 }
 
@@ -637,6 +674,10 @@ static int ensure_mailbox(int d) {
     CUDA_TRY(cudaMemset(dv.box, 0, kMailboxBytes));
   }
   if (!dv.box_table) CUDA_TRY(cudaMalloc((void **)&dv.box_table, sizeof(unsigned long long *) * kMaxWorld));
+  if (!dv.status) {
+    CUDA_TRY(cudaHostAlloc((void **)&dv.status, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    *dv.status = 0;
+  }
   return NL_OK;
 }
 
@@ -679,6 +720,7 @@ static int setup_local_mailboxes() {
   for (int d = 0; d < g_ndev; d++) {
     CUDA_TRY(cudaSetDevice(g_dev[d].id));
     CUDA_TRY(cudaMemcpy(g_dev[d].box_table, table, sizeof(table[0]) * (size_t)g_ndev, cudaMemcpyHostToDevice));
+    memcpy(g_dev[d].box_host_table, table, sizeof(table));
     g_dev[d].epoch = 0;
   }
   g_peer_ready = true;
@@ -686,6 +728,14 @@ static int setup_local_mailboxes() {
 }
 
 int nl_comm_peer_ready(void) { return g_peer_ready ? 1 : 0; }
+
+int nl_comm_abort(int dev) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  if (!g_peer_ready) { set_error("nl_comm_abort: no peer mailboxes"); return NL_ERR_NCCL; }
+  post_abort(g_dev[dev], g_dev[dev].epoch + 1);
+  return NL_OK;
+}
 
 int nl_comm_mailbox_export(int dev, void *handle_out) {
   int rc = check_dev(dev, 0);
@@ -704,6 +754,9 @@ int nl_comm_mailbox_export(int dev, void *handle_out) {
 int nl_comm_mailbox_import(const void *handles) {
   if (!handles) { set_error("nl_comm_mailbox_import: null"); return NL_ERR_INVALID; }
   if (!g_world || g_world > kMaxWorld) { set_error("nl_comm_mailbox_import before nl_comm_init"); return NL_ERR_NCCL; }
+  // importing twice would restart the epochs over mailboxes that still hold the old ones (a slot left at epoch 1
+  // would satisfy the first wait at once): a communicator is set up once, nl_comm_destroy() gives fresh mailboxes
+  if (g_peer_ready) { set_error("nl_comm_mailbox_import: the mailboxes are already set up (nl_comm_destroy first)"); return NL_ERR_INVALID; }
   const char *hb = (const char *)handles;
   for (int d = 0; d < g_ndev; d++) {
     int rc = ensure_mailbox(d);
@@ -733,6 +786,7 @@ int nl_comm_mailbox_import(const void *handles) {
     }
     CUDA_TRY(cudaSetDevice(g_dev[d].id));
     CUDA_TRY(cudaMemcpy(g_dev[d].box_table, table, sizeof(table[0]) * (size_t)g_world, cudaMemcpyHostToDevice));
+    memcpy(g_dev[d].box_host_table, table, sizeof(table));
     g_dev[d].epoch = 0;
   }
   g_peer_ready = true;
@@ -751,6 +805,8 @@ int nl_comm_destroy(void) {
       if (g_ipc_mapped[d][r]) { cudaIpcCloseMemHandle(g_ipc_mapped[d][r]); g_ipc_mapped[d][r] = nullptr; }
     if (g_dev[d].box) { cudaFree(g_dev[d].box); g_dev[d].box = nullptr; }
     if (g_dev[d].box_table) { cudaFree(g_dev[d].box_table); g_dev[d].box_table = nullptr; }
+    if (g_dev[d].status) { cudaFreeHost(g_dev[d].status); g_dev[d].status = nullptr; }
+    memset(g_dev[d].box_host_table, 0, sizeof(g_dev[d].box_host_table));
     g_dev[d].epoch = 0;
   }
   g_world = 0;
@@ -833,7 +889,10 @@ int nl_tune(const char *key, int value) {
   } else if (!strcmp(key, "max_ctas_per_sm")) {
     if (value < 0 || value > 32) { set_error("nl_tune(max_ctas_per_sm): 0 (occupancy) .. 32"); return NL_ERR_INVALID; }
     set_max_ctas_per_sm(value);
+  } else if (!strcmp(key, "peer_timeout_ms")) {
+    set_peer_timeout_ms(value);
   } else if (!strcmp(key, "reset")) {
+    set_peer_timeout_ms(0);
     set_compact_pipe_enabled(1); set_compact_prefer_pipe(0); set_compact_pipe_dynamic(0); set_compact_pipe_side(1);
     set_compact_pipe_lag(0); set_max_ctas_per_sm(0);
   } else {
