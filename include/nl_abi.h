@@ -222,6 +222,19 @@ NL_API int nl_device_count(void);                  /* local devices after nl_ini
 NL_API int nl_device_info(int dev, char *name, size_t name_len, int *sm_count,
                    int *cc_major, int *cc_minor, size_t *total_mem);
 
+NL_API int nl_device_cuda_id(int dev);              /* CUDA ordinal of local device `dev` (DLPack / __cuda_array_interface__ consumers) */
+
+/* CUDA graphs: everything enqueued on (dev, stream 0) between nl_graph_begin and nl_graph_end — pipeline
+ * launches, assignments, fills on FIXED buffers — is captured instead of run and can then be replayed
+ * with one call (small pipelines are launch-bound: the reference's per-pipeline JIT cost has no
+ * counterpart here, but the per-launch host cost remains).  No allocation, synchronisation, fused
+ * multi-GPU finish or sort inside a capture. */
+typedef struct nl_graph_s *nl_graph;
+NL_API int nl_graph_begin(int dev);
+NL_API int nl_graph_end(int dev, nl_graph *graph_out);
+NL_API int nl_graph_launch(nl_graph graph);
+NL_API int nl_graph_destroy(nl_graph graph);
+
 NL_API int nl_malloc(int dev, size_t bytes, void **ptr_out);
 NL_API int nl_free(int dev, void *ptr);
 /* Give the free blocks of the device's stream-ordered pool back to the driver (synchronises the

@@ -29,16 +29,23 @@ class DeviceShard:
     without a copy.  Keeps the thunk alive; the memory is the thunk's own storage (do not assign to
     the thunk while a view is in use)."""
 
-    def __init__(self, owner, device, ptr, start, count, typestr):
-        self.owner, self.device, self.start, self.count = owner, device, start, count
+    def __init__(self, owner, index, device, ptr, start, count, typestr):
+        self.owner, self.index, self.device, self.start, self.count = owner, index, device, start, count
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False),
                                          "version": 3, "strides": None}
 
     def __len__(self):
         return self.count
 
+    # DLPack (torch.from_dlpack(shard), cupy.from_dlpack(shard), jax.dlpack.from_dlpack(shard))
+    def __dlpack__(self, stream=None, **_):
+        return self.owner._dlpack(self.index)      # the data is complete: the export synchronises first
+
+    def __dlpack_device__(self):
+        return (2, self.device)                    # (kDLCUDA, CUDA ordinal)
+
 
 def device_shards(thunk):
     """Evaluate `thunk` and return its shards as DeviceShard views, in global index order
     (the host<->device edge of SURVEY 8f-3: results can stay on the GPUs)."""
-    return [DeviceShard(thunk, *t) for t in thunk.device_shards()]
+    return [DeviceShard(thunk, i, *t) for i, t in enumerate(thunk.device_shards())]

@@ -197,6 +197,11 @@ _SIGNATURES = {
     "nl_device_count": (C.c_int, []),
     "nl_device_info": (C.c_int, [C.c_int, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "nl_device_cuda_id": (C.c_int, [C.c_int]),
+    "nl_graph_begin": (C.c_int, [C.c_int]),
+    "nl_graph_end": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "nl_graph_launch": (C.c_int, [_VP]),
+    "nl_graph_destroy": (C.c_int, [_VP]),
     "nl_malloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_VP)]),
     "nl_free": (C.c_int, [C.c_int, _VP]),
     "nl_pool_trim": (C.c_int, [C.c_int]),

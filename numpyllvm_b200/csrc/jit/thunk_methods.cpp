@@ -90,12 +90,94 @@ static PyObject *_thunk_device_shards(PyThunkObject *self, PyObject *args) {
   if (!list) return NULL;
   for (const Shard &sh : s->shards) {
     if (s->replicated && sh.dev != 0) continue;          // an allreduced scalar is the same everywhere
-    PyObject *t = Py_BuildValue("(iKLLs)", sh.dev, (unsigned long long)(uintptr_t)sh.ptr, (long long)sh.start,
+    PyObject *t = Py_BuildValue("(iKLLs)", nl_device_cuda_id(sh.dev), (unsigned long long)(uintptr_t)sh.ptr, (long long)sh.start,
                                 (long long)(s->replicated ? 1 : sh.count), typestr);
     if (!t || PyList_Append(list, t) < 0) { Py_XDECREF(t); Py_DECREF(list); return NULL; }
     Py_DECREF(t);
   }
   return list;
+}
+
+// __array__(dtype=None, copy=None): numpy.asarray(thunk) / numpy.array(thunk) materialise the thunk like
+// asnumpyarray() (thunk.cpp:115-124) — the NumPy side of the host<->device edge
+static PyObject *_thunk_array(PyThunkObject *self, PyObject *args, PyObject *kwargs) {
+  static const char *kwlist[] = {"dtype", "copy", NULL};
+  PyObject *dtype = Py_None, *copy = Py_None;
+  if (!PyArg_ParseTupleAndKeywords(args, kwargs, "|OO", (char **)kwlist, &dtype, &copy)) return NULL;
+  PyObject *arr = PyThunk_AsArray((PyObject *)self);
+  if (arr == NULL) return NULL;
+  if (copy == Py_False && dtype != Py_None) {
+    PyErr_SetString(PyExc_ValueError, "a thunk cannot be converted to another dtype without a copy");
+    return NULL;
+  }
+  if (dtype == Py_None && copy != Py_True) { Py_INCREF(arr); return arr; }     // the cached, read-only host copy
+  PyArray_Descr *descr = NULL;
+  if (dtype != Py_None) {
+    if (!PyArray_DescrConverter(dtype, &descr)) return NULL;
+  } else {
+    descr = PyArray_DESCR((PyArrayObject *)arr);
+    Py_INCREF(descr);
+  }
+  return PyArray_FromArray((PyArrayObject *)arr, descr, NPY_ARRAY_ENSURECOPY | NPY_ARRAY_WRITEABLE | NPY_ARRAY_FORCECAST);   // steals descr
+}
+
+// ---- DLPack export of one shard (consumers: torch.from_dlpack, cupy.from_dlpack, jax) -------------------
+// The structs are the stable DLPack ABI (dlpack.h v0.8); the capsule keeps the thunk alive until the
+// consumer's deleter runs.
+extern "C" {
+typedef struct { int32_t device_type; int32_t device_id; } NLDLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } NLDLDataType;
+typedef struct { void *data; NLDLDevice device; int32_t ndim; NLDLDataType dtype; int64_t *shape; int64_t *strides; uint64_t byte_offset; } NLDLTensor;
+typedef struct NLDLManagedTensor { NLDLTensor dl_tensor; void *manager_ctx; void (*deleter)(struct NLDLManagedTensor *); } NLDLManagedTensor;
+}
+struct DLOwner { NLDLManagedTensor m; int64_t shape[1]; PyObject *thunk; };
+
+static void dl_deleter(NLDLManagedTensor *m) {
+  DLOwner *o = (DLOwner *)m->manager_ctx;
+  PyGILState_STATE g = PyGILState_Ensure();
+  Py_XDECREF(o->thunk);
+  PyGILState_Release(g);
+  delete o;
+}
+static void dl_capsule_destructor(PyObject *cap) {
+  // a capsule nobody consumed still owns the tensor (a consumer renames it to "used_dltensor")
+  if (PyCapsule_IsValid(cap, "dltensor")) {
+    NLDLManagedTensor *m = (NLDLManagedTensor *)PyCapsule_GetPointer(cap, "dltensor");
+    if (m && m->deleter) m->deleter(m);
+  }
+}
+
+// _dlpack(i) -> "dltensor" capsule of shard i (numpyllvm_b200.DeviceShard.__dlpack__ calls this)
+static PyObject *_thunk_dlpack(PyThunkObject *self, PyObject *arg) {
+  const long idx = PyLong_AsLong(arg);
+  if (idx == -1 && PyErr_Occurred()) return NULL;
+  if (PyThunk_Evaluate(self) == NULL) return NULL;
+  if (PyThunk_EnsureDevice(self) < 0) return NULL;
+  Storage *s = self->storage;
+  if (!s || s->host_scalar) { PyErr_SetString(PyExc_ValueError, "a size-1 thunk made from host data has no device buffer"); return NULL; }
+  if (idx < 0 || idx >= (long)s->shards.size()) { PyErr_SetString(PyExc_IndexError, "shard index out of range"); return NULL; }
+  if (storage_settle(s) < 0 || nljit_sync_devices() < 0) return NULL;
+  const Shard &sh = s->shards[(size_t)idx];
+  DLOwner *o = new DLOwner();
+  o->shape[0] = s->replicated ? 1 : sh.count;
+  o->thunk = (PyObject *)self;
+  Py_INCREF(o->thunk);
+  o->m.dl_tensor.data = sh.ptr;
+  o->m.dl_tensor.device.device_type = 2;                   // kDLCUDA
+  o->m.dl_tensor.device.device_id = nl_device_cuda_id(sh.dev);
+  o->m.dl_tensor.ndim = 1;
+  const int dt = s->dtype;
+  o->m.dl_tensor.dtype.code = (dt == NL_F32 || dt == NL_F64) ? 2 : (dt == NL_BOOL ? 6 : 0);   // kDLFloat / kDLBool / kDLInt
+  o->m.dl_tensor.dtype.bits = (uint8_t)(8 * nl_dtype_size(dt));
+  o->m.dl_tensor.dtype.lanes = 1;
+  o->m.dl_tensor.shape = o->shape;
+  o->m.dl_tensor.strides = NULL;
+  o->m.dl_tensor.byte_offset = 0;
+  o->m.manager_ctx = o;
+  o->m.deleter = dl_deleter;
+  PyObject *cap = PyCapsule_New(&o->m, "dltensor", dl_capsule_destructor);
+  if (!cap) { dl_deleter(&o->m); return NULL; }
+  return cap;
 }
 
 struct PyMethodDef thunk_methods[] = {
@@ -108,5 +190,7 @@ struct PyMethodDef thunk_methods[] = {
     {"sum", (PyCFunction)_thunk_sum, METH_NOARGS, "sum() => "},
     {"device_shards", (PyCFunction)_thunk_device_shards, METH_NOARGS,
      "device_shards() => [(device, pointer, first_index, count, typestr), ...] of the evaluated thunk"},
+    {"__array__", (PyCFunction)(void (*)(void))_thunk_array, METH_VARARGS | METH_KEYWORDS, "__array__(dtype=None, copy=None) => host ndarray (numpy.asarray(thunk))"},
+    {"_dlpack", (PyCFunction)_thunk_dlpack, METH_O, "_dlpack(i) => DLPack capsule of shard i (see numpyllvm_b200.DeviceShard)"},
     {NULL, NULL, 0, NULL} /* Sentinel */
 };

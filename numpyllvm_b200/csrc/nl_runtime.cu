@@ -7,9 +7,11 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types and enums only; symbols are resolved with dlsym
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler is attached
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -61,6 +63,19 @@ static unsigned long long g_peer_timeout_ns = 10ull * 1000 * 1000 * 1000;   // b
 void set_peer_timeout_ms(int ms) { g_peer_timeout_ns = (unsigned long long)(ms > 0 ? ms : 10000) * 1000ull * 1000ull; }
 static bool g_peer_ready = false;
 static void *g_ipc_mapped[NL_MAX_DEVICES][kMaxWorld];          // IPC mappings to close at destroy
+
+// NVTX range around every pipeline launch (what PrintPipeline's progress lines were for, debug_printer.cpp:131-160;
+// NL_NVTX=0 turns them off)
+static bool nvtx_on() {
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("NL_NVTX"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char *name) : on(nvtx_on()) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 
 static Device g_dev[NL_MAX_DEVICES];
 static int g_ndev = 0;
@@ -242,6 +257,62 @@ int nl_device_info(int dev, char *name, size_t name_len, int *sm_count, int *cc_
   if (cc_major) *cc_major = prop.major;
   if (cc_minor) *cc_minor = prop.minor;
   if (total_mem) *total_mem = prop.totalGlobalMem;
+  return NL_OK;
+}
+
+int nl_device_cuda_id(int dev) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  return g_dev[dev].id;
+}
+
+// ---- CUDA graphs: a fixed sequence of launches captured once and replayed (launch-bound small pipelines) ----
+struct nl_graph_s {
+  cudaGraphExec_t exec;
+  int dev;
+};
+
+int nl_graph_begin(int dev) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  Device &d = g_dev[dev];
+  CUDA_TRY(cudaSetDevice(d.id));
+  // what a launch may need to allocate must exist before the capture starts
+  rc = ensure_scratch(d, 0, kTileDescOff + ((size_t)1 << 22));
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamBeginCapture(d.stream[0], cudaStreamCaptureModeThreadLocal));
+  return NL_OK;
+}
+
+int nl_graph_end(int dev, nl_graph *graph_out) {
+  int rc = check_dev(dev, 0);
+  if (rc) return rc;
+  if (!graph_out) { set_error("nl_graph_end: null"); return NL_ERR_INVALID; }
+  Device &d = g_dev[dev];
+  CUDA_TRY(cudaSetDevice(d.id));
+  cudaGraph_t g = nullptr;
+  CUDA_TRY(cudaStreamEndCapture(d.stream[0], &g));
+  nl_graph_s *out = new nl_graph_s;
+  out->dev = dev;
+  cudaError_t e = cudaGraphInstantiate(&out->exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { delete out; CUDA_TRY(e); }
+  *graph_out = out;
+  return NL_OK;
+}
+
+int nl_graph_launch(nl_graph graph) {
+  if (!graph) { set_error("nl_graph_launch: null"); return NL_ERR_INVALID; }
+  Device &d = g_dev[graph->dev];
+  CUDA_TRY(cudaSetDevice(d.id));
+  CUDA_TRY(cudaGraphLaunch(graph->exec, d.stream[0]));
+  return NL_OK;
+}
+
+int nl_graph_destroy(nl_graph graph) {
+  if (!graph) return NL_OK;
+  cudaGraphExecDestroy(graph->exec);
+  delete graph;
   return NL_OK;
 }
 
@@ -538,6 +609,7 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
 
   LaunchInfo info;
   if (fuse_finish) d.epoch++;
+  NvtxRange range(fuse_finish ? (peer_offsets ? "nl_pipeline+allgather" : "nl_pipeline+allreduce") : "nl_pipeline");
   rc = launch_pipeline_kernel(plan, kp, vec16, d.sm_count, d.stream[stream], &info);
   if (rc == NL_OK) g_last_info = info;
   else if (fuse_finish) post_abort(d, kp.peer_epoch);

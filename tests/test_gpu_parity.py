@@ -479,3 +479,35 @@ def test_checksum_kernel_matches_its_host_definition(nl, nbytes, misalign):
     abi.check(nl.nl_checksum(0, 0, C.c_void_p(d.ptr + misalign), nbytes, C.c_void_p(out.ptr)))
     got = tuple(int(v) for v in rt.download(out))
     assert got == bench.words_checksum(host[misalign:])[1:]
+
+
+def test_cuda_graph_replays_a_chain_of_small_pipelines(nl, rt):
+    """nl_graph_*: three dependent small pipelines captured once and replayed; the replay computes what the
+    eager launches compute (launch-bound small pipelines)."""
+    n = 50_000
+    x = oracle.fill(np.float32, 0, n, 2, 2)
+    dx = rt.upload(x)
+    t1, t2, res = rt.empty(np.float32, n), rt.empty(np.float32, n), rt.empty(np.float32, 1)
+    sizes = rt.empty(np.int64, 4)
+    e1 = Expr(np.float32); e1.materialize(e1.add(e1.mul(e1.array(), e1.scalar(2.0)), e1.scalar(1.0)))
+    e2 = Expr(np.float32); e2.materialize(e2.mul(e2.array(), e2.array()))
+    e3 = Expr(np.float32); a3 = e3.array(); e3.materialize(e3.max(e3.filter(a3, e3.gt(e3.ref(a3), e3.scalar(3.0)))))
+    p1, p2, p3 = (abi.compile_plan(e) for e in (e1, e2, e3))
+
+    def enqueue():
+        rt.launch(p1, [t1.ptr], [dx.ptr, None, None], 0, n, sizes.ptr)
+        rt.launch(p2, [t2.ptr], [t1.ptr, dx.ptr], 0, n, sizes.ptr)
+        rt.launch(p3, [res.ptr], [t2.ptr, None], 0, n, sizes.ptr)
+    enqueue()
+    want = rt.download(res)[0]
+    assert want == ((x * 2 + 1) * x).max()
+    abi.check(nl.nl_graph_begin(0))
+    enqueue()
+    g = C.c_void_p()
+    abi.check(nl.nl_graph_end(0, C.byref(g)))
+    for rep in range(5):
+        x2 = oracle.fill(np.float32, 0, n, 3 + rep, 2)
+        abi.check(nl.nl_memcpy_h2d(0, 0, C.c_void_p(dx.ptr), C.c_void_p(x2.ctypes.data), x2.nbytes))
+        abi.check(nl.nl_graph_launch(g))
+        assert rt.download(res)[0] == ((x2 * 2 + 1) * x2).max()
+    abi.check(nl.nl_graph_destroy(g))

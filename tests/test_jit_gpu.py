@@ -298,8 +298,8 @@ def test_results_can_stay_on_the_device():
         cai = s.__cuda_array_interface__
         assert cai["typestr"] == "<f4" and cai["version"] == 3 and cai["shape"] == (s.count,)
         if s.count:
-            abi.check(lib.nl_memcpy_d2h(s.device, 0, C.c_void_p(got[s.start:].ctypes.data), C.c_void_p(cai["data"][0]), s.count * 4))
-            abi.check(lib.nl_stream_sync(s.device, 0))
+            abi.check(lib.nl_memcpy_d2h(s.index, 0, C.c_void_p(got[s.start:].ctypes.data), C.c_void_p(cai["data"][0]), s.count * 4))
+            abi.check(lib.nl_stream_sync(s.index, 0))
     assert np.array_equal(got, a_n * 2 + 1)
     total = numpyllvm_b200.device_shards(jit.thunk(np.arange(1000, dtype=np.int64)).sum())
     assert len(total) == 1 and total[0].count == 1
@@ -491,3 +491,25 @@ def test_the_cached_host_copy_is_read_only():
     arr = t.asnumpyarray()
     with pytest.raises(ValueError):
         arr[0] = 1
+
+
+def test_numpy_and_dlpack_edges():
+    """numpy.asarray(thunk) (__array__) and DLPack export of the device shards."""
+    import numpyllvm_b200
+    n = 100_003
+    a_n = np.arange(n, dtype=np.float64)
+    t = jit.thunk(a_n) * 0.5
+    assert np.array_equal(np.asarray(t), a_n * 0.5)
+    assert np.asarray(t, dtype=np.float32).dtype == np.float32
+    w = np.array(t)                                   # a private, writable copy
+    w[0] = -1
+    assert np.asarray(t)[0] == 0.0
+    assert np.add(t, 1)[1] == 1.5                     # ufuncs coerce a thunk like any array-like
+    torch = pytest.importorskip("torch")
+    parts = [torch.from_dlpack(s) for s in numpyllvm_b200.device_shards(t) if len(s)]
+    assert all(p.is_cuda and p.dtype == torch.float64 for p in parts)
+    got = torch.cat([p.cpu() for p in parts]).numpy()
+    assert np.array_equal(got, a_n * 0.5)
+    m = jit.thunk(np.arange(10)) > 4                 # bool and int shards keep their dtypes
+    assert torch.from_dlpack(numpyllvm_b200.device_shards(m)[0]).dtype == torch.bool
+    del parts                                         # the capsules kept `t` alive; dropping the tensors releases it
