@@ -578,9 +578,56 @@ def run_extra(args, rt, lib, ranks, peak, timed, threads):
                 ok &= got == combine_checksums(oracle_stream(n1, c1_chunk, threads))[1:]
             extra["parity"] = verdict(ok, f"64-bit checksums of all {n1} elements of all 3 result columns")
         report("C1", "C1 Tests/multiplication.py (d*e*f)*(a*b*c)", "f64", n1, 56 * n1, ms, extra, k=30)
+        # the same launches replayed from a CUDA graph (one graph = the three column sets in turn)
+        try:
+            abi.check(lib.nl_graph_begin(0))
+            for _ in range(3):
+                c1(None)
+            graph = C.c_void_p()
+            abi.check(lib.nl_graph_end(0, C.byref(graph)))
+            ms, _ = timed(lambda _: abi.check(lib.nl_graph_launch(graph)), 10, 3)
+            report("C1 graph", "C1 replayed from a CUDA graph (nl_graph_*: 3 launches per replay)", "f64", n1, 56 * n1 * 3, ms, {"launches_per_step": 3}, k=10)
+            lib.nl_graph_destroy(graph)
+        except Exception as exc:
+            out.append({"id": "C1 graph", "config": "C1 replayed from a CUDA graph", "error": f"{type(exc).__name__}: {exc}"})
         for cols in sets:
             for x in cols:
                 x.free()
+        # ... and through the `jit` API with device-resident thunks: what one small pipeline costs end to end on the
+        # host side (parse, lower, plan, allocate, launch); evaluation is stream-ordered, so launches overlap kernels
+        try:
+            import numpyllvm_b200
+            jit = numpyllvm_b200.install_jit_alias()
+            hosts = [oracle.fill(np.float64, 0, n1, 100 + j, 2) for j in range(6)]
+            ts = [jit.thunk(h) for h in hosts]
+            jit.synchronize()
+
+            def jit_step():
+                r = (ts[0] * ts[1] * ts[2]) * (ts[3] * ts[4] * ts[5])
+                r.evaluate()
+                return r
+            keep = [jit_step() for _ in range(3)]
+            jit.synchronize()
+            t0 = time.perf_counter()
+            r = jit_step()
+            jit.synchronize()
+            one = time.perf_counter() - t0                       # latency of ONE pipeline, launch to completion
+            t0 = time.perf_counter()
+            for _ in range(30):
+                keep[0] = jit_step()
+            t_host = time.perf_counter() - t0                    # host time to enqueue 30 pipelines
+            jit.synchronize()
+            t_all = time.perf_counter() - t0
+            okj = bool(np.array_equal(r.asnumpyarray()[:4096], ((hosts[0] * hosts[1]) * hosts[2] * ((hosts[3] * hosts[4]) * hosts[5]))[:4096]))
+            out.append({"id": "C1 jit", "config": "C1 through the jit API, device-resident thunks: r = (d*e*f)*(a*b*c); r.evaluate()", "dtype": "f64",
+                        "elements_per_gpu": n1, "latency_ms_one_pipeline": round(one * 1e3, 4), "ms_per_step": round(t_all / 30 * 1e3, 5),
+                        "host_enqueue_ms_per_step": round(t_host / 30 * 1e3, 5), "GB/s": round(56 * n1 * 30 / t_all / 1e9, 2),
+                        "frac_of_measured_peak": round(56 * n1 * 30 / t_all / 1e9 / peak, 4),
+                        "parity": verdict(okj, "first 4096 elements vs NumPy (same association)")})
+            del ts, keep, r
+            jit.synchronize()
+        except Exception as exc:
+            out.append({"id": "C1 jit", "config": "C1 through the jit API", "error": f"{type(exc).__name__}: {exc}"})
 
     # C3: max / sum over 2^31 f64 / int64 (sharded: 2^31 / G per GPU), partials exchanged over NVLink
     n3_total = 1 << args.log2n_reduce

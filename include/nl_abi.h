@@ -77,14 +77,24 @@ enum {
                                 must give the filters below the root pipelines of their own */
 };
 
-/* ---- element types (subset of getLLVMType, compiler.cpp:156-182) ---------- */
+/* ---- element types (getLLVMType, compiler.cpp:156-182: bool/i8, i16, i32, i64, f32, f64; the
+ *      reference leaves the unsigned types as a todo, :168-172 — here they compute with unsigned
+ *      compares and wrap like NumPy's).  The build-time shapes and shape families exist for the
+ *      first four value types; the others run on the step interpreter.  f16 is not implemented. */
 typedef enum {
   NL_BOOL = 0,   /* NPY_BOOL, one byte, canonical 0x00/0x01 on store (Q4)      */
   NL_I32  = 1,
   NL_I64  = 2,
   NL_F32  = 3,
-  NL_F64  = 4
+  NL_F64  = 4,
+  NL_I8   = 5,
+  NL_I16  = 6,
+  NL_U8   = 7,
+  NL_U16  = 8,
+  NL_U32  = 9,
+  NL_U64  = 10
 } nl_dtype;
+#define NL_N_DTYPES 11
 
 /* ---- operators: the per-operator "emitters" of the reference -------------- */
 typedef enum {
@@ -344,6 +354,12 @@ NL_API int nl_assign_copy(int dev, int stream, void *dst, int dtype,
  * 3: floats in [0,1).   */
 NL_API int nl_fill(int dev, int stream, void *dst, int dtype, int64_t first_index,
             int64_t count, uint64_t seed, int kind);
+
+/* dst[i] = (dst_dtype)src[i], i in [0, count): the materialise-store cast of compiler.cpp:256-260 as a pass of
+ * its own, used where two columns of different types meet (NumPy promotion; the reference gives the result
+ * its LEFT operand's type and leaves "todo: correct type", thunk_as_number.cpp:78).  Any value type to any
+ * value type, bool as a source only; C conversion rules (integer narrowing wraps, float -> int truncates). */
+NL_API int nl_cast(int dev, int stream, void *dst, int dst_dtype, const void *src, int src_dtype, int64_t count);
 
 /* Three 64-bit checksums of `nbytes` of device memory read as little-endian 64-bit words w_i (a
  * trailing partial word zero-padded; `ptr` 8-byte aligned):

@@ -29,8 +29,11 @@ NL_ERR_SPLIT_FILTER = -8
 
 # dtypes
 NL_BOOL, NL_I32, NL_I64, NL_F32, NL_F64 = 0, 1, 2, 3, 4
+NL_I8, NL_I16, NL_U8, NL_U16, NL_U32, NL_U64 = 5, 6, 7, 8, 9, 10
 _NP2NL = {np.dtype(np.bool_): NL_BOOL, np.dtype(np.int32): NL_I32, np.dtype(np.int64): NL_I64,
-          np.dtype(np.float32): NL_F32, np.dtype(np.float64): NL_F64}
+          np.dtype(np.float32): NL_F32, np.dtype(np.float64): NL_F64,
+          np.dtype(np.int8): NL_I8, np.dtype(np.int16): NL_I16, np.dtype(np.uint8): NL_U8, np.dtype(np.uint16): NL_U16,
+          np.dtype(np.uint32): NL_U32, np.dtype(np.uint64): NL_U64}
 _NL2NP = {v: k for k, v in _NP2NL.items()}
 
 # ops
@@ -54,7 +57,7 @@ PLAN_HAS_FILTER, PLAN_HAS_COMPACT, PLAN_HAS_REDUCE, PLAN_HAS_WHERE = 1, 2, 4, 8
 def nl_dtype_of(dt) -> int:
     dt = np.dtype(dt)
     if dt not in _NP2NL:
-        raise TypeError(f"dtype {dt} is outside the kernel library (bool, int32, int64, float32, float64)")
+        raise TypeError(f"dtype {dt} is outside the kernel library (bool, int8..int64, uint8..uint64, float32, float64)")
     return _NP2NL[dt]
 
 
@@ -236,6 +239,7 @@ _SIGNATURES = {
     "nl_assign_fill": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_uint64]),
     "nl_assign_copy": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, C.c_int64, C.c_int64, C.c_int64, _VP]),
     "nl_fill": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, C.c_int64, C.c_int64, C.c_uint64, C.c_int]),
+    "nl_cast": (C.c_int, [C.c_int, C.c_int, _VP, C.c_int, _VP, C.c_int, C.c_int64]),
     "nl_checksum": (C.c_int, [C.c_int, C.c_int, _VP, C.c_size_t, _VP]),
     "nl_sort": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int64]),
     "nl_gather": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int64, C.POINTER(_VP), C.POINTER(C.c_int64), C.c_int, C.c_int64, _VP]),

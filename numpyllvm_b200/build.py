@@ -30,7 +30,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", f"-I{INCLUDE}", f"-I{CSRC}"]
 NVCC_FLAGS += os.environ.get("NL_EXTRA_NVCC_FLAGS", "").split()   # tuning experiments (-DNL_PIPE_ROWS=8 ...); use with --force
 
-KERNEL_SOURCES = ["nl_plan.cpp", "nl_kernels.cu", "nl_runtime.cu", "nl_sort.cu", "nl_checksum.cu",
+KERNEL_SOURCES = ["nl_plan.cpp", "nl_kernels.cu", "nl_runtime.cu", "nl_sort.cu", "nl_checksum.cu", "nl_cast.cu",
+                  "nl_dynamic_i8.cu", "nl_dynamic_i16.cu", "nl_dynamic_u8.cu", "nl_dynamic_u16.cu", "nl_dynamic_u32.cu", "nl_dynamic_u64.cu",
                   "nl_dynamic_i32.cu", "nl_dynamic_i64.cu", "nl_dynamic_f32.cu", "nl_dynamic_f64.cu",
                   "nl_static_i32.cu", "nl_static_i64.cu", "nl_static_f32.cu", "nl_static_f64.cu",
                   "nl_static_i32_b.cu", "nl_static_i64_b.cu", "nl_static_f32_b.cu", "nl_static_f64_b.cu",

@@ -22,6 +22,12 @@ namespace {
 // the kernels' order-preserving bijection (nl_sort.cu: order_key), for the host-side splitters
 uint64_t host_order_key(uint64_t bits, int dtype) {
   switch (dtype) {
+    case NL_I8: return (uint64_t)((uint8_t)bits ^ 0x80u);
+    case NL_I16: return (uint64_t)((uint16_t)bits ^ 0x8000u);
+    case NL_U8: return (uint64_t)(uint8_t)bits;
+    case NL_U16: return (uint64_t)(uint16_t)bits;
+    case NL_U32: return (uint64_t)(uint32_t)bits;
+    case NL_U64: return bits;
     case NL_I32: return (uint64_t)((uint32_t)bits ^ 0x80000000u);
     case NL_I64: return bits ^ 0x8000000000000000ull;
     case NL_F32: {

@@ -3,40 +3,54 @@
 
 #include <cstring>
 
-static double bits_to_double(uint64_t bits, int dtype) {
+static bool dt_is_float(int t) { return t == NL_F32 || t == NL_F64; }
+static bool dt_is_unsigned(int t) { return t == NL_BOOL || t == NL_U8 || t == NL_U16 || t == NL_U32 || t == NL_U64; }
+
+// the value behind a bit pattern of type `dtype`, in the widest type of its kind
+template <typename W>
+static W bits_as(uint64_t bits, int dtype) {
   switch (dtype) {
-    case NL_BOOL: return (double)(bits & 0xff ? 1 : 0);
-    case NL_I32: { int32_t v; memcpy(&v, &bits, 4); return (double)v; }
-    case NL_I64: { int64_t v; memcpy(&v, &bits, 8); return (double)v; }
-    case NL_F32: { float v; memcpy(&v, &bits, 4); return (double)v; }
-    default: { double v; memcpy(&v, &bits, 8); return v; }
+    case NL_BOOL: return (W)((bits & 0xff) ? 1 : 0);
+    case NL_I8: { int8_t v; memcpy(&v, &bits, 1); return (W)v; }
+    case NL_I16: { int16_t v; memcpy(&v, &bits, 2); return (W)v; }
+    case NL_I32: { int32_t v; memcpy(&v, &bits, 4); return (W)v; }
+    case NL_I64: { int64_t v; memcpy(&v, &bits, 8); return (W)v; }
+    case NL_U8: { uint8_t v; memcpy(&v, &bits, 1); return (W)v; }
+    case NL_U16: { uint16_t v; memcpy(&v, &bits, 2); return (W)v; }
+    case NL_U32: { uint32_t v; memcpy(&v, &bits, 4); return (W)v; }
+    case NL_U64: { uint64_t v; memcpy(&v, &bits, 8); return (W)v; }
+    case NL_F32: { float v; memcpy(&v, &bits, 4); return (W)v; }
+    default: { double v; memcpy(&v, &bits, 8); return (W)v; }
   }
 }
 
-static int64_t bits_to_int(uint64_t bits, int dtype) {
-  switch (dtype) {
-    case NL_BOOL: return (bits & 0xff) ? 1 : 0;
-    case NL_I32: { int32_t v; memcpy(&v, &bits, 4); return v; }
-    case NL_I64: { int64_t v; memcpy(&v, &bits, 8); return v; }
-    case NL_F32: { float v; memcpy(&v, &bits, 4); return (int64_t)v; }
-    default: { double v; memcpy(&v, &bits, 8); return (int64_t)v; }
-  }
+template <typename D>
+static uint64_t store_as(uint64_t bits, int from) {
+  D v = dt_is_float(from) ? (D)bits_as<double>(bits, from) : dt_is_unsigned(from) ? (D)bits_as<uint64_t>(bits, from) : (D)bits_as<int64_t>(bits, from);
+  uint64_t out = 0;
+  memcpy(&out, &v, sizeof(D));
+  return out;
 }
 
 // getLLVMConstant (compiler.cpp:125-154) baked a size-1 input as an immediate of the column
-// type; the conversion to the pipeline's value type happens here, on the host
-static uint64_t convert_scalar(uint64_t bits, int from, int to) {
+// type; the conversion to the pipeline's value type happens here, on the host (C conversion rules)
+uint64_t nljit_convert_scalar(uint64_t bits, int from, int to) {
   if (from == to) return bits;
-  uint64_t out = 0;
   switch (to) {
-    case NL_I32: { int32_t v = (int32_t)bits_to_int(bits, from); memcpy(&out, &v, 4); break; }
-    case NL_I64: { int64_t v = bits_to_int(bits, from); memcpy(&out, &v, 8); break; }
-    case NL_F32: { float v = (from == NL_F64 || from == NL_F32) ? (float)bits_to_double(bits, from) : (float)bits_to_int(bits, from); memcpy(&out, &v, 4); break; }
-    case NL_F64: { double v = (from == NL_F64 || from == NL_F32) ? bits_to_double(bits, from) : (double)bits_to_int(bits, from); memcpy(&out, &v, 8); break; }
-    default: out = (bits & 0xff) ? 1 : 0; break;
+    case NL_I8: return store_as<int8_t>(bits, from);
+    case NL_I16: return store_as<int16_t>(bits, from);
+    case NL_I32: return store_as<int32_t>(bits, from);
+    case NL_I64: return store_as<int64_t>(bits, from);
+    case NL_U8: return store_as<uint8_t>(bits, from);
+    case NL_U16: return store_as<uint16_t>(bits, from);
+    case NL_U32: return store_as<uint32_t>(bits, from);
+    case NL_U64: return store_as<uint64_t>(bits, from);
+    case NL_F32: return store_as<float>(bits, from);
+    case NL_F64: return store_as<double>(bits, from);
+    default: return (bits_as<double>(bits, from) != 0.0) ? 1 : 0;
   }
-  return out;
 }
+static uint64_t convert_scalar(uint64_t bits, int from, int to) { return nljit_convert_scalar(bits, from, to); }
 
 struct Lowering {
   Pipeline *pipeline;

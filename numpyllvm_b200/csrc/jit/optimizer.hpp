@@ -26,5 +26,7 @@ struct LoweredPipeline {
 // filter below the root when a column meets a filter result inside one pipeline (a[m] * b[m]).
 // -1: error, Python exception set.
 int LowerPipeline(Pipeline *pipeline, LoweredPipeline *out, std::vector<PyThunkObject *> *cuts_out);
+// bit pattern of a scalar of nl type `from` converted to nl type `to` (C conversion rules)
+uint64_t nljit_convert_scalar(uint64_t bits, int from, int to);
 
 #endif

@@ -66,6 +66,39 @@ static int run_base_function(Pipeline *pipeline) {
     storage_incref(in->storage);
   }
   if (!in->storage) { PyErr_SetString(PyExc_ValueError, "base function input is not evaluated"); return -1; }
+  if (top->name == "astype") {
+    // conversion to the output thunk's element type: one nl_cast pass per shard, same layout as the input
+    Binding &out = pipeline->outputs[0];
+    Storage *src = in->storage;
+    const int to = nljit_npy_to_nl(out.source->object->npy_type);
+    Storage *dst = storage_new(to, src->bound);
+    dst->ragged = src->ragged;
+    dst->replicated = src->replicated;
+    if (src->host_scalar) {
+      dst->host_scalar = true;
+      dst->scalar_bits = nljit_convert_scalar(src->scalar_bits, src->dtype, to);
+    } else {
+      if (nljit_ensure_runtime() < 0 || storage_settle(src) < 0) { storage_decref(dst); return -1; }
+      const size_t es = nl_dtype_size(to);
+      for (const Shard &sh : src->shards) {
+        Shard o = sh;
+        o.marks.clear();
+        o.ptr = NULL;
+        const int64_t cnt = src->replicated ? 1 : sh.count;
+        o.capacity = cnt;
+        int rc = NL_OK;
+        if (cnt > 0) rc = nl_malloc(sh.dev, (size_t)cnt * es, &o.ptr);
+        if (rc == NL_OK && cnt > 0) rc = nl_cast(sh.dev, 0, o.ptr, to, sh.ptr, src->dtype, cnt);
+        dst->shards.push_back(o);
+        if (rc != NL_OK) { nljit_raise(rc, "jit: dtype conversion failed"); storage_decref(dst); return -1; }
+      }
+    }
+    out.source->storage = dst;                          // the pipeline's reference
+    out.source->size = (ssize_t)dst->cardinality();
+    storage_incref(dst);
+    PyThunk_MarkEvaluated(out.source->object, dst);     // the thunk holds its own reference
+    return 0;
+  }
   if (top->name == "sort" && !in->storage->host_scalar && !in->storage->replicated && nljit_ensure_runtime() == 0) {
     // sort() runs where the data lives: radix sort per GPU, sample sort across GPUs (device_sort.cpp)
     Storage *sorted = device_sort(in->storage);

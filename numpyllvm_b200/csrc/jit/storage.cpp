@@ -54,6 +54,15 @@ int nljit_npy_to_nl(int t) {
 #endif
     case NPY_FLOAT32: return NL_F32;
     case NPY_FLOAT64: return NL_F64;
+    case NPY_INT8: return NL_I8;
+    case NPY_INT16: return NL_I16;
+    case NPY_UINT8: return NL_U8;
+    case NPY_UINT16: return NL_U16;
+    case NPY_UINT32: return NL_U32;
+    case NPY_UINT64: return NL_U64;
+#if NPY_ULONGLONG != NPY_UINT64
+    case NPY_ULONGLONG: return NL_U64;
+#endif
   }
   return -1;
 }
@@ -65,6 +74,12 @@ int nljit_nl_to_npy(int t) {
     case NL_I64: return NPY_INT64;
     case NL_F32: return NPY_FLOAT32;
     case NL_F64: return NPY_FLOAT64;
+    case NL_I8: return NPY_INT8;
+    case NL_I16: return NPY_INT16;
+    case NL_U8: return NPY_UINT8;
+    case NL_U16: return NPY_UINT16;
+    case NL_U32: return NPY_UINT32;
+    case NL_U64: return NPY_UINT64;
   }
   return NPY_NOTYPE;
 }

@@ -7,6 +7,7 @@
 // once it is evaluated.
 #include "thunk.hpp"
 #include "parser.hpp"
+#include "optimizer.hpp"
 #include "scheduler.hpp"
 #include "debug_printer.hpp"
 
@@ -53,7 +54,7 @@ PyObject *PyThunk_FromArray(PyObject *unused, PyObject *input) {
   PyArrayObject *a = (PyArrayObject *)arr;
   const int nl_type = nljit_npy_to_nl(PyArray_TYPE(a));
   if (nl_type < 0) {
-    PyErr_Format(PyExc_TypeError, "thunk: dtype %R is outside the kernel library (bool, int32, int64, float32, float64)",
+    PyErr_Format(PyExc_TypeError, "thunk: dtype %R is outside the kernel library (bool, int8..int64, uint8..uint64, float32, float64)",
                  (PyObject *)PyArray_DESCR(a));
     Py_DECREF(arr);
     return NULL;
@@ -100,6 +101,38 @@ PyObject *PyThunk_Coerce(PyObject *obj) {
   PyObject *t = PyThunk_FromArray(NULL, arr);
   Py_DECREF(arr);
   return t;
+}
+
+// astype(): conversion to another element type.  An evaluated host scalar is converted here; anything else gets a
+// lazy full breaker whose work is one nl_cast pass per shard (scheduler.cpp: run_base_function) — the reference's
+// only cast is the signed integer cast of its materialise store (compiler.cpp:256-260).
+PyObject *PyThunk_AsType(PyThunkObject *thunk, int npy_type) {
+  if (thunk->npy_type == npy_type) { Py_INCREF(thunk); return (PyObject *)thunk; }
+  if (nljit_npy_to_nl(npy_type) < 0) {
+    PyErr_SetString(PyExc_TypeError, "astype: dtype is outside the kernel library");
+    return NULL;
+  }
+  if (npy_type == NPY_BOOL || thunk->npy_type == NPY_BOOL) {
+    PyErr_SetString(PyExc_TypeError, "astype: conversions from or to bool are not supported (compare with 0 instead)");
+    return NULL;
+  }
+  if (thunk->evaluated && thunk->storage && thunk->storage->host_scalar) {
+    Storage *s = storage_new(nljit_npy_to_nl(npy_type), 1);
+    s->host_scalar = true;
+    s->scalar_bits = nljit_convert_scalar(thunk->storage->scalar_bits, thunk->storage->dtype, s->dtype);
+    PyThunkObject *out = thunk_alloc();
+    if (!out) { storage_decref(s); return NULL; }
+    out->evaluated = true;
+    out->card.n = 1;
+    out->card.kind = CardinalityKind::Exact;
+    out->npy_type = npy_type;
+    out->name = getname("A");
+    out->storage = s;
+    return (PyObject *)out;
+  }
+  ThunkOperation *op = NewUnaryOperation((PyObject *)thunk, OpClass::FullBreaker, -1, NULL, "astype");
+  if (!op) return PyErr_NoMemory();
+  return PyThunk_FromOperation(op, cardinality_same_as_operand, thunk->card.kind, npy_type);
 }
 
 PyObject *PyThunk_FromOperation(ThunkOperation *operation, CardinalityFn cardinality_func,

@@ -46,6 +46,7 @@ extern PyTypeObject PyThunk_Type;
 PyObject *PyThunk_FromArray(PyObject *unused, PyObject *input);
 PyObject *PyThunk_FromOperation(ThunkOperation *operation, CardinalityFn fn, CardinalityKind kind, int npy_type);
 PyObject *PyThunk_Coerce(PyObject *obj);           /* thunk, ndarray or Python scalar -> new reference to a thunk */
+PyObject *PyThunk_AsType(PyThunkObject *thunk, int npy_type);   /* new reference: the thunk itself or a (lazy) conversion */
 
 int PyThunk_Init(void);
 PyObject *PyThunk_Evaluate(PyThunkObject *thunk);

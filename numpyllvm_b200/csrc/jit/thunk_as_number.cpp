@@ -6,33 +6,74 @@
 
 static bool is_float_type(int t) { return t == NPY_FLOAT32 || t == NPY_FLOAT64; }
 
-// The reference types the result after the LEFT operand (thunk_as_number.cpp:78, "todo: correct
-// type") and would hand LLVM mismatched operand widths (Q3).  Here: scalars adopt the dtype of
-// the array operand (NumPy's weak-scalar rule), two arrays must agree, and a float scalar is
-// never silently truncated into an integer column.
-static int binary_value_type(PyThunkObject *l, PyThunkObject *r, int *type_out) {
-  const bool ls = l->card.n == 1, rs = r->card.n == 1;
+// ---- operand types ------------------------------------------------------------------------------
+// The reference types the result after the LEFT operand (thunk_as_number.cpp:78, "todo: correct type")
+// and would hand LLVM mismatched operand widths (Q3).  Here the result type is NumPy's:
+//   two columns (or NumPy scalars)   numpy.promote_types of the two dtypes
+//   a Python int                     weak: the column's dtype (OverflowError if it does not fit, as in NumPy 2)
+//   a Python float                   weak: the column's dtype if that is a float, float64 otherwise
+//   /                                a float type: the promoted type, or float64 for integer operands
+// and an operand of another type is converted first: a host scalar on the host, a column by a lazy
+// astype() — a pass of its own (nl_cast) whose result the fused pipeline reads in the common type.
+struct Weak { bool is_int, is_float; };
+
+static Weak weakness(PyObject *obj) {
+  Weak w = {false, false};
+  if (PyThunk_Check(obj) || PyArray_Check(obj) || PyArray_IsScalar(obj, Generic)) return w;
+  if (PyBool_Check(obj)) return w;
+  if (PyLong_Check(obj)) w.is_int = true;
+  else if (PyFloat_Check(obj)) w.is_float = true;
+  return w;
+}
+
+static int result_type(PyThunkObject *l, Weak lw, PyThunkObject *r, Weak rw, int opcode, int *type_out) {
   if (l->npy_type == NPY_BOOL || r->npy_type == NPY_BOOL) {
     PyErr_SetString(PyExc_TypeError, "arithmetic and comparisons on boolean thunks are not supported");
     return -1;
   }
+  const bool l_weak = lw.is_int || lw.is_float, r_weak = rw.is_int || rw.is_float;
   int t;
-  if (ls && !rs) t = r->npy_type;
-  else if (rs && !ls) t = l->npy_type;
-  else {
-    if (l->npy_type != r->npy_type && !(ls && rs)) {
-      PyErr_SetString(PyExc_TypeError, "operands must have the same dtype (no implicit promotion between columns)");
-      return -1;
-    }
+  if (l_weak != r_weak) {
+    const int other = l_weak ? r->npy_type : l->npy_type;
+    const Weak w = l_weak ? lw : rw;
+    t = w.is_int ? other : (is_float_type(other) ? other : NPY_FLOAT64);
+  } else if (l->npy_type == r->npy_type) {
     t = l->npy_type;
+  } else {
+    PyArray_Descr *a = PyArray_DescrFromType(l->npy_type), *b = PyArray_DescrFromType(r->npy_type);
+    PyArray_Descr *c = (a && b) ? PyArray_PromoteTypes(a, b) : NULL;
+    Py_XDECREF(a);
+    Py_XDECREF(b);
+    if (!c) return -1;
+    t = c->type_num;
+    Py_DECREF(c);
   }
-  PyThunkObject *scalar = (ls && !rs) ? l : (rs && !ls) ? r : NULL;
-  if (scalar && is_float_type(scalar->npy_type) && !is_float_type(t)) {
-    PyErr_SetString(PyExc_TypeError, "a float scalar cannot be combined with an integer column");
+  if (opcode == NL_OP_DIV && !is_float_type(t)) t = NPY_FLOAT64;      // int / int is a float64 in NumPy
+  if (nljit_npy_to_nl(t) < 0 || t == NPY_BOOL) {
+    PyErr_SetString(PyExc_TypeError, "the promoted dtype of the operands is outside the kernel library");
     return -1;
   }
   *type_out = t;
   return 0;
+}
+
+// a size-1 thunk of dtype `t` holding the Python scalar `value` (NumPy's own conversion: OverflowError when a
+// Python int does not fit the column type)
+static PyObject *scalar_thunk_of(PyObject *value, int t) {
+  npy_intp one = 1;
+  PyObject *arr = PyArray_SimpleNew(1, &one, t);
+  if (!arr) return NULL;
+  if (PyArray_SETITEM((PyArrayObject *)arr, (char *)PyArray_DATA((PyArrayObject *)arr), value) < 0) { Py_DECREF(arr); return NULL; }
+  PyObject *th = PyThunk_FromArray(NULL, arr);
+  Py_DECREF(arr);
+  return th;
+}
+
+// new reference to `operand` as a thunk of dtype `t`
+static PyObject *conform(PyObject *original, PyThunkObject *operand, Weak w, int t) {
+  if (w.is_int || w.is_float) return scalar_thunk_of(original, t);
+  if (operand->npy_type == t) { Py_INCREF(operand); return (PyObject *)operand; }
+  return PyThunk_AsType(operand, t);
 }
 
 static int check_cardinality(PyThunkObject *l, PyThunkObject *r) {
@@ -53,12 +94,16 @@ static PyObject *lazy_binary(PyObject *v, PyObject *w, int opcode, const char *o
   if (!ro) { Py_DECREF(lo); return NULL; }
   PyThunkObject *left = (PyThunkObject *)lo, *right = (PyThunkObject *)ro;
   int type;
-  if (binary_value_type(left, right, &type) < 0 || check_cardinality(left, right) < 0) {
+  if (result_type(left, weakness(v), right, weakness(w), opcode, &type) < 0 || check_cardinality(left, right) < 0) {
     Py_DECREF(lo); Py_DECREF(ro);
     return NULL;
   }
-  ThunkOperation *op = NewBinaryOperation(lo, ro, OpClass::Vectorizable, opcode, opname);
-  Py_DECREF(lo); Py_DECREF(ro);      // the operation holds its own references
+  PyObject *lc = conform(v, left, weakness(v), type);
+  PyObject *rc = lc ? conform(w, right, weakness(w), type) : NULL;
+  Py_DECREF(lo); Py_DECREF(ro);
+  if (!lc || !rc) { Py_XDECREF(lc); Py_XDECREF(rc); return NULL; }
+  ThunkOperation *op = NewBinaryOperation(lc, rc, OpClass::Vectorizable, opcode, opname);
+  Py_DECREF(lc); Py_DECREF(rc);      // the operation holds its own references
   if (!op) return PyErr_NoMemory();
   return PyThunk_FromOperation(op, cardinality_broadcast, CardinalityKind::Exact, type);
 }
@@ -66,22 +111,11 @@ static PyObject *lazy_binary(PyObject *v, PyObject *w, int opcode, const char *o
 static PyObject *thunk_lazymultiply(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_MUL, "*"); }
 static PyObject *thunk_lazyadd(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_ADD, "+"); }
 static PyObject *thunk_lazysubtract(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_SUB, "-"); }
-// Division is not in the reference.  `/` exists for float thunks only — NumPy's int / int
-// is a float and this engine keeps the left operand's dtype (Q3); `//` is NumPy's floor_divide.
-static PyObject *thunk_lazytruedivide(PyObject *v, PyObject *w) {
-  PyObject *r = lazy_binary(v, w, NL_OP_DIV, "/");
-  if (r && r != Py_NotImplemented) {
-    const int t = ((PyThunkObject *)r)->npy_type;
-    if (t != NPY_FLOAT32 && t != NPY_FLOAT64) {
-      Py_DECREF(r);
-      PyErr_SetString(PyExc_TypeError, "true division of integer thunks would change the dtype; use // or convert to float first");
-      return NULL;
-    }
-  }
-  return r;
-}
+// Division is not in the reference.  `/` is NumPy's true_divide: the result is a float type (integer
+// operands are converted to float64 first); `//` is NumPy's floor_divide.
+static PyObject *thunk_lazytruedivide(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_DIV, "/"); }
 static PyObject *thunk_lazyfloordivide(PyObject *v, PyObject *w) { return lazy_binary(v, w, NL_OP_FLOORDIV, "//"); }
-// -a == a * (-1): exact for floats (sign flip, also of zeros) and wrapping for ints like NumPy
+// floats: -a == a * (-1), exact (sign flip, also of zeros); integers: -a == 0 - a, wrapping like NumPy (also unsigned)
 static PyObject *thunk_lazynegative(PyObject *v) {
   PyThunkObject *l = (PyThunkObject *)v;
   if (l->npy_type == NPY_BOOL) {
@@ -91,11 +125,12 @@ static PyObject *thunk_lazynegative(PyObject *v) {
   npy_intp one = 1;
   PyObject *m = PyArray_SimpleNew(1, &one, l->npy_type);
   if (!m) return NULL;
-  PyObject *minus_one = PyLong_FromLong(-1);
-  const int rc = minus_one ? PyArray_SETITEM((PyArrayObject *)m, (char *)PyArray_DATA((PyArrayObject *)m), minus_one) : -1;
-  Py_XDECREF(minus_one);
+  const bool flt = is_float_type(l->npy_type);
+  PyObject *k = PyLong_FromLong(flt ? -1 : 0);
+  const int rc = k ? PyArray_SETITEM((PyArrayObject *)m, (char *)PyArray_DATA((PyArrayObject *)m), k) : -1;
+  Py_XDECREF(k);
   if (rc < 0) { Py_DECREF(m); return NULL; }
-  PyObject *r = lazy_binary(v, m, NL_OP_MUL, "neg");
+  PyObject *r = flt ? lazy_binary(v, m, NL_OP_MUL, "neg") : lazy_binary(m, v, NL_OP_SUB, "neg");
   Py_DECREF(m);
   return r;
 }
@@ -119,12 +154,17 @@ PyObject *PyThunk_LazyRichCompare(PyObject *self, PyObject *other, int cmp_op) {
   if (!ro) return NULL;
   PyThunkObject *left = (PyThunkObject *)self, *right = (PyThunkObject *)ro;
   int type;
-  if (binary_value_type(left, right, &type) < 0 || check_cardinality(left, right) < 0) {
+  const Weak none = {false, false};
+  if (result_type(left, none, right, weakness(other), opcode, &type) < 0 || check_cardinality(left, right) < 0) {
     Py_DECREF(ro);
     return NULL;
   }
-  ThunkOperation *op = NewBinaryOperation(self, ro, OpClass::Vectorizable, opcode, name);
+  PyObject *lc = conform(self, left, none, type);
+  PyObject *rc = lc ? conform(other, right, weakness(other), type) : NULL;
   Py_DECREF(ro);
+  if (!lc || !rc) { Py_XDECREF(lc); Py_XDECREF(rc); return NULL; }
+  ThunkOperation *op = NewBinaryOperation(lc, rc, OpClass::Vectorizable, opcode, name);
+  Py_DECREF(lc); Py_DECREF(rc);
   if (!op) return PyErr_NoMemory();
   return PyThunk_FromOperation(op, cardinality_broadcast, CardinalityKind::Exact,
                                NPY_BOOL /* returns a boolean array */);

@@ -83,8 +83,8 @@ static PyObject *_thunk_device_shards(PyThunkObject *self, PyObject *args) {
     PyErr_SetString(PyExc_ValueError, "a size-1 thunk made from host data has no device buffer");
     return NULL;
   }
-  const char *typestr = s->dtype == NL_I32 ? "<i4" : s->dtype == NL_I64 ? "<i8" : s->dtype == NL_F32 ? "<f4"
-                        : s->dtype == NL_F64 ? "<f8" : "|b1";
+  static const char *typestrs[NL_N_DTYPES] = {"|b1", "<i4", "<i8", "<f4", "<f8", "|i1", "<i2", "|u1", "<u2", "<u4", "<u8"};
+  const char *typestr = typestrs[s->dtype];
   if (storage_settle(s) < 0 || nljit_sync_devices() < 0) return NULL;
   PyObject *list = PyList_New(0);
   if (!list) return NULL;
@@ -167,7 +167,8 @@ static PyObject *_thunk_dlpack(PyThunkObject *self, PyObject *arg) {
   o->m.dl_tensor.device.device_id = nl_device_cuda_id(sh.dev);
   o->m.dl_tensor.ndim = 1;
   const int dt = s->dtype;
-  o->m.dl_tensor.dtype.code = (dt == NL_F32 || dt == NL_F64) ? 2 : (dt == NL_BOOL ? 6 : 0);   // kDLFloat / kDLBool / kDLInt
+  const bool uns = dt == NL_U8 || dt == NL_U16 || dt == NL_U32 || dt == NL_U64;
+  o->m.dl_tensor.dtype.code = (dt == NL_F32 || dt == NL_F64) ? 2 : (dt == NL_BOOL ? 6 : (uns ? 1 : 0));   // kDLFloat / kDLBool / kDLUInt / kDLInt
   o->m.dl_tensor.dtype.bits = (uint8_t)(8 * nl_dtype_size(dt));
   o->m.dl_tensor.dtype.lanes = 1;
   o->m.dl_tensor.shape = o->shape;
@@ -180,6 +181,15 @@ static PyObject *_thunk_dlpack(PyThunkObject *self, PyObject *arg) {
   return cap;
 }
 
+// astype(dtype) => lazy conversion to another element type (NumPy's ndarray.astype)
+static PyObject *_thunk_astype(PyThunkObject *self, PyObject *arg) {
+  PyArray_Descr *descr = NULL;
+  if (!PyArray_DescrConverter(arg, &descr)) return NULL;
+  const int t = descr->type_num;
+  Py_DECREF(descr);
+  return PyThunk_AsType(self, t);
+}
+
 struct PyMethodDef thunk_methods[] = {
     {"evaluate", (PyCFunction)_thunk_evaluate, METH_NOARGS, "evaluate() => "},
     {"isevaluated", (PyCFunction)_thunk_isevaluated, METH_NOARGS, "isevaluated() => "},
@@ -190,6 +200,7 @@ struct PyMethodDef thunk_methods[] = {
     {"sum", (PyCFunction)_thunk_sum, METH_NOARGS, "sum() => "},
     {"device_shards", (PyCFunction)_thunk_device_shards, METH_NOARGS,
      "device_shards() => [(device, pointer, first_index, count, typestr), ...] of the evaluated thunk"},
+    {"astype", (PyCFunction)_thunk_astype, METH_O, "astype(dtype) => lazy conversion to another element type"},
     {"__array__", (PyCFunction)(void (*)(void))_thunk_array, METH_VARARGS | METH_KEYWORDS, "__array__(dtype=None, copy=None) => host ndarray (numpy.asarray(thunk))"},
     {"_dlpack", (PyCFunction)_thunk_dlpack, METH_O, "_dlpack(i) => DLPack capsule of shard i (see numpyllvm_b200.DeviceShard)"},
     {NULL, NULL, 0, NULL} /* Sentinel */

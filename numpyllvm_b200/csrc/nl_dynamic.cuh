@@ -12,7 +12,7 @@ namespace nl {
 
 template <typename T, class Prog>
 static pipeline_fn dyn_pick_T(bool vec16, bool compact, bool reduce) {
-  constexpr int V16 = 16 / sizeof(T);
+  constexpr int V16 = wide_v<T>();
   if (vec16) {
     if (compact) return reduce ? pipeline_kernel<T, V16, kRows, true, true, Prog> : pipeline_kernel<T, V16, kRows, true, false, Prog>;
     return reduce ? pipeline_kernel<T, V16, kRows, false, true, Prog> : pipeline_kernel<T, V16, kRows, false, false, Prog>;
@@ -26,13 +26,18 @@ pipeline_fn NL_DYN_CAT(dynamic_kernel_, NL_DYN_SUFFIX)(bool vec16, bool compact,
 }
 
 pipeline_fn NL_DYN_CAT(dynamic_pipe_, NL_DYN_SUFFIX)(int rows) {
-  constexpr int V16 = 16 / sizeof(NL_DYN_T);
-  if (rows == kPipeRowsNarrow) return compact_pipe_kernel<NL_DYN_T, V16, DynSplit, kPipeRowsNarrow>;
-  return compact_pipe_kernel<NL_DYN_T, V16, DynSplit>;
+  if constexpr (sizeof(NL_DYN_T) >= 4) {
+    constexpr int V16 = 16 / sizeof(NL_DYN_T);
+    if (rows == kPipeRowsNarrow) return compact_pipe_kernel<NL_DYN_T, V16, DynSplit, kPipeRowsNarrow>;
+    return compact_pipe_kernel<NL_DYN_T, V16, DynSplit>;
+  } else {
+    (void)rows;
+    return nullptr;
+  }
 }
 
 pipeline_fn NL_DYN_CAT(dynamic_super_, NL_DYN_SUFFIX)(bool uses_temps) {
-  constexpr int V16 = 16 / sizeof(NL_DYN_T);
+  constexpr int V16 = wide_v<NL_DYN_T>();
   return uses_temps ? compact_super_kernel<NL_DYN_T, V16, kRows, DynSplit, true, kMinBlocks>
                     : compact_super_kernel<NL_DYN_T, V16, kRows, DynSplit, false, kMinBlocksLight>;
 }

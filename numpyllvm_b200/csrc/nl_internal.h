@@ -9,6 +9,19 @@ namespace nl {
 
 void set_error(const char *fmt, ...);
 
+// elements of one "wide" row of a thread: 16 bytes for 4- and 8-byte types; the 1- and 2-byte types use rows of
+// four elements (one predicate bit per element and 8-bit packed row counters bound a tile to 32 elements per thread)
+inline int nl_vec_elems(int dtype) {
+  const size_t s = nl_dtype_size(dtype);
+  return s >= 4 ? (int)(16 / s) : 4;
+}
+
+// every value type the pipeline kernels are instantiated for: X(nl_dtype, C type, suffix)
+#define NL_FOR_VALUE_DTYPES(X)                                                                       \
+  X(NL_I32, int32_t, i32) X(NL_I64, long long, i64) X(NL_F32, float, f32) X(NL_F64, double, f64)     \
+  X(NL_I8, signed char, i8) X(NL_I16, short, i16) X(NL_U8, unsigned char, u8) X(NL_U16, unsigned short, u16) \
+  X(NL_U32, unsigned int, u32) X(NL_U64, unsigned long long, u64)
+
 // ---- kernel parameters of the pipeline kernel (passed as __grid_constant__) -------
 struct KParams {
   const void *in[NL_MAX_INPUTS];
@@ -90,6 +103,8 @@ int launch_fill(void *stream, int sm_count, void *dst, int dtype, int64_t first_
 int launch_empty_range(void *stream, const nl_plan *plan, const KParams &kp);
 int launch_gather(void *stream, int sm_count, int dtype, void *out, const int64_t *idx, int64_t count, const void *const *shard_ptr,
                   const int64_t *shard_start, int n_shards, int64_t total, int64_t *bad);
+// nl_cast.cu
+int launch_cast(void *stream, int sm_count, void *dst, int dst_dtype, const void *src, int src_dtype, int64_t n);
 // nl_checksum.cu
 int launch_checksum(void *stream, int sm_count, const void *ptr, size_t nbytes, unsigned long long *out);
 // nl_sort.cu

@@ -99,13 +99,13 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 // synthetic inputs, bit-identical to the oracle's nlo_fill
-template <typename T>
+template <typename T, bool kBool = false>
 __global__ void __launch_bounds__(256) fill_kernel(T *__restrict__ dst, int64_t first_index, int64_t count, uint64_t seed, int kind) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
     const uint64_t z = splitmix64(seed ^ (uint64_t)(first_index + k));
     T v;
-    if constexpr (sizeof(T) == 1) {
+    if constexpr (kBool) {
       v = (T)(z & 1);
     } else if constexpr (!TT<T>::is_float) {
       v = (kind == 0) ? (T)(1 + (((z >> 32) * 99ULL) >> 32)) : (T)(long long)z;
@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(256) fill_kernel(T *__restrict__ dst, int64_t 
     dst[k] = v;
   }
 }
-template <> struct TT<unsigned char> { static constexpr bool is_float = false; };
 
 // ------------------------------------------------------------------ host-side dispatch
 // The interpreter-driven kernels are instantiated per dtype in nl_dynamic_<dtype>.cu (one translation
@@ -127,10 +126,9 @@ template <> struct TT<unsigned char> { static constexpr bool is_float = false; }
 // light variant (fewer registers, one more resident CTA per SM: measured +10-17 %).
 static pipeline_fn pick_dynamic(int dtype, bool vec16, bool compact, bool reduce, bool uses_temps) {
   switch (dtype) {
-    case NL_I32: return dynamic_kernel_i32(vec16, compact, reduce, uses_temps);
-    case NL_I64: return dynamic_kernel_i64(vec16, compact, reduce, uses_temps);
-    case NL_F32: return dynamic_kernel_f32(vec16, compact, reduce, uses_temps);
-    case NL_F64: return dynamic_kernel_f64(vec16, compact, reduce, uses_temps);
+#define NL_CASE(dt, T, sfx) case dt: return dynamic_kernel_##sfx(vec16, compact, reduce, uses_temps);
+    NL_FOR_VALUE_DTYPES(NL_CASE)
+#undef NL_CASE
   }
   return nullptr;
 }
@@ -181,8 +179,8 @@ static pipeline_fn pick(const nl_plan *plan, bool vec16, const char **static_nam
 }
 
 static const char *dt_name(int d) {
-  static const char *n[] = {"bool", "i32", "i64", "f32", "f64"};
-  return (d >= 0 && d <= 4) ? n[d] : "?";
+  static const char *n[] = {"bool", "i32", "i64", "f32", "f64", "i8", "i16", "u8", "u16", "u32", "u64"};
+  return (d >= 0 && d < NL_N_DTYPES) ? n[d] : "?";
 }
 
 #define CUDA_TRY(expr)                                                             \
@@ -197,10 +195,9 @@ static const char *dt_name(int d) {
 // the interpreter's staged compaction pipeline, one per dtype
 static pipeline_fn pick_dynamic_pipe(int dtype, int rows) {
   switch (dtype) {
-    case NL_I32: return dynamic_pipe_i32(rows);
-    case NL_I64: return dynamic_pipe_i64(rows);
-    case NL_F32: return dynamic_pipe_f32(rows);
-    case NL_F64: return dynamic_pipe_f64(rows);
+#define NL_CASE(dt, T, sfx) case dt: return dynamic_pipe_##sfx(rows);
+    NL_FOR_VALUE_DTYPES(NL_CASE)
+#undef NL_CASE
   }
   return nullptr;
 }
@@ -252,10 +249,9 @@ void set_compact_prefer_pipe(int on) { g_prefer_pipe = on; }
 // the interpreter's super-tile kernel
 static pipeline_fn pick_dynamic_super(int dtype, bool uses_temps) {
   switch (dtype) {
-    case NL_I32: return dynamic_super_i32(uses_temps);
-    case NL_I64: return dynamic_super_i64(uses_temps);
-    case NL_F32: return dynamic_super_f32(uses_temps);
-    case NL_F64: return dynamic_super_f64(uses_temps);
+#define NL_CASE(dt, T, sfx) case dt: return dynamic_super_##sfx(uses_temps);
+    NL_FOR_VALUE_DTYPES(NL_CASE)
+#undef NL_CASE
   }
   return nullptr;
 }
@@ -267,7 +263,7 @@ static bool super_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPa
   if (filter < 0) return false;
   const StaticEntry *se = find_static(plan, true);
   const int rows = (se && se->super) ? se->super_rows : kRows;
-  const int64_t tile = (int64_t)kBlock * rows * (int64_t)(16 / nl_dtype_size(plan->dtype));
+  const int64_t tile = (int64_t)kBlock * rows * (int64_t)nl_vec_elems(plan->dtype);
   if (n_elems < tile * kSuperK * sm_count) return false;      // at least one super-tile per SM
   if (kp) {
     kp->super_k = kSuperK;
@@ -303,6 +299,7 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
   if (se && !se->pipe) return false;          // a build-time shape whose plain kernel is the fast one
   const int rows = (cols == 1) ? kPipeRows : kPipeRowsNarrow;
   if (has_static_pipe && se->pipe_rows != rows) return false;   // e.g. a scalar slot of the shape bound to a column
+  if (es < 4) return false;                    // the TMA ring is laid out in 16-byte rows of 4- and 8-byte elements
   const int64_t tile = (int64_t)kPipeConsumers * rows * (int64_t)(16 / es);
   if (n_elems < tile * 2 * sm_count) return false;
   // the side buffer can take a survivor only if everything after the filter works on a bare
@@ -344,7 +341,7 @@ static bool pipe_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPar
 
 int64_t pipeline_tile_elems(const nl_plan *plan, bool vec16, int64_t n_elems, KParams *kp, int sm_count) {
   if (sm_count < 1) sm_count = 148;        // host-only callers (plan descriptions): a B200
-  const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
+  const int v = vec16 ? nl_vec_elems(plan->dtype) : 1;
   KParams local;
   KParams *q = kp ? kp : &local;
   q->super_k = 0;
@@ -363,7 +360,7 @@ int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t
   if (!fn) { set_error("no pipeline kernel for dtype %d", plan->dtype); return NL_ERR_UNSUPPORTED; }
   const bool compact = (plan->flags & NL_PLAN_HAS_COMPACT) != 0;
   const bool reduce = (plan->flags & NL_PLAN_HAS_REDUCE) != 0;
-  const int v = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
+  const int v = vec16 ? nl_vec_elems(plan->dtype) : 1;
   if (name && name_len) {
     if (sname) snprintf(name, name_len, "pipeline_kernel<%s,V=%d,%s%s>", dt_name(plan->dtype), v, strncmp(sname, "family:", 7) ? "static:" : "", sname);
     else snprintf(name, name_len, "pipeline_kernel<%s,V=%d,compact=%d,reduce=%d,dynamic%s>", dt_name(plan->dtype), v, (int)compact, (int)reduce,
@@ -385,7 +382,7 @@ static int launch_compact_pipe(const nl_plan *plan, const KParams &kp, int sm_co
   CUDA_TRY(cudaGetLastError());
   count_launch();
   if (info) {
-    const int v = (int)(16 / nl_dtype_size(plan->dtype));
+    const int v = nl_vec_elems(plan->dtype);
     snprintf(info->kernel, sizeof(info->kernel), "compact_pipe_kernel<%s,V=%d,U=%d,%s%s,slots=%d,lag=%d,side=%d>", dt_name(plan->dtype), v, kp.pipe_rows,
              (e && e->pipe) ? "static:" : "dynamic", (e && e->pipe) ? e->name : "", kp.n_slots, kp.lag, kp.side_cap);
     info->grid = (int)grid;
@@ -415,7 +412,7 @@ static int launch_compact_super(const nl_plan *plan, const KParams &kp, int sm_c
   CUDA_TRY(cudaGetLastError());
   count_launch();
   if (info) {
-    const int v = (int)(16 / nl_dtype_size(plan->dtype));
+    const int v = nl_vec_elems(plan->dtype);
     snprintf(info->kernel, sizeof(info->kernel), "compact_super_kernel<%s,V=%d,U=%d,K=%d,%s%s>", dt_name(plan->dtype), v, kp.super_rows, kp.super_k,
              is_static ? (strncmp(e->name, "family:", 7) ? "static:" : "") : (plan->n_temps > 0 ? "dynamic" : "dynamic-light"), is_static ? e->name : "");
     info->grid = (int)grid;
@@ -447,17 +444,16 @@ int launch_pipeline_kernel(const nl_plan *plan, const KParams &kp, bool vec16, i
     describe_pipeline_kernel(plan, vec16, info->kernel, sizeof(info->kernel), nullptr);
     info->grid = (int)grid;
     info->block = kBlock;
-    info->vec_elems = vec16 ? (int)(16 / nl_dtype_size(plan->dtype)) : 1;
+    info->vec_elems = vec16 ? nl_vec_elems(plan->dtype) : 1;
   }
   return NL_OK;
 }
 
 int launch_empty_range(void *stream, const nl_plan *plan, const KParams &kp) {
   switch (plan->dtype) {
-    case NL_I32: empty_range_kernel<int32_t><<<1, 32, 0, (cudaStream_t)stream>>>(kp); break;
-    case NL_I64: empty_range_kernel<long long><<<1, 32, 0, (cudaStream_t)stream>>>(kp); break;
-    case NL_F32: empty_range_kernel<float><<<1, 32, 0, (cudaStream_t)stream>>>(kp); break;
-    case NL_F64: empty_range_kernel<double><<<1, 32, 0, (cudaStream_t)stream>>>(kp); break;
+#define NL_CASE(dt, T, sfx) case dt: empty_range_kernel<T><<<1, 32, 0, (cudaStream_t)stream>>>(kp); break;
+    NL_FOR_VALUE_DTYPES(NL_CASE)
+#undef NL_CASE
     default: set_error("bad dtype"); return NL_ERR_INVALID;
   }
   CUDA_TRY(cudaGetLastError());
@@ -468,10 +464,9 @@ int launch_empty_range(void *stream, const nl_plan *plan, const KParams &kp) {
 int launch_finalize_partials(void *stream, int rop, int dtype, const void *partials, int n, void *out) {
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case NL_I32: finalize_partials_kernel<int32_t><<<1, 32, 0, st>>>(rop, (const int32_t *)partials, n, (int32_t *)out); break;
-    case NL_I64: finalize_partials_kernel<long long><<<1, 32, 0, st>>>(rop, (const long long *)partials, n, (long long *)out); break;
-    case NL_F32: finalize_partials_kernel<float><<<1, 32, 0, st>>>(rop, (const float *)partials, n, (float *)out); break;
-    case NL_F64: finalize_partials_kernel<double><<<1, 32, 0, st>>>(rop, (const double *)partials, n, (double *)out); break;
+#define NL_CASE(dt, T, sfx) case dt: finalize_partials_kernel<T><<<1, 32, 0, st>>>(rop, (const T *)partials, n, (T *)out); break;
+    NL_FOR_VALUE_DTYPES(NL_CASE)
+#undef NL_CASE
     default: set_error("bad dtype"); return NL_ERR_INVALID;
   }
   CUDA_TRY(cudaGetLastError());
@@ -523,6 +518,7 @@ int launch_gather(void *stream, int sm_count, int dtype, void *out, const int64_
     case 4: gather_kernel<uint32_t><<<(unsigned)blocks, 256, 0, st>>>((uint32_t *)out, (const long long *)idx, count, sh, (unsigned long long *)bad); break;
     case 8: gather_kernel<unsigned long long><<<(unsigned)blocks, 256, 0, st>>>((unsigned long long *)out, (const long long *)idx, count, sh, (unsigned long long *)bad); break;
     case 1: gather_kernel<unsigned char><<<(unsigned)blocks, 256, 0, st>>>((unsigned char *)out, (const long long *)idx, count, sh, (unsigned long long *)bad); break;
+    case 2: gather_kernel<unsigned short><<<(unsigned)blocks, 256, 0, st>>>((unsigned short *)out, (const long long *)idx, count, sh, (unsigned long long *)bad); break;
     default: set_error("nl_gather: bad dtype"); return NL_ERR_INVALID;
   }
   CUDA_TRY(cudaGetLastError());
@@ -552,10 +548,11 @@ static void fill_dispatch(cudaStream_t st, int sm_count, void *dst, int64_t lo, 
 int launch_assign_fill(void *stream, int sm_count, void *dst, int dtype, int64_t lo, int64_t step, int64_t count, uint64_t bits) {
   cudaStream_t st = (cudaStream_t)stream;
   if (count <= 0) return NL_OK;
-  switch (dtype) {
-    case NL_BOOL: fill_dispatch<unsigned char>(st, sm_count, dst, lo, step, count, bits); break;
-    case NL_I32: case NL_F32: fill_dispatch<uint32_t>(st, sm_count, dst, lo, step, count, bits); break;
-    case NL_I64: case NL_F64: fill_dispatch<unsigned long long>(st, sm_count, dst, lo, step, count, bits); break;
+  switch (nl_dtype_size(dtype)) {            // a fill moves bit patterns: the item size is all that matters
+    case 1: fill_dispatch<unsigned char>(st, sm_count, dst, lo, step, count, bits); break;
+    case 2: fill_dispatch<unsigned short>(st, sm_count, dst, lo, step, count, bits); break;
+    case 4: fill_dispatch<uint32_t>(st, sm_count, dst, lo, step, count, bits); break;
+    case 8: fill_dispatch<unsigned long long>(st, sm_count, dst, lo, step, count, bits); break;
     default: set_error("bad dtype"); return NL_ERR_INVALID;
   }
   CUDA_TRY(cudaGetLastError());
@@ -567,10 +564,11 @@ int launch_assign_copy(void *stream, int sm_count, void *dst, int dtype, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   if (count <= 0) return NL_OK;
   const unsigned g = grid_for(count, sm_count);
-  switch (dtype) {
-    case NL_BOOL: assign_copy_kernel<unsigned char><<<g, 256, 0, st>>>((unsigned char *)dst, lo, step, count, (const unsigned char *)src); break;
-    case NL_I32: case NL_F32: assign_copy_kernel<uint32_t><<<g, 256, 0, st>>>((uint32_t *)dst, lo, step, count, (const uint32_t *)src); break;
-    case NL_I64: case NL_F64: assign_copy_kernel<unsigned long long><<<g, 256, 0, st>>>((unsigned long long *)dst, lo, step, count, (const unsigned long long *)src); break;
+  switch (nl_dtype_size(dtype)) {
+    case 1: assign_copy_kernel<unsigned char><<<g, 256, 0, st>>>((unsigned char *)dst, lo, step, count, (const unsigned char *)src); break;
+    case 2: assign_copy_kernel<unsigned short><<<g, 256, 0, st>>>((unsigned short *)dst, lo, step, count, (const unsigned short *)src); break;
+    case 4: assign_copy_kernel<uint32_t><<<g, 256, 0, st>>>((uint32_t *)dst, lo, step, count, (const uint32_t *)src); break;
+    case 8: assign_copy_kernel<unsigned long long><<<g, 256, 0, st>>>((unsigned long long *)dst, lo, step, count, (const unsigned long long *)src); break;
     default: set_error("bad dtype"); return NL_ERR_INVALID;
   }
   CUDA_TRY(cudaGetLastError());
@@ -590,11 +588,10 @@ int launch_fill(void *stream, int sm_count, void *dst, int dtype, int64_t first_
   if (count <= 0) return NL_OK;
   const unsigned g = grid_for(count, sm_count);
   switch (dtype) {
-    case NL_BOOL: fill_kernel<unsigned char><<<g, 256, 0, st>>>((unsigned char *)dst, first_index, count, seed, kind); break;
-    case NL_I32: fill_kernel<int32_t><<<g, 256, 0, st>>>((int32_t *)dst, first_index, count, seed, kind); break;
-    case NL_I64: fill_kernel<long long><<<g, 256, 0, st>>>((long long *)dst, first_index, count, seed, kind); break;
-    case NL_F32: fill_kernel<float><<<g, 256, 0, st>>>((float *)dst, first_index, count, seed, kind); break;
-    case NL_F64: fill_kernel<double><<<g, 256, 0, st>>>((double *)dst, first_index, count, seed, kind); break;
+    case NL_BOOL: fill_kernel<unsigned char, true><<<g, 256, 0, st>>>((unsigned char *)dst, first_index, count, seed, kind); break;
+#define NL_CASE(dt, T, sfx) case dt: fill_kernel<T><<<g, 256, 0, st>>>((T *)dst, first_index, count, seed, kind); break;
+    NL_FOR_VALUE_DTYPES(NL_CASE)
+#undef NL_CASE
     default: set_error("bad dtype"); return NL_ERR_INVALID;
   }
   CUDA_TRY(cudaGetLastError());

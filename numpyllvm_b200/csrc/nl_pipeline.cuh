@@ -56,6 +56,39 @@ template <> struct TT<long long> {
   __device__ static long long lowest() { return LLONG_MIN; }
   __device__ static long long highest() { return LLONG_MAX; }
 };
+// the narrow and the unsigned integer types (getLLVMType's i8 / i16, compiler.cpp:156-167, and the unsigned
+// types it leaves as a todo, :168-172): every operation wraps to the column type like NumPy's, sums run in a
+// 64-bit accumulator of the same signedness and are cast back on store
+template <> struct TT<signed char> {
+  using U = unsigned char; using Acc = long long; static constexpr bool is_float = false;
+  __device__ static signed char lowest() { return SCHAR_MIN; }
+  __device__ static signed char highest() { return SCHAR_MAX; }
+};
+template <> struct TT<short> {
+  using U = unsigned short; using Acc = long long; static constexpr bool is_float = false;
+  __device__ static short lowest() { return SHRT_MIN; }
+  __device__ static short highest() { return SHRT_MAX; }
+};
+template <> struct TT<unsigned char> {
+  using U = unsigned char; using Acc = unsigned long long; static constexpr bool is_float = false;
+  __device__ static unsigned char lowest() { return 0; }
+  __device__ static unsigned char highest() { return UCHAR_MAX; }
+};
+template <> struct TT<unsigned short> {
+  using U = unsigned short; using Acc = unsigned long long; static constexpr bool is_float = false;
+  __device__ static unsigned short lowest() { return 0; }
+  __device__ static unsigned short highest() { return USHRT_MAX; }
+};
+template <> struct TT<unsigned int> {
+  using U = unsigned int; using Acc = unsigned long long; static constexpr bool is_float = false;
+  __device__ static unsigned int lowest() { return 0; }
+  __device__ static unsigned int highest() { return UINT_MAX; }
+};
+template <> struct TT<unsigned long long> {
+  using U = unsigned long long; using Acc = unsigned long long; static constexpr bool is_float = false;
+  __device__ static unsigned long long lowest() { return 0; }
+  __device__ static unsigned long long highest() { return ULLONG_MAX; }
+};
 template <> struct TT<float> {
   using U = uint32_t; using Acc = double; static constexpr bool is_float = true;
   __device__ static float lowest() { return -INFINITY; }
@@ -99,10 +132,14 @@ template <typename T> __device__ __noinline__ T op_floordiv(T a, T b) {
   } else {
     using U = typename TT<T>::U;
     if (b == T(0)) return T(0);
-    if (b == T(-1)) return (T)((U)0 - (U)a);
-    T q = a / b;
-    if ((a % b != T(0)) && ((a < T(0)) != (b < T(0)))) q -= T(1);
-    return q;
+    if constexpr (T(-1) < T(0)) {
+      if (b == T(-1)) return (T)((U)0 - (U)a);
+      T q = (T)(a / b);
+      if ((a % b != T(0)) && ((a < T(0)) != (b < T(0)))) q -= T(1);
+      return q;
+    } else {
+      return (T)(a / b);             // unsigned: truncation is the floor
+    }
   }
 }
 // max/min with NumPy semantics: NaN is sticky
@@ -113,7 +150,11 @@ template <typename T> __device__ __forceinline__ T op_min(T cur, T l) {
   if constexpr (TT<T>::is_float) return (l < cur || l != l) ? l : cur; else return l < cur ? l : cur;
 }
 __device__ __forceinline__ long long acc_add(long long a, long long b) { return (long long)((unsigned long long)a + (unsigned long long)b); }
+__device__ __forceinline__ unsigned long long acc_add(unsigned long long a, unsigned long long b) { return a + b; }
 __device__ __forceinline__ double acc_add(double a, double b) { return a + b; }
+
+// elements of one wide row of a thread (host twin: nl_vec_elems)
+template <typename T> constexpr int wide_v() { return sizeof(T) >= 4 ? (int)(16 / sizeof(T)) : 4; }
 
 // ------------------------------------------------------------------ vector access
 template <int BYTES> struct VecOf;
@@ -175,11 +216,15 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned l
 
 template <typename T> __device__ __forceinline__ T from_bits(uint64_t bits) {
   if constexpr (sizeof(T) == 8) { union { uint64_t b; T t; } u; u.b = bits; return u.t; }
-  else { union { uint32_t b; T t; } u; u.b = (uint32_t)bits; return u.t; }
+  else if constexpr (sizeof(T) == 4) { union { uint32_t b; T t; } u; u.b = (uint32_t)bits; return u.t; }
+  else if constexpr (sizeof(T) == 2) { union { uint16_t b; T t; } u; u.b = (uint16_t)bits; return u.t; }
+  else { union { uint8_t b; T t; } u; u.b = (uint8_t)bits; return u.t; }
 }
 template <typename T> __device__ __forceinline__ unsigned long long to_bits(T v) {
   if constexpr (sizeof(T) == 8) { union { unsigned long long b; T t; } u; u.t = v; return u.b; }
-  else { union { uint32_t b; T t; } u; u.t = v; return u.b; }
+  else if constexpr (sizeof(T) == 4) { union { uint32_t b; T t; } u; u.t = v; return u.b; }
+  else if constexpr (sizeof(T) == 2) { union { uint16_t b; T t; } u; u.t = v; return u.b; }
+  else { union { uint8_t b; T t; } u; u.t = v; return u.b; }
 }
 
 constexpr unsigned long long kDescValueMask = (1ull << 62) - 1;
@@ -1129,19 +1174,14 @@ const StaticEntry *static_table_i32(int *n);
 const StaticEntry *static_table_i64(int *n);
 const StaticEntry *static_table_f32(int *n);
 const StaticEntry *static_table_f64(int *n);
-// per-dtype interpreter-driven instantiations, defined in nl_dynamic_<dtype>.cu
-pipeline_fn dynamic_kernel_i32(bool vec16, bool compact, bool reduce, bool uses_temps);
-pipeline_fn dynamic_pipe_i32(int rows);
-pipeline_fn dynamic_super_i32(bool uses_temps);
-pipeline_fn dynamic_kernel_i64(bool vec16, bool compact, bool reduce, bool uses_temps);
-pipeline_fn dynamic_pipe_i64(int rows);
-pipeline_fn dynamic_super_i64(bool uses_temps);
-pipeline_fn dynamic_kernel_f32(bool vec16, bool compact, bool reduce, bool uses_temps);
-pipeline_fn dynamic_pipe_f32(int rows);
-pipeline_fn dynamic_super_f32(bool uses_temps);
-pipeline_fn dynamic_kernel_f64(bool vec16, bool compact, bool reduce, bool uses_temps);
-pipeline_fn dynamic_pipe_f64(int rows);
-pipeline_fn dynamic_super_f64(bool uses_temps);
+// per-dtype interpreter-driven instantiations, defined in nl_dynamic_<dtype>.cu (the staged pipeline only for
+// the 4- and 8-byte types: its TMA ring is laid out in 16-byte rows)
+#define NL_DECLARE_DYNAMIC(dt, T, sfx)                                                     \
+  pipeline_fn dynamic_kernel_##sfx(bool vec16, bool compact, bool reduce, bool uses_temps); \
+  pipeline_fn dynamic_pipe_##sfx(int rows);                                                 \
+  pipeline_fn dynamic_super_##sfx(bool uses_temps);
+NL_FOR_VALUE_DTYPES(NL_DECLARE_DYNAMIC)
+#undef NL_DECLARE_DYNAMIC
 const StaticEntry *static_table_i32_b(int *n);
 const StaticEntry *static_table_i64_b(int *n);
 const StaticEntry *static_table_f32_b(int *n);

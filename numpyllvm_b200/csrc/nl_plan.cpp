@@ -301,9 +301,10 @@ const char *nl_last_error(void) { return g_err; }
 
 size_t nl_dtype_size(int dtype) {
   switch (dtype) {
-    case NL_BOOL: return 1;
-    case NL_I32: case NL_F32: return 4;
-    case NL_I64: case NL_F64: return 8;
+    case NL_BOOL: case NL_I8: case NL_U8: return 1;
+    case NL_I16: case NL_U16: return 2;
+    case NL_I32: case NL_U32: case NL_F32: return 4;
+    case NL_I64: case NL_U64: case NL_F64: return 8;
   }
   return 0;
 }
@@ -391,8 +392,8 @@ int nl_plan_compile(const nl_expr_node *nodes, int n_nodes, const nl_input_desc 
 }
 
 static const char *dtype_name(int d) {
-  static const char *n[] = {"bool", "i32", "i64", "f32", "f64"};
-  return (d >= 0 && d <= 4) ? n[d] : "?";
+  static const char *n[] = {"bool", "i32", "i64", "f32", "f64", "i8", "i16", "u8", "u16", "u32", "u64"};
+  return (d >= 0 && d < NL_N_DTYPES) ? n[d] : "?";
 }
 
 int nl_plan_dump(const nl_plan *plan, char *buf, size_t buflen) {
@@ -407,7 +408,7 @@ int nl_plan_dump(const nl_plan *plan, char *buf, size_t buflen) {
     if (w > 0) off += (size_t)w;
     if (off >= buflen) off = buflen - 1;
   };
-  static const char *vop[] = {"mul", "add", "sub", "rsub"};
+  static const char *vop[] = {"mul", "add", "sub", "rsub", "div", "rdiv", "floordiv", "rfloordiv"};
   static const char *cop[] = {"ge", "gt", "le", "lt", "eq", "ne"};
   static const char *pop[] = {"and", "or", "xor"};
   static const char *rop[] = {"max", "min", "sum"};
@@ -429,7 +430,7 @@ int nl_plan_dump(const nl_plan *plan, char *buf, size_t buflen) {
       case S_LOAD:   put("  %2d: acc = in%u\n", i, a); break;
       case S_LOADT:  put("  %2d: acc = t%u\n", i, a); break;
       case S_SAVE:   put("  %2d: t%u = acc\n", i, a); break;
-      case S_BIN:    put("  %2d: acc = %s(acc, %s)\n", i, vop[a & 3], src); break;
+      case S_BIN:    put("  %2d: acc = %s(acc, %s)\n", i, vop[a & 7], src); break;
       case S_CMP:    put("  %2d: pacc = %s(acc, %s)\n", i, cop[a % 6], src); break;
       case S_PLOAD:  put("  %2d: pacc = in%u\n", i, a); break;
       case S_PLOADT: put("  %2d: pacc = p%u\n", i, a); break;

@@ -532,14 +532,14 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
   if (!outputs || (plan->n_inputs > 0 && !inputs) || !output_sizes) { set_error("nl_launch_pipeline: null argument"); return NL_ERR_INVALID; }
   if (start < 0 || end < start || thread_nr < 0) { set_error("nl_launch_pipeline: bad range [%lld,%lld) / thread_nr", (long long)start, (long long)end); return NL_ERR_INVALID; }
   const size_t tsize = nl_dtype_size(plan->dtype);
-  if (tsize != 4 && tsize != 8) { set_error("nl_launch_pipeline: bad plan dtype"); return NL_ERR_INVALID; }
+  if (tsize == 0 || plan->dtype == NL_BOOL) { set_error("nl_launch_pipeline: bad plan dtype"); return NL_ERR_INVALID; }
 
   Device &d = g_dev[dev];
   CUDA_TRY(cudaSetDevice(d.id));
 
   KParams kp;
   memset(&kp, 0, sizeof(kp));
-  const int V16 = (int)(16 / tsize);
+  const int V16 = nl_vec_elems(plan->dtype);
   bool vec16 = true;
   for (int k = 0; k < plan->n_inputs; k++) {
     kp.in[k] = inputs[k];
@@ -680,6 +680,14 @@ int nl_gather(int dev, int stream, int dtype, void *out, const int64_t *idx, int
   if (count == 0) return NL_OK;
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
   return launch_gather(g_dev[dev].stream[stream], g_dev[dev].sm_count, dtype, out, idx, count, shard_ptr, shard_start, n_shards, total, bad);
+}
+
+int nl_cast(int dev, int stream, void *dst, int dst_dtype, const void *src, int src_dtype, int64_t count) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (count < 0 || (count > 0 && (!dst || !src))) { set_error("nl_cast: bad argument"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_cast(g_dev[dev].stream[stream], g_dev[dev].sm_count, dst, dst_dtype, src, src_dtype, count);
 }
 
 int nl_checksum(int dev, int stream, const void *ptr, size_t nbytes, uint64_t *out) {

@@ -47,11 +47,13 @@ constexpr int kSortItems = 8;                          // keys per thread per ti
 constexpr int kSortTile = kSortBlock * kSortItems;     // 2048
 constexpr int kSortWarps = kSortBlock / 32;
 
-template <typename UK, bool kFloat>
+template <typename UK, int kFloat>
 __device__ __forceinline__ UK order_key(UK bits) {
   constexpr int B = sizeof(UK) * 8;
   constexpr UK SIGN = (UK)1 << (B - 1);
-  if constexpr (!kFloat) {
+  if constexpr (kFloat == 2) {
+    return bits;                       // unsigned integers already sort by their bit patterns
+  } else if constexpr (kFloat == 0) {
     return bits ^ SIGN;
   } else {
     const UK k = bits ^ ((bits >> (B - 1)) ? (UK)~(UK)0 : SIGN);
@@ -61,7 +63,7 @@ __device__ __forceinline__ UK order_key(UK bits) {
   }
 }
 
-template <typename UK, bool kFloat>
+template <typename UK, int kFloat>
 __global__ void __launch_bounds__(kSortBlock) sort_histogram_kernel(const UK *__restrict__ keys, long long n,
                                                                      unsigned long long *__restrict__ ghist /*[sizeof(UK)][256]*/) {
   constexpr int P = sizeof(UK);
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(kSortBlock) sort_histogram_kernel(const UK *__
 }
 
 // counts of one digit position over the CTA's contiguous chunk -> hist[digit * gridDim.x + cta]
-template <typename UK, bool kFloat>
+template <typename UK, int kFloat>
 __global__ void __launch_bounds__(kSortBlock) chunk_histogram_kernel(const UK *__restrict__ keys, long long n, long long chunk, int shift,
                                                                       unsigned int *__restrict__ hist) {
   __shared__ unsigned int h[256];
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(kSortBlock) chunk_offsets_kernel(const unsigne
   }
 }
 
-template <typename UK, bool kFloat, int ITEMS>
+template <typename UK, int kFloat, int ITEMS>
 __global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) scatter_kernel(const UK *__restrict__ in, UK *__restrict__ out, long long n, long long chunk,
                                                               int shift, const long long *__restrict__ offs) {
   __shared__ unsigned int cnt[kSortWarps][256];     // per warp: keys of each digit seen so far in the tile
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) scatter_kernel(c
   }
 }
 
-template <typename UK, bool kFloat>
+template <typename UK, int kFloat>
 static int sort_impl(cudaStream_t st, int sm_count, void *keys_v, void *tmp_v, int64_t n) {
   constexpr int P = sizeof(UK);
   // keys per thread and tile in the scatter: 16 KB of keys per tile for either key width
@@ -284,10 +286,17 @@ static int sort_impl(cudaStream_t st, int sm_count, void *keys_v, void *tmp_v, i
 int launch_sort(void *stream, int sm_count, int dtype, void *keys, void *tmp, int64_t n) {
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case NL_I32: return sort_impl<uint32_t, false>(st, sm_count, keys, tmp, n);
-    case NL_I64: return sort_impl<unsigned long long, false>(st, sm_count, keys, tmp, n);
-    case NL_F32: return sort_impl<uint32_t, true>(st, sm_count, keys, tmp, n);
-    case NL_F64: return sort_impl<unsigned long long, true>(st, sm_count, keys, tmp, n);
+    // (key kind: 0 signed integer, 1 float, 2 unsigned integer)
+    case NL_I32: return sort_impl<uint32_t, 0>(st, sm_count, keys, tmp, n);
+    case NL_I64: return sort_impl<unsigned long long, 0>(st, sm_count, keys, tmp, n);
+    case NL_F32: return sort_impl<uint32_t, 1>(st, sm_count, keys, tmp, n);
+    case NL_F64: return sort_impl<unsigned long long, 1>(st, sm_count, keys, tmp, n);
+    case NL_I8: return sort_impl<uint8_t, 0>(st, sm_count, keys, tmp, n);
+    case NL_I16: return sort_impl<uint16_t, 0>(st, sm_count, keys, tmp, n);
+    case NL_U8: return sort_impl<uint8_t, 2>(st, sm_count, keys, tmp, n);
+    case NL_U16: return sort_impl<uint16_t, 2>(st, sm_count, keys, tmp, n);
+    case NL_U32: return sort_impl<uint32_t, 2>(st, sm_count, keys, tmp, n);
+    case NL_U64: return sort_impl<unsigned long long, 2>(st, sm_count, keys, tmp, n);
     default: set_error("nl_sort: unsupported dtype %d", dtype); return NL_ERR_UNSUPPORTED;
   }
 }

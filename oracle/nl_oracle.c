@@ -29,6 +29,7 @@
 #define ACC int64_t
 #define SFX i32
 #define IS_FLOAT 0
+#define IS_UNSIGNED 0
 #define T_LOWEST INT32_MIN
 #define T_HIGHEST INT32_MAX
 #include "nl_oracle_eval.inc"
@@ -38,6 +39,7 @@
 #define ACC int64_t
 #define SFX i64
 #define IS_FLOAT 0
+#define IS_UNSIGNED 0
 #define T_LOWEST INT64_MIN
 #define T_HIGHEST INT64_MAX
 #include "nl_oracle_eval.inc"
@@ -47,6 +49,7 @@
 #define ACC double
 #define SFX f32
 #define IS_FLOAT 1
+#define IS_UNSIGNED 0
 #define T_LOWEST (-INFINITY)
 #define T_HIGHEST (INFINITY)
 #include "nl_oracle_eval.inc"
@@ -56,16 +59,79 @@
 #define ACC double
 #define SFX f64
 #define IS_FLOAT 1
+#define IS_UNSIGNED 0
 #define T_LOWEST (-INFINITY)
 #define T_HIGHEST (INFINITY)
+#include "nl_oracle_eval.inc"
+
+/* the narrow and the unsigned integer types */
+#define T int8_t
+#define UT uint8_t
+#define ACC int64_t
+#define SFX i8
+#define IS_FLOAT 0
+#define IS_UNSIGNED 0
+#define T_LOWEST INT8_MIN
+#define T_HIGHEST INT8_MAX
+#include "nl_oracle_eval.inc"
+
+#define T int16_t
+#define UT uint16_t
+#define ACC int64_t
+#define SFX i16
+#define IS_FLOAT 0
+#define IS_UNSIGNED 0
+#define T_LOWEST INT16_MIN
+#define T_HIGHEST INT16_MAX
+#include "nl_oracle_eval.inc"
+
+#define T uint8_t
+#define UT uint8_t
+#define ACC uint64_t
+#define SFX u8
+#define IS_FLOAT 0
+#define IS_UNSIGNED 1
+#define T_LOWEST 0
+#define T_HIGHEST UINT8_MAX
+#include "nl_oracle_eval.inc"
+
+#define T uint16_t
+#define UT uint16_t
+#define ACC uint64_t
+#define SFX u16
+#define IS_FLOAT 0
+#define IS_UNSIGNED 1
+#define T_LOWEST 0
+#define T_HIGHEST UINT16_MAX
+#include "nl_oracle_eval.inc"
+
+#define T uint32_t
+#define UT uint32_t
+#define ACC uint64_t
+#define SFX u32
+#define IS_FLOAT 0
+#define IS_UNSIGNED 1
+#define T_LOWEST 0
+#define T_HIGHEST UINT32_MAX
+#include "nl_oracle_eval.inc"
+
+#define T uint64_t
+#define UT uint64_t
+#define ACC uint64_t
+#define SFX u64
+#define IS_FLOAT 0
+#define IS_UNSIGNED 1
+#define T_LOWEST 0
+#define T_HIGHEST UINT64_MAX
 #include "nl_oracle_eval.inc"
 
 /* ------------------------------------------------------------------------- */
 static size_t dsize(int dtype) {
   switch (dtype) {
-    case NL_BOOL: return 1;
-    case NL_I32: case NL_F32: return 4;
-    case NL_I64: case NL_F64: return 8;
+    case NL_BOOL: case NL_I8: case NL_U8: return 1;
+    case NL_I16: case NL_U16: return 2;
+    case NL_I32: case NL_U32: case NL_F32: return 4;
+    case NL_I64: case NL_U64: case NL_F64: return 8;
   }
   return 0;
 }
@@ -113,12 +179,20 @@ typedef struct {
 static void run_chunk(job_t *jb, int j) {
   int64_t s, e, sizes[NL_MAX_OUTPUTS];
   nlo_partition(jb->size, jb->thread_count, j, &s, &e);
+#define CHUNK(sfx) chunk_##sfx(jb->nodes, jb->n_nodes, jb->in, jb->inputs, jb->outputs, jb->out_space, jb->out_counter_node, jb->n_outputs, s, e, j, sizes)
   switch (jb->value_dtype) {
-    case NL_I32: chunk_i32(jb->nodes, jb->n_nodes, jb->in, jb->inputs, jb->outputs, jb->out_space, jb->out_counter_node, jb->n_outputs, s, e, j, sizes); break;
-    case NL_I64: chunk_i64(jb->nodes, jb->n_nodes, jb->in, jb->inputs, jb->outputs, jb->out_space, jb->out_counter_node, jb->n_outputs, s, e, j, sizes); break;
-    case NL_F32: chunk_f32(jb->nodes, jb->n_nodes, jb->in, jb->inputs, jb->outputs, jb->out_space, jb->out_counter_node, jb->n_outputs, s, e, j, sizes); break;
-    default:     chunk_f64(jb->nodes, jb->n_nodes, jb->in, jb->inputs, jb->outputs, jb->out_space, jb->out_counter_node, jb->n_outputs, s, e, j, sizes); break;
+    case NL_I32: CHUNK(i32); break;
+    case NL_I64: CHUNK(i64); break;
+    case NL_F32: CHUNK(f32); break;
+    case NL_I8: CHUNK(i8); break;
+    case NL_I16: CHUNK(i16); break;
+    case NL_U8: CHUNK(u8); break;
+    case NL_U16: CHUNK(u16); break;
+    case NL_U32: CHUNK(u32); break;
+    case NL_U64: CHUNK(u64); break;
+    default:     CHUNK(f64); break;
   }
+#undef CHUNK
   /* ExecuteFunction bookkeeping (compiler.cpp:88-91) */
   jb->output_starts[j] = s;
   for (int k = 0; k < jb->n_outputs; k++) jb->output_ends[k][j] = sizes[k];
@@ -166,6 +240,12 @@ int nlo_run(const nl_expr_node *nodes, int n_nodes, const nl_input_desc *in, int
         case NL_I32: init_partials_i32(out_op[k], partials[k], thread_count); break;
         case NL_I64: init_partials_i64(out_op[k], partials[k], thread_count); break;
         case NL_F32: init_partials_f32(out_op[k], partials[k], thread_count); break;
+        case NL_I8: init_partials_i8(out_op[k], partials[k], thread_count); break;
+        case NL_I16: init_partials_i16(out_op[k], partials[k], thread_count); break;
+        case NL_U8: init_partials_u8(out_op[k], partials[k], thread_count); break;
+        case NL_U16: init_partials_u16(out_op[k], partials[k], thread_count); break;
+        case NL_U32: init_partials_u32(out_op[k], partials[k], thread_count); break;
+        case NL_U64: init_partials_u64(out_op[k], partials[k], thread_count); break;
         default:     init_partials_f64(out_op[k], partials[k], thread_count); break;
       }
       eff_outputs[k] = partials[k];
@@ -194,6 +274,12 @@ int nlo_run(const nl_expr_node *nodes, int n_nodes, const nl_input_desc *in, int
         case NL_I32: finalize_i32(out_op[k], partials[k], thread_count, outputs[k]); break;
         case NL_I64: finalize_i64(out_op[k], partials[k], thread_count, outputs[k]); break;
         case NL_F32: finalize_f32(out_op[k], partials[k], thread_count, outputs[k]); break;
+        case NL_I8: finalize_i8(out_op[k], partials[k], thread_count, outputs[k]); break;
+        case NL_I16: finalize_i16(out_op[k], partials[k], thread_count, outputs[k]); break;
+        case NL_U8: finalize_u8(out_op[k], partials[k], thread_count, outputs[k]); break;
+        case NL_U16: finalize_u16(out_op[k], partials[k], thread_count, outputs[k]); break;
+        case NL_U32: finalize_u32(out_op[k], partials[k], thread_count, outputs[k]); break;
+        case NL_U64: finalize_u64(out_op[k], partials[k], thread_count, outputs[k]); break;
         default:     finalize_f64(out_op[k], partials[k], thread_count, outputs[k]); break;
       }
       free(partials[k]);
@@ -239,9 +325,14 @@ int nlo_fill(void *dst, int dtype, int64_t first_index, int64_t count, uint64_t 
   for (int64_t k = 0; k < count; k++) {
     uint64_t z = splitmix64(seed ^ (uint64_t)(first_index + k));
     switch (dtype) {
-      case NL_I32: case NL_I64: {
+      case NL_I32: case NL_I64: case NL_I8: case NL_I16: case NL_U8: case NL_U16: case NL_U32: case NL_U64: {
         int64_t v = (kind == 0) ? (int64_t)(1 + (((z >> 32) * 99ULL) >> 32)) : (int64_t)z;
-        if (dtype == NL_I32) ((int32_t *)dst)[k] = (int32_t)v; else ((int64_t *)dst)[k] = v;
+        switch (dsize(dtype)) {          /* the low bytes: the same bits for the signed and the unsigned type */
+          case 1: ((int8_t *)dst)[k] = (int8_t)v; break;
+          case 2: ((int16_t *)dst)[k] = (int16_t)v; break;
+          case 4: ((int32_t *)dst)[k] = (int32_t)v; break;
+          default: ((int64_t *)dst)[k] = v; break;
+        }
         break;
       }
       case NL_F32: {

@@ -511,3 +511,81 @@ def test_cuda_graph_replays_a_chain_of_small_pipelines(nl, rt):
         abi.check(nl.nl_graph_launch(g))
         assert rt.download(res)[0] == ((x2 * 2 + 1) * x2).max()
     abi.check(nl.nl_graph_destroy(g))
+
+
+# ---- the narrow and the unsigned integer types: interpreter kernels vs the oracle ----------------
+NEW_DTYPES = [np.int8, np.int16, np.uint8, np.uint16, np.uint32, np.uint64]
+
+
+@pytest.mark.parametrize("dtype", NEW_DTYPES, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [0, 1, 1023, 4097, 300_001])
+def test_new_integer_types(rt, driver, dtype, n):
+    if driver != "dynamic":
+        pytest.skip("these types have interpreter kernels only")
+    a, b = oracle.fill(dtype, 0, n, 11, 1), oracle.fill(dtype, 0, n, 12, 1)      # full range: everything wraps
+    small = oracle.fill(dtype, 0, n, 13, 0)                                      # [1, 100)
+    cases = []
+    e = Expr(dtype); x, y = e.array(), e.array(); e.materialize(e.sub(e.add(e.mul(x, y), e.scalar(3)), e.ref(y)))
+    cases.append((e, [a, b, None]))
+    e = Expr(dtype); x = e.array(); e.materialize(e.filter(x, e.gt(e.ref(x), e.scalar(50))))
+    cases.append((e, [small, None]))
+    e = Expr(dtype); x, y = e.array(), e.array(); e.materialize(e.filter(y, e.le(x, e.ref(y))))
+    cases.append((e, [a, b]))
+    e = Expr(dtype); x, y = e.array(), e.array(); e.materialize(e.floordiv(x, y))
+    cases.append((e, [a, b]))
+    e = Expr(dtype); x = e.array(); e.materialize(e.ge(e.mul(x, e.scalar(2)), e.scalar(77)))
+    cases.append((e, [a, None, None]))
+    for name in ("max", "min", "sum"):
+        e = Expr(dtype); x = e.array(); e.materialize(getattr(e, name)(x))
+        cases.append((e, [a]))
+        e = Expr(dtype); x = e.array(); e.materialize(getattr(e, name)(e.filter(x, e.lt(e.ref(x), e.scalar(40)))))
+        cases.append((e, [small, None]))
+    for e, ins in cases:
+        want = oracle.run(e, ins, n)
+        got = run_pipeline(rt, e, ins, n)
+        for w, g in zip(want, got):
+            assert w.dtype == g.dtype and w.shape == g.shape and w.tobytes() == g.tobytes()
+
+
+@pytest.mark.parametrize("dtype", NEW_DTYPES, ids=lambda d: np.dtype(d).name)
+def test_new_integer_types_large_filter_runs_the_super_tile_kernel(rt, nl, driver, dtype):
+    if driver != "dynamic":
+        pytest.skip("these types have interpreter kernels only")
+    n = 256 * 4 * 4 * 4 * 148 + 12345           # above one super-tile (4 tiles of 4 rows x 4 elements) per SM
+    a = oracle.fill(dtype, 0, n, 21, 0)
+    e = Expr(dtype); x = e.array(); e.materialize(e.filter(x, e.ge(e.ref(x), e.scalar(30))))
+    (got,) = run_pipeline(rt, e, [a, None], n)
+    assert "compact_super_kernel" in rt.last_launch()[0]
+    assert got.tobytes() == a[a >= dtype(30)].tobytes()
+
+
+ALL_VALUE_DTYPES = DTYPES + NEW_DTYPES
+
+
+@pytest.mark.parametrize("src", ALL_VALUE_DTYPES + [np.bool_], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("dst", ALL_VALUE_DTYPES, ids=lambda d: np.dtype(d).name)
+def test_cast_matches_numpy_astype(nl, rt, src, dst):
+    n = 100_003
+    if src == np.bool_:
+        x = (oracle.fill(np.int64, 0, n, 3, 0) > 50)
+    elif np.dtype(src).kind == "f":
+        x = (oracle.fill(src, 0, n, 3, 3) * 200 - (0 if np.dtype(dst).kind == "u" else 100)).astype(src)   # in range of every target
+    else:
+        x = oracle.fill(src, 0, n, 3, 0 if np.dtype(dst).kind == "f" else 1)
+        if np.dtype(dst).kind == "f" and np.dtype(src).itemsize == 8:
+            x = oracle.fill(src, 0, n, 3, 1)                                      # full range: rounding of 64-bit ints to float
+    d_in = rt.upload(x)
+    d_out = rt.empty(dst, n)
+    abi.check(nl.nl_cast(0, 0, C.c_void_p(d_out.ptr), abi.nl_dtype_of(dst), C.c_void_p(d_in.ptr), abi.nl_dtype_of(x.dtype), n))
+    with np.errstate(invalid="ignore", over="ignore"):
+        want = x.astype(dst)
+    assert rt.download(d_out).tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("dtype", NEW_DTYPES, ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [1000, 300_001])
+def test_sort_new_integer_types(rt, dtype, n):
+    x = oracle.fill(dtype, 0, n, 31, 1)
+    d = rt.upload(x)
+    rt.sort(d)
+    assert rt.download(d).tobytes() == np.sort(x).tobytes()

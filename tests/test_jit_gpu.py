@@ -513,3 +513,64 @@ def test_numpy_and_dlpack_edges():
     m = jit.thunk(np.arange(10)) > 4                 # bool and int shards keep their dtypes
     assert torch.from_dlpack(numpyllvm_b200.device_shards(m)[0]).dtype == torch.bool
     del parts                                         # the capsules kept `t` alive; dropping the tensors releases it
+
+
+# ---- dtypes and NumPy promotion ---------------------------------------------
+@pytest.mark.parametrize("dtype", [np.int8, np.int16, np.uint8, np.uint16, np.uint32, np.uint64], ids=lambda d: np.dtype(d).name)
+def test_narrow_and_unsigned_types_match_numpy(dtype):
+    rng = np.random.default_rng(41)
+    n = 100_003
+    info = np.iinfo(dtype)
+    a_n = rng.integers(info.min, info.max, n, dtype=dtype, endpoint=True)
+    b_n = rng.integers(info.min, info.max, n, dtype=dtype, endpoint=True)
+    a, b = jit.thunk(a_n), jit.thunk(b_n)
+    with np.errstate(over="ignore", divide="ignore"):
+        assert np.array_equal((a * b + 3 - b).asnumpyarray(), a_n * b_n + dtype(3) - b_n)        # wraps like NumPy
+        assert (a * b).asnumpyarray().dtype == dtype
+        assert np.array_equal((-a).asnumpyarray(), -a_n)
+        assert np.array_equal(a[a > b].asnumpyarray(), a_n[a_n > b_n])
+        assert np.array_equal(a[a >= 7].asnumpyarray(), a_n[a_n >= 7])
+        assert np.array_equal((a <= b).asnumpyarray(), a_n <= b_n)
+        bz = np.where(b_n == 0, 1, b_n)
+        assert np.array_equal((a // jit.thunk(bz)).asnumpyarray(), a_n // bz)
+        assert a.max().asnumpyarray()[0] == a_n.max() and a.min().asnumpyarray()[0] == a_n.min()
+        assert a.sum().asnumpyarray()[0] == a_n.sum(dtype=dtype)          # reductions keep the column type (thunk_methods.cpp:164-184)
+    assert np.array_equal(a.sort().asnumpyarray(), np.sort(a_n))
+    t = jit.thunk(a_n)
+    t[5:50:3] = 9
+    a2 = a_n.copy(); a2[5:50:3] = 9
+    assert np.array_equal(t.asnumpyarray(), a2)
+
+
+def test_numpy_promotion_between_columns_and_scalars():
+    rng = np.random.default_rng(43)
+    n = 50_001
+    cols = {dt: rng.integers(1, 100, n).astype(dt) for dt in (np.int8, np.uint8, np.int16, np.int32, np.uint32, np.int64, np.uint64,
+                                                               np.float32, np.float64)}
+    th = {dt: jit.thunk(v) for dt, v in cols.items()}
+    pairs = [(np.int8, np.uint8), (np.int32, np.float32), (np.int16, np.float32), (np.int64, np.uint64), (np.int32, np.int64),
+             (np.uint8, np.float64), (np.uint32, np.int32), (np.float32, np.float64), (np.int8, np.int64)]
+    for l, r in pairs:
+        for op in ("__mul__", "__add__", "__sub__", "__truediv__", "__floordiv__", "__ge__", "__lt__"):
+            want = getattr(cols[l], op)(cols[r])
+            got = getattr(th[l], op)(th[r]).asnumpyarray()
+            assert got.dtype == want.dtype, (l, r, op, got.dtype, want.dtype)
+            if want.dtype.kind == "f":
+                np.testing.assert_array_equal(got, want)
+            else:
+                assert np.array_equal(got, want), (l, r, op)
+    # weak Python scalars, strong NumPy scalars
+    i32, f32 = th[np.int32], th[np.float32]
+    for expr, want in (((i32 * 2.5), cols[np.int32] * 2.5), ((f32 * 2.5), cols[np.float32] * 2.5), ((i32 * 3), cols[np.int32] * 3),
+                       ((i32 / 4), cols[np.int32] / 4), ((i32 * np.int64(5)), cols[np.int32] * np.int64(5)),
+                       ((f32 + np.float64(0.1)), cols[np.float32] + np.float64(0.1)), ((2.0 / f32), 2.0 / cols[np.float32]),
+                       ((i32 > 49.5), cols[np.int32] > 49.5)):
+        got = expr.asnumpyarray()
+        assert got.dtype == want.dtype and np.array_equal(got, want)
+    # a reduction result (device scalar) of one type meeting a column of another
+    s = th[np.int32].sum()
+    assert np.array_equal((th[np.float64] * s).asnumpyarray(), cols[np.float64] * cols[np.int32].sum(dtype=np.int32))
+    # astype() itself, also of a filter result
+    assert np.array_equal(th[np.float64].astype(np.int16).asnumpyarray(), cols[np.float64].astype(np.int16))
+    f = th[np.int64][th[np.int64] > 50].astype(np.float32)
+    assert np.array_equal(f.asnumpyarray(), cols[np.int64][cols[np.int64] > 50].astype(np.float32))

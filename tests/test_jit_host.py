@@ -41,7 +41,11 @@ def test_thunk_rejects_non_arrays_like_the_reference():
     with pytest.raises(TypeError):
         jit.thunk(np.array(["a", "b"]))
     with pytest.raises(TypeError):
-        jit.thunk(np.arange(4, dtype=np.uint16))
+        jit.thunk(np.arange(4, dtype=np.float16))          # f16 is the one getLLVMType entry (compiler.cpp:156-182) not built
+    with pytest.raises(TypeError):
+        jit.thunk(np.arange(4, dtype=np.complex64))
+    for dt in (np.int8, np.int16, np.uint8, np.uint16, np.uint32, np.uint64):
+        assert jit.thunk(np.arange(4, dtype=dt)).isevaluated()
 
 
 def test_lazy_operators_build_thunks_without_computing():
@@ -63,10 +67,8 @@ def test_error_behaviour():
         a[jit.thunk(np.arange(3))]                        # the gather is eager: without a GPU it fails loudly
     with pytest.raises(TypeError):
         a * jit.thunk(np.arange(7))                       # "Incompatible cardinality." (the check Q9 broke)
-    with pytest.raises(TypeError):
-        a * jit.thunk(np.arange(100.0))                   # no implicit promotion between columns (Q3)
-    with pytest.raises(TypeError):
-        a * 2.5                                           # a float scalar is never truncated into ints
+    with pytest.raises(OverflowError):
+        jit.thunk(np.arange(100, dtype=np.int8)) * 1000   # a Python int that does not fit the column type (NumPy 2)
     with pytest.raises(TypeError):
         (a >= 3) * a
     with pytest.raises(TypeError):
@@ -196,3 +198,24 @@ def test_a_column_meeting_a_filter_result_is_split_not_rejected():
     assert "will be split" in jit.plan(a[m] * b[m])
     f = a[a > 5]
     assert "will be split" in jit.plan(f[f < 10])
+
+
+def test_numpy_promotion_builds_lazy_conversions():
+    # two columns of different types meet in NumPy's promoted type; the narrower one goes
+    # through a lazy astype() (a pass of its own), scalars are converted on the host
+    a = jit.thunk(vec())                                   # int64
+    f = jit.thunk(np.arange(100.0))
+    assert jit.plan(a * f).count("base function astype") == 1
+    assert "astype" in jit.plan(a * 2.5)                   # int column, Python float: float64 like NumPy
+    assert "astype" not in jit.plan(f * 2) and "in1: f64 imm" in jit.plan(f * 2)
+    assert jit.plan(a / a).count("base function astype") == 2      # int / int is a float64: both operands are converted
+    assert "astype" not in jit.plan(f / 2)
+    u = jit.thunk(np.arange(100, dtype=np.uint8))
+    i = jit.thunk(np.arange(100, dtype=np.int8))
+    assert jit.plan(u * i).count("base function astype") == 2      # uint8 * int8 -> int16
+    assert "dtype=u8" in jit.plan(u * 3) and "dynamic" in jit.plan(u * 3)      # the new types run on the interpreter
+    assert "dtype=u8" in jit.plan(u[u > 7]) and "dtype=i8" in jit.plan((-i).max())
+    assert a.astype(np.int64) is a                          # a no-op conversion is the thunk itself
+    assert not a.astype(np.float32).isevaluated()
+    with pytest.raises(TypeError):
+        a.astype(np.bool_)

@@ -349,3 +349,26 @@ def test_true_division_is_ieee(dtype):
         ei = Expr(np.int64)
         ei.materialize(ei.div(ei.array(), ei.array()))
         abi.compile_plan(ei)                               # int / int would be a float: rejected
+
+
+# ---- the narrow and the unsigned integer types (PARITY UNPINNED in the reference: pinned against NumPy) ----
+@pytest.mark.parametrize("dtype", [np.int8, np.int16, np.uint8, np.uint16, np.uint32, np.uint64], ids=lambda d: np.dtype(d).name)
+def test_oracle_new_integer_types_match_numpy(dtype):
+    import oracle
+    from numpyllvm_b200.abi import Expr
+    n = 5000
+    a, b = oracle.fill(dtype, 0, n, 1, 1), oracle.fill(dtype, 0, n, 2, 1)      # full range: every op wraps
+    e = Expr(dtype); x, y = e.array(), e.array(); e.materialize(e.sub(e.add(e.mul(x, y), e.scalar(3)), e.ref(y)))
+    with np.errstate(over="ignore"):
+        want = (a * b + dtype(3) - b).astype(dtype)
+    assert np.array_equal(oracle.run(e, [a, b, None], n)[0], want)
+    e = Expr(dtype); x = e.array(); e.materialize(e.filter(x, e.gt(e.ref(x), e.scalar(50))))
+    assert np.array_equal(oracle.run(e, [a, None], n)[0], a[a > dtype(50)])       # unsigned compares for the unsigned types
+    e = Expr(dtype); x, y = e.array(), e.array(); e.materialize(e.floordiv(x, y))
+    with np.errstate(divide="ignore", over="ignore"):
+        want = np.where(b == 0, 0, a // np.where(b == 0, 1, b)).astype(dtype)
+    assert np.array_equal(oracle.run(e, [a, b], n)[0], want)
+    for name in ("max", "min", "sum"):
+        e = Expr(dtype); x = e.array(); e.materialize(getattr(e, name)(x))
+        want = getattr(a, name)() if name != "sum" else a.sum(dtype=dtype)        # reductions keep the column type (and wrap)
+        assert oracle.run(e, [a], n)[0][0] == want
