@@ -189,8 +189,13 @@ static int assign_run(PyThunkObject *self, int64_t lo, int64_t step, int64_t cou
     return 0;
   }
   if (st->ragged && st->shards.size() > 1) {
-    PyErr_SetString(PyExc_ValueError, "assignment into a filtered thunk sharded over several devices is not supported");
-    return -1;
+    // a filter result keeps per-shard runs of different lengths; an index into it means the concatenated array
+    // (what the reference's gather leaves behind, compiler.cpp:36-48): re-cut it into the regular partition first
+    Storage *regular = storage_repartition(st);
+    if (!regular) return -1;
+    storage_decref(self->storage);
+    self->storage = regular;
+    st = regular;
   }
   // a column-valued thunk of the target's dtype stays on the GPUs: the pieces each target shard needs
   // travel device-to-device (NVLink peer copies across GPUs), no host round trip

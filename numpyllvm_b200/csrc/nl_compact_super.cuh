@@ -103,7 +103,12 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) compact_super_kernel(const _
         while (!done) {
           const long long q = j - lane;
           unsigned long long d = (q >= 0) ? ld_relaxed_u64(&p.tile_desc[q * kDescStride]) : kDescPrefix;
-          while ((d >> 62) == 0) d = ld_relaxed_u64(&p.tile_desc[q * kDescStride]);
+          while ((d >> 62) == 0) {
+            // the predecessor has not published yet: polling flat out costs issue slots and L2 bandwidth — and power,
+            // which is what throttles this kernel in long runs
+            if (p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
+            d = ld_relaxed_u64(&p.tile_desc[q * kDescStride]);
+          }
           const uint32_t has_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2);
           const int first = has_prefix ? (__ffs(has_prefix) - 1) : 31;
           unsigned long long v = (lane <= first) ? (d & kDescValueMask) : 0ull;

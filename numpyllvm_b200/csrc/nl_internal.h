@@ -56,6 +56,7 @@ struct KParams {
   int32_t super_k;                    // > 0: super-tile compaction kernel (nl_compact_super.cuh), tiles per super-tile
   int32_t super_rows;                 // ... and its rows per thread
   int32_t super_keep_ctas;            // a CTA that was not among the first `super_keep_ctas` on its SM retires when it meets a dense super-tile
+  uint32_t poll_sleep_ns;             // back-off between two polls of a look-back descriptor (0: none)
   int32_t store_prefix;               // the store pass re-runs the value steps before the filter (nl_step.h: store_pass_needs_prefix)
   // fused multi-GPU finish of a reduction over peer memory (NVLink mailboxes, nl_pipeline.cuh)
   unsigned long long *const *peer_box;   // device array: mailbox of every rank, mapped here (NULL: no fused finish)
@@ -116,6 +117,7 @@ void set_compact_pipe_side(int on);
 void set_compact_pipe_dynamic(int on);
 void set_compact_prefer_pipe(int on);
 void set_max_ctas_per_sm(int n);
+void set_poll_sleep_ns(int v);
 void set_compact_pipe_lag(int l);
 
 void count_launch(int n = 1);

@@ -243,6 +243,8 @@ static int split_point(const nl_plan *plan) {
   return filter;
 }
 
+static int g_poll_sleep_ns = 0;     // tuning: back-off in the look-back poll of the super-tile kernel
+void set_poll_sleep_ns(int v) { g_poll_sleep_ns = v < 0 ? 0 : v; }
 static int g_prefer_pipe = 0;      // tuning: staged pipeline before the super-tile kernel
 void set_compact_prefer_pipe(int on) { g_prefer_pipe = on; }
 
@@ -271,6 +273,7 @@ static bool super_eligible(const nl_plan *plan, bool vec16, int64_t n_elems, KPa
     kp->filter_step = filter;
     kp->n_inputs = plan->n_inputs;
     kp->store_prefix = store_pass_needs_prefix(plan->step, plan->n_steps, filter) ? 1 : 0;
+    kp->poll_sleep_ns = (uint32_t)g_poll_sleep_ns;
   }
   return true;
 }

@@ -969,6 +969,8 @@ int nl_tune(const char *key, int value) {
   } else if (!strcmp(key, "max_ctas_per_sm")) {
     if (value < 0 || value > 32) { set_error("nl_tune(max_ctas_per_sm): 0 (occupancy) .. 32"); return NL_ERR_INVALID; }
     set_max_ctas_per_sm(value);
+  } else if (!strcmp(key, "poll_sleep_ns")) {
+    set_poll_sleep_ns(value);
   } else if (!strcmp(key, "peer_timeout_ms")) {
     set_peer_timeout_ms(value);
   } else if (!strcmp(key, "reset")) {

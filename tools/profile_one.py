@@ -89,6 +89,7 @@ def main():
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--trend", action="store_true", help="time every launch and print the trend over the repetitions")
     ap.add_argument("--tier", type=int, default=1, help="nl_set_static_kernels(): 1 all tiers, 2 families + interpreter, 0 interpreter")
     ap.add_argument("--tune", action="append", default=[], help="nl_tune key=value (repeatable), e.g. compact_kernel=1")
     args = ap.parse_args()
@@ -103,6 +104,16 @@ def main():
     for _ in range(args.warmup):
         rt.launch(plan, outs, ins, 0, n, sizes.ptr)
     rt.sync()
+    if args.trend:
+        evs = [rt.event() for _ in range(args.reps + 1)]
+        rt.record(evs[0])
+        for i in range(args.reps):
+            rt.launch(plan, outs, ins, 0, n, sizes.ptr)
+            rt.record(evs[i + 1])
+        rt.sync()
+        t = [rt.elapsed_ms(evs[i], evs[i + 1]) for i in range(args.reps)]
+        picks = sorted(set(i for i in (0, 1, 2, 5, 10, 20, 40, 80, 120, 160, 199, 299, 399) if i < args.reps))
+        print("  per-launch ms:", " ".join(f"[{i}]{t[i]:.4f}" for i in picks), f" min {min(t):.4f} max {max(t):.4f}")
     e0, e1 = rt.event(), rt.event()
     rt.record(e0)
     for _ in range(args.reps):
