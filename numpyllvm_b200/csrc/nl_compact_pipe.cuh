@@ -172,6 +172,8 @@ struct DynSplit {
   }
   // store pass of the super-tile kernel: do the steps before the filter have to run again? (host: store_pass_needs_prefix)
   static __device__ __forceinline__ bool needs_prefix(const KParams &p) { return p.store_prefix != 0; }
+  static constexpr bool stash_ok = false;        // (the interpreter keeps the two-pass form)
+  static constexpr int stash_output = 0;
 };
 
 template <uint32_t... S>
@@ -217,6 +219,18 @@ struct StaticSplit {
     return store_pass_needs_prefix(st, N, filter_index());
   }
   static __device__ __forceinline__ bool needs_prefix(const KParams &) { return needs_prefix_c(); }
+  // Nothing but the compacted store follows the filter (`a[pred(a)]`): the survivors of a sparse warp-tile can wait
+  // in shared memory between the passes instead of being re-read and re-ranked (compact_super_kernel: stash)
+  NL_HD static constexpr bool stash_ok_c() {
+    constexpr uint32_t st[] = {S...};
+    return filter_index() + 2 == N && step_op(st[N - 1]) == S_STORE && step_b(st[N - 1]) == NL_IDX_COMPACT;
+  }
+  static constexpr bool stash_ok = stash_ok_c();
+  NL_HD static constexpr int stash_output_c() {
+    constexpr uint32_t st[] = {S...};
+    return (int)step_a(st[N - 1]);
+  }
+  static constexpr int stash_output = stash_output_c();
 };
 
 // The same split for a shape family (FamilyProg): the step kinds on either side of the filter are
@@ -248,6 +262,30 @@ struct FamilySplit {
     return store_pass_needs_prefix(st, N, filter_index());
   }
   static __device__ __forceinline__ bool needs_prefix(const KParams &) { return needs_prefix_c(); }
+  // Nothing but the compacted store follows the filter (`a[pred(a)]`): the survivors of a sparse warp-tile can wait
+  // in shared memory between the passes instead of being re-read and re-ranked (compact_super_kernel: stash)
+  // (a family knows which operands are scalars: operators on the survivors may follow the filter — `(a*2+1)[a > t]`)
+  NL_HD static constexpr bool stash_ok_c() {
+    constexpr uint32_t st[] = {K...};
+    if (filter_index() + 2 > N || step_op(st[N - 1]) != S_STORE || step_b(st[N - 1]) != NL_IDX_COMPACT) return false;
+    for (int i = filter_index() + 1; i < N - 1; i++)
+      if (step_op(st[i]) != S_BIN || (step_b(st[i]) & SRC_TEMP) || step_b(st[i]) != FK_SCALAR) return false;
+    return true;
+  }
+  template <typename T>
+  static __device__ __forceinline__ void after_sparse(const KParams &p, T v, long long pos) {
+#pragma unroll
+    for (int i = filter_index() + 1; i < N; i++) {
+      const uint32_t s = p.step[i];
+      sparse_step<T>(p, step_op(s), step_a(s), step_b(s), v, pos);
+    }
+  }
+  static constexpr bool stash_ok = stash_ok_c();
+  NL_HD static constexpr int stash_output_c() {
+    constexpr uint32_t st[] = {K...};
+    return (int)step_a(st[N - 1]);
+  }
+  static constexpr int stash_output = stash_output_c();
 };
 
 // Optional per-role time breakdown (cycles), printed by CTA 0 when built with -DNL_PIPE_STATS.
