@@ -18,10 +18,16 @@ summary of every pipeline row.
 """
 from __future__ import annotations
 
+import os
+
+# NCCL's own log stays on (the driver reads the ranks of the communicator from it); set before anything that might
+# load or initialise NCCL is imported
+os.environ.setdefault("NCCL_DEBUG", "INFO")
+os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+
 import argparse
 import ctypes as C
 import json
-import os
 import statistics
 import subprocess
 import sys
@@ -178,8 +184,6 @@ def run_gpu(args):
     # NCCL's own log stays on (the driver reads the ranks of the communicator from it).  NCCL prints to
     # the process's stdout, and the JSON line is the only thing this arm may print there: file descriptor 1
     # is pointed at stderr for everything native, the line itself goes out through a private copy.
-    os.environ.setdefault("NCCL_DEBUG", "INFO")
-    os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     sys.stdout.flush()
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
@@ -189,6 +193,11 @@ def run_gpu(args):
     abi.check(lib.nl_init(1, dev_ids))          # one rank drives one GPU
     rt = Runtime.get(1)
     ranks.init_library_comm(lib)                # NCCL communicator for the data-path collectives
+    if ranks.world > 1:
+        # this repo's own note beside NCCL's INFO lines: what the library's communicator looks like from this rank
+        print(f"[numpyllvm_b200] rank {ranks.rank}: libnlkernels communicator ready, nranks {lib.nl_comm_world_size()}, "
+              f"cudaDev {ranks.local_rank}, NVLink mailboxes {'mapped (fused in-kernel finish)' if lib.nl_comm_peer_ready() else 'not available (NCCL finish)'}",
+              file=sys.stderr, flush=True)
     peak, peak_src = measured_peak()
     G = ranks.world
     n = 1 << args.log2n           # elements per GPU (weak scaling)
@@ -334,6 +343,10 @@ def run_gpu(args):
     if ranks.rank == 0:
         print(json.dumps(result), file=json_out, flush=True)
     ranks.finish()
+    try:
+        C.CDLL(None).fflush(None)               # NCCL logs through C stdio, which is fully buffered on a pipe
+    except Exception:
+        pass
 
 
 def load_traffic(key):
