@@ -12,8 +12,11 @@ from numpyllvm_b200 import abi  # noqa: E402
 from numpyllvm_b200.device import Runtime  # noqa: E402
 
 log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 28
+algo = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 n = 1 << log2n
 rt = Runtime.get(1)
+abi.check(rt.lib.nl_tune(b"sort_algo", algo))
+print(f"sort_algo={algo}")
 for dtype, kind, label in ((np.int64, 1, "i64 full range"), (np.int64, 0, "i64 in [1,100)"), (np.float64, 3, "f64 [0,1)"),
                            (np.int32, 1, "i32 full range"), (np.float32, 3, "f32 [0,1)")):
     x = rt.empty(dtype, n)
@@ -30,9 +33,10 @@ for dtype, kind, label in ((np.int64, 1, "i64 full range"), (np.int64, 0, "i64 i
         rt.sync()
         best = min(best, rt.elapsed_ms(e0, e1))
         launches = rt.lib.nl_launch_count() - before
-    passes = (launches - 1) // 3
+    per_pass = 1 if algo else 3
+    passes = (launches - 1) // per_pass
     es = np.dtype(dtype).itemsize
-    traffic = n * es * (1 + 3 * passes + (2 if passes % 2 else 0))
+    traffic = n * es * (1 + (2 if algo else 3) * passes + (2 if passes % 2 else 0))
     head = rt.download(x, 4096)
     assert np.all(head[:-1] <= head[1:])
     print(f"{label:16s} n=2^{log2n}: {best:8.3f} ms  {n / best / 1e6:7.2f} Gkeys/s  {passes} passes  {traffic / best / 1e6:7.0f} GB/s of pass traffic")
