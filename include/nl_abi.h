@@ -432,9 +432,10 @@ NL_API int nl_set_static_kernels(int mode);
  *   "pipe_side_buffers"  0: no side buffers in the staged pipeline (default 1)
  *   "pipe_lag"           tiles between count and store phase of the staged pipeline (0: half the ring)
  *   "max_ctas_per_sm"    cap on resident CTAs per SM of the streaming kernels (0: by occupancy)
- *   "sort_algo"          radix sort: 0 count + scatter per digit position (default); 1 one sweep per position
- *                        (decoupled look-back over tile histograms; measured slower, nl_sort.cu); 2 one sweep with
- *                        match.any ranking
+ *   "sort_algo"          radix sort of 4- and 8-byte keys: 0 one sweep per digit position (default: decoupled look-back over
+ *                        tile histograms, 16 B per 8-byte key and position); 1 count + scatter per position (24 B; always
+ *                        used for 1- and 2-byte keys)
+ *   "sort_portion_log2"  keys per launch of the one-sweep form (13..28; 0: default 28) — the tests shrink it to chain launches
  *   "poll_sleep_ns"      back-off between two polls of a look-back descriptor in the super-tile kernel (default 0)
  *   "peer_timeout_ms"    how long a fused multi-GPU finish waits for a peer's mailbox slot before it gives up
  *                        and the next synchronisation returns NL_ERR_NCCL (default 10000; 0: default)

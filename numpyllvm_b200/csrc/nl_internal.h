@@ -119,6 +119,7 @@ void set_compact_prefer_pipe(int on);
 void set_max_ctas_per_sm(int n);
 void set_poll_sleep_ns(int v);
 void set_sort_algo(int a);
+void set_sort_portion_log2(int l);
 void set_compact_pipe_lag(int l);
 
 void count_launch(int n = 1);

@@ -970,8 +970,11 @@ int nl_tune(const char *key, int value) {
     if (value < 0 || value > 32) { set_error("nl_tune(max_ctas_per_sm): 0 (occupancy) .. 32"); return NL_ERR_INVALID; }
     set_max_ctas_per_sm(value);
   } else if (!strcmp(key, "sort_algo")) {
-    if (value < 0 || value > 2) { set_error("nl_tune(sort_algo): 0 count + scatter (default), 1 one sweep, 2 one sweep with match.any"); return NL_ERR_INVALID; }
+    if (value < 0 || value > 1) { set_error("nl_tune(sort_algo): 0 one sweep per position (default), 1 count + scatter"); return NL_ERR_INVALID; }
     set_sort_algo(value);
+  } else if (!strcmp(key, "sort_portion_log2")) {
+    if (value != 0 && (value < 13 || value > 28)) { set_error("nl_tune(sort_portion_log2): 13 .. 28 (0: default 28)"); return NL_ERR_INVALID; }
+    set_sort_portion_log2(value ? value : 28);
   } else if (!strcmp(key, "poll_sleep_ns")) {
     set_poll_sleep_ns(value);
   } else if (!strcmp(key, "peer_timeout_ms")) {
@@ -979,7 +982,7 @@ int nl_tune(const char *key, int value) {
   } else if (!strcmp(key, "reset")) {
     set_peer_timeout_ms(0);
     set_compact_pipe_enabled(1); set_compact_prefer_pipe(0); set_compact_pipe_dynamic(0); set_compact_pipe_side(1);
-    set_compact_pipe_lag(0); set_max_ctas_per_sm(0); set_poll_sleep_ns(0); set_sort_algo(0);
+    set_compact_pipe_lag(0); set_max_ctas_per_sm(0); set_poll_sleep_ns(0); set_sort_algo(0); set_sort_portion_log2(28);
   } else {
     set_error("nl_tune: unknown key '%s'", key);
     return NL_ERR_INVALID;

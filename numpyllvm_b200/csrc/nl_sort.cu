@@ -13,7 +13,8 @@
 //                                                   keys regrouped by digit in shared memory so
 //                                                   that global stores form runs)
 //
-// Traffic per executed pass: 8 B read (counts) + 8 B read + 8 B write (scatter) per 8-byte key.
+// Traffic per executed pass: 8 B read (counts) + 8 B read + 8 B write (scatter) per 8-byte key for this form;
+// 4- and 8-byte keys take the one-sweep form below instead (8 B read + 8 B write).
 // Keys are compared through an order-preserving bijection of their bit patterns (sign flip for
 // ints; the usual float flip, rotated so that negative NaNs also land at the end like NumPy's
 // sort puts every NaN last); the stored values are the original bits.
@@ -245,12 +246,28 @@ __global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) scatter_kernel(c
   }
 }
 
-// ---- one sweep per digit position ------------------------------------------------------------------------
-// The per-position counting pass is gone: a tile's digit histogram is chained to its predecessors' with a decoupled
-// look-back (one 32-bit descriptor per tile and digit: 2 status bits + 30 count bits), so every executed position
-// reads the keys once and writes them once — 16 B per 8-byte key instead of 24.  Tiles are handed out by a ticket,
-// so every predecessor of a tile belongs to a running CTA.  The in-tile ranking is the scatter kernel's.
+// ---- one sweep per digit position (4- and 8-byte keys) ---------------------------------------------------------
+// Every executed position reads the keys once from HBM and writes them once: 16 B per 8-byte key instead of the 24 B of
+// count + scatter.  A tile's 256 digit counts are chained to its predecessors' with a decoupled look-back (one 32-bit
+// descriptor per tile and digit: 2 status bits + 30 count bits; tiles are handed out by a ticket, so every predecessor
+// belongs to a running CTA).  What tools/sort_lab.cu measured on B200 (2^28 keys, ms per position, 64-bit keys):
+//   * keys held in registers from the load to the regrouping: 1.59-1.86 whatever the ranking (eight ballots, shared
+//     atomicOr, match.any 2.56) and whatever the tile (2048..8192 keys): 80 registers, 24 warps per SM, and a CTA that
+//     waits 2-3 us for the look-back of a 4096-key tile with nothing else to do (the same kernel with the look-back
+//     faked: 1.34);
+//   * THIS form: no key stays in a register across a barrier.  The tile is read twice — once to count (digit ->
+//     shared atomic on the warp's histogram), and, when the counts are public and turned into running slots of the
+//     regrouped tile, again (from L2, batches of CH keys in flight) to rank: eight ballots find the lanes with the same
+//     digit, one LDS + one STS per key advance the warp's slot, and the key goes straight to its place in shared
+//     memory.  64-77 registers with 6144/8192-key tiles -> 1.18 ms (64-bit, 26 Gkeys/s for a full sort; CUB's
+//     DeviceRadixSort 12.2) and 0.84 ms (32-bit, 71 Gkeys/s; CUB 45.5).
+//   * a look-back window of 4 tiles per round trip is best (1: 3.2 ms, 2: 2.0, 8: +5 %, 16: +25 %).
+// The ballots are PTX with immediate masks: ptxas then moves the eight digit bits into predicates with one R2P and
+// spends VOTE + 2 LOP3 per bit (25 instructions per key; the C++ form compiled to 6 per bit).
 constexpr unsigned int kSweepAgg = 1u << 30, kSweepPrefix = 2u << 30, kSweepMask = (1u << 30) - 1u;
+constexpr int kSweepWindow = 4;
+static long long g_sweep_portion = 1ll << 28;     // keys per launch: a tile's running digit offsets stay below 2^30 (tests shrink it)
+void set_sort_portion_log2(int l) { g_sweep_portion = 1ll << l; }
 
 __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
   unsigned int v;
@@ -261,173 +278,270 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v) 
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-template <typename UK, int kFloat, int ITEMS, bool kMatch>
-__global__ void __launch_bounds__(kSortBlock, NL_SORT_MIN_CTAS) onesweep_kernel(const UK *__restrict__ in, UK *__restrict__ out, long long n, int shift,
-                                                               const unsigned long long *__restrict__ ghist_pass /*[256]*/,
-                                                               unsigned int *__restrict__ desc /*[n_tiles][256], zeroed*/,
-                                                               unsigned int *__restrict__ ticket /*zeroed*/, int n_tiles) {
-  constexpr int TILE = kSortBlock * ITEMS;
-  __shared__ unsigned int cnt[kSortWarps][256];     // per warp: keys of each digit seen so far in the tile
-  __shared__ unsigned int tile_start[256];          // exclusive scan of the tile's digit counts
-  __shared__ long long goff[256];                   // where this tile's run of each digit starts in the output
-  __shared__ long long digit_start[256];            // where each digit starts in the output (exclusive scan of the global histogram)
-  __shared__ UK staged[TILE];
-  __shared__ unsigned int wsum[kSortWarps];
-  __shared__ int sh_tile;
+template <int B>
+__device__ __forceinline__ unsigned int same_bit(unsigned int d) {
+  unsigned int x;
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t, bal, s;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tvote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+      "selp.b32 s, 0, 0xffffffff, p;\n\txor.b32 %0, bal, s;\n\t}"
+      : "=r"(x) : "r"(d), "n"(1u << B));
+  return x;
+}
+// lanes of the (converged) warp whose 8-bit digit equals mine
+__device__ __forceinline__ unsigned int match_digit(unsigned int d) {
+  return same_bit<0>(d) & same_bit<1>(d) & same_bit<2>(d) & same_bit<3>(d) & same_bit<4>(d) & same_bit<5>(d) & same_bit<6>(d) & same_bit<7>(d);
+}
 
+struct SweepShared {             // views into the CTA's dynamic shared memory
+  void *staged;                  // the tile regrouped by digit
+  unsigned int (*cnt)[256];      // per warp: digit counts, then the warp's next slot of each digit
+  long long *gdelta;             // per digit: (start of the tile's run in the output) - (start of the run in the tile)
+  unsigned int *wsum;
+  int *next_tile;
+};
+
+template <typename UK, int kFloat, int ITEMS, int CH, bool FULL>
+__device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, int shift, long long dstart,
+                                           unsigned long long *__restrict__ bins_out, unsigned int *__restrict__ desc, unsigned int *__restrict__ ticket,
+                                           int tile, int n_tiles, const SweepShared &sh) {
+  constexpr int WARPS = kSortWarps, TILE = kSortBlock * ITEMS, W = kSweepWindow;
+  static_assert(ITEMS % CH == 0, "the tile is read in whole batches");
+  UK *staged = (UK *)sh.staged;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned int lt = (1u << lane) - 1u;
-  {
-    // exclusive scan of the 256 global digit counts (once per CTA)
-    const long long c = (long long)ghist_pass[tid];
-    long long incl = c;
+  const unsigned int base = (unsigned int)tile * TILE;
+  const int valid = FULL ? TILE : (int)(n - base);
+  unsigned int *cw = &sh.cnt[warp][0];
+  // warp-striped keys: item i of lane l in warp w is tile element w*32*ITEMS + i*32 + l, so the order (warp, item, lane)
+  // is the input order and the ranking below is stable
+  const UK *src = in + base + warp * (32 * ITEMS) + lane;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
+  for (int i0 = 0; i0 < ITEMS; i0 += CH) {
+    UK key[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+      if (FULL) key[i] = __ldcg(src + (i0 + i) * 32);      // stays in L2 for the second read
+      else key[i] = (warp * (32 * ITEMS) + (i0 + i) * 32 + lane < valid) ? src[(i0 + i) * 32] : (UK)0;
     }
-    __shared__ long long wtot[kSortWarps];
-    if (lane == 31) wtot[warp] = incl;
-    __syncthreads();
-    long long wbase = 0;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; w++)
-      if (w < warp) wbase += wtot[w];
-    digit_start[tid] = wbase + incl - c;
+    for (int i = 0; i < CH; i++) {
+      const unsigned int d = (unsigned int)(order_key<UK, kFloat>(key[i]) >> shift) & 0xff;
+      if (FULL || (warp * (32 * ITEMS) + (i0 + i) * 32 + lane < valid)) atomicAdd(&cw[d], 1u);
+    }
   }
-
-  while (true) {
-    __syncthreads();
-    if (tid == 0) sh_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  // thread d: digit d's counts of the warps; the tile's count goes public before anything else happens
+  unsigned int run = 0, excl, c[WARPS];
+  unsigned int *mine = desc + (size_t)tile * 256 + tid;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; w++) cnt[w][tid] = 0;
-    __syncthreads();
-    const int tile = sh_tile;
-    if (tile >= n_tiles) break;
-    const long long base = (long long)tile * TILE;
-    const int valid = (int)((n - base < TILE) ? (n - base) : TILE);
-
-    // warp-striped keys: item i of lane l in warp w is tile element w*32*ITEMS + i*32 + l, so the order
-    // (warp, item, lane) is the input order and the ranking below is stable
-    UK key[ITEMS];
-    unsigned int rank[ITEMS];
-    int dig[ITEMS];
+  for (int w = 0; w < WARPS; w++) c[w] = sh.cnt[w][tid];
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-      const int e = warp * (32 * ITEMS) + i * 32 + lane;
-      const bool ok = e < valid;
-      key[i] = ok ? in[base + e] : (UK)0;
-      dig[i] = ok ? (int)((order_key<UK, kFloat>(key[i]) >> shift) & 0xff) : -1;
-    }
-#pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-      const bool ok = dig[i] >= 0;
-      unsigned int m;
-      if constexpr (kMatch) {
-        m = __match_any_sync(0xffffffffu, dig[i]);
-      } else {
-        m = __ballot_sync(0xffffffffu, ok);
-#pragma unroll
-        for (int b = 0; b < 8; b++) {
-          const bool bit = (dig[i] >> b) & 1;
-          const unsigned int bal = __ballot_sync(0xffffffffu, bit);
-          m &= bit ? bal : ~bal;
-        }
-      }
-      unsigned int before = 0;
-      if (ok) before = cnt[warp][dig[i]];
-      __syncwarp();
-      rank[i] = before + __popc(m & lt);
-      if (ok && (m & lt) == 0) cnt[warp][dig[i]] = before + __popc(m);
-      __syncwarp();
-    }
-    __syncthreads();
-    // thread d: digit d's counts of the warps -> exclusive over the warps, total of the tile
-    unsigned int run = 0;
-#pragma unroll
-    for (int w = 0; w < kSortWarps; w++) {
-      const unsigned int c = cnt[w][tid];
-      cnt[w][tid] = run;
-      run += c;
-    }
-    // publish this tile's count of digit d, then chain it to the predecessors'
-    unsigned int *mine = desc + (size_t)tile * 256 + tid;
-    unsigned long long excl = 0;
-    if (tile == 0) {
-      st_relaxed_u32(mine, kSweepPrefix | run);
-    } else {
-      st_relaxed_u32(mine, kSweepAgg | run);
-      for (int t = tile - 1;; t--) {
-        const unsigned int *pd = desc + (size_t)t * 256 + tid;
-        unsigned int d = ld_relaxed_u32(pd);
-        while ((d >> 30) == 0) d = ld_relaxed_u32(pd);
-        excl += d & kSweepMask;
-        if ((d >> 30) == 2) break;
-      }
-      st_relaxed_u32(mine, kSweepPrefix | (unsigned int)((excl + run) & kSweepMask));
-    }
-    goff[tid] = digit_start[tid] + (long long)excl;
-    // exclusive scan of the 256 digit totals of the tile
+  for (int w = 0; w < WARPS; w++) run += c[w];
+  if (tile > 0) st_relaxed_u32(mine, kSweepAgg | run);
+  {
     unsigned int incl = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
+    if (lane == 31) sh.wsum[warp] = incl;
+    excl = incl - run;
+  }
+  __syncthreads();
+  {
     unsigned int wbase = 0;
 #pragma unroll
-    for (int w = 0; w < kSortWarps; w++)
-      if (w < warp) wbase += wsum[w];
-    tile_start[tid] = wbase + incl - run;
-    __syncthreads();
+    for (int w = 0; w < WARPS; w++)
+      if (w < warp) wbase += sh.wsum[w];
+    excl += wbase;                       // where digit tid starts in the regrouped tile
+    unsigned int slot = excl;
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++)
-      if (dig[i] >= 0) staged[tile_start[dig[i]] + cnt[warp][dig[i]] + rank[i]] = key[i];
-    __syncthreads();
+    for (int w = 0; w < WARPS; w++) {    // the counters become the warps' next free slot of the digit
+      sh.cnt[w][tid] = slot;
+      slot += c[w];
+    }
+  }
+  __syncthreads();
 #pragma unroll
-    for (int i = 0; i < ITEMS; i++) {
-      const int pos = i * kSortBlock + tid;
-      if (pos < valid) {
-        const UK k = staged[pos];
-        const int d = (int)((order_key<UK, kFloat>(k) >> shift) & 0xff);
-        out[goff[d] + (long long)(pos - (int)tile_start[d])] = k;
+  for (int i0 = 0; i0 < ITEMS; i0 += CH) {
+    UK key[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+      if (FULL) key[i] = __ldcs(src + (i0 + i) * 32);
+      else key[i] = (warp * (32 * ITEMS) + (i0 + i) * 32 + lane < valid) ? src[(i0 + i) * 32] : (UK)0;
+    }
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+      const unsigned int d = (unsigned int)(order_key<UK, kFloat>(key[i]) >> shift) & 0xff;
+      const bool ok = FULL || (warp * (32 * ITEMS) + (i0 + i) * 32 + lane < valid);
+      unsigned int m = match_digit(d);
+      if (!FULL) m &= __ballot_sync(0xffffffffu, ok);
+      unsigned int before = 0;
+      if (ok) before = cw[d];
+      __syncwarp();
+      if (ok && (m & lt) == 0) cw[d] = before + __popc(m);
+      if (ok) staged[before + __popc(m & lt)] = key[i];
+      __syncwarp();
+    }
+  }
+  if (tid == 0) *sh.next_tile = (int)atomicAdd(ticket, 1u);
+  {
+    // chain the tile's counts to its predecessors': W descriptors per round trip
+    unsigned long long before = 0;
+    if (tile > 0) {
+      int t = tile - 1;
+      while (true) {
+        unsigned int look[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) look[j] = (t - j >= 0) ? ld_relaxed_u32(desc + (size_t)(t - j) * 256 + tid) : kSweepPrefix;
+        bool done = false;
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+          if (!done) {
+            unsigned int v = look[j];
+            while ((v >> 30) == 0) v = ld_relaxed_u32(desc + (size_t)(t - j) * 256 + tid);
+            before += v & kSweepMask;
+            if ((v >> 30) == 2) done = true;
+          }
+        }
+        if (done) break;
+        t -= W;
       }
+    }
+    st_relaxed_u32(mine, kSweepPrefix | (unsigned int)(before + run));
+    sh.gdelta[tid] = dstart + (long long)before - (long long)excl;
+    if (tile == n_tiles - 1 && bins_out) bins_out[tid] = (unsigned long long)(dstart + (long long)before + (long long)run);   // where the next launch continues
+  }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < WARPS; w++) sh.cnt[w][tid] = 0;
+#pragma unroll
+  for (int i = 0; i < ITEMS; i++) {
+    const int pos = i * kSortBlock + tid;
+    if (FULL || pos < valid) {
+      const UK k = staged[pos];
+      const unsigned int d = (unsigned int)(order_key<UK, kFloat>(k) >> shift) & 0xff;
+      out[sh.gdelta[d] + (long long)pos] = k;
     }
   }
 }
 
-// Measured on B200, 2^28 keys (tools/sort_bench.py): count + scatter 13.5 Gkeys/s (i64) / 29.6 (i32); one sweep
-// 12.3 / 25.5; one sweep with match.any 10.4 / 22.0.  With 2048-key tiles the per-tile look-back (256 chains, 1 KB of
-// descriptors per tile, a 128 MB memset per position) costs more than the counting pass it removes (13 % of a
-// position), and the ranking — not memory — bounds the scatter either way.  The counting form stays the default.
-static int g_sort_algo = 0;          // 0: count + scatter per position (default); 1: one sweep per position; 2: one sweep with match.any
+template <typename UK, int kFloat, int ITEMS, int CH>
+__device__ __noinline__ void sweep_partial_tile(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, int shift, long long dstart,
+                                                unsigned long long *__restrict__ bins_out, unsigned int *__restrict__ desc, unsigned int *__restrict__ ticket,
+                                                int tile, int n_tiles, const SweepShared &sh) {
+  sweep_tile<UK, kFloat, ITEMS, CH, false>(in, out, n, shift, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
+}
+
+template <typename UK, int kFloat, int ITEMS, int CH, int MINCTAS>
+__global__ void __launch_bounds__(kSortBlock, MINCTAS) onesweep_kernel(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, int shift,
+                                                                       const unsigned long long *__restrict__ bins_in /*[256]: where each digit continues in out*/,
+                                                                       unsigned long long *__restrict__ bins_out /*[256] for the next launch, or null*/,
+                                                                       unsigned int *__restrict__ desc /*[n_tiles][256], zeroed*/,
+                                                                       unsigned int *__restrict__ ticket /*zeroed*/, int n_tiles) {
+  constexpr int TILE = kSortBlock * ITEMS;
+  extern __shared__ __align__(16) unsigned char sweep_smem[];
+  __shared__ int sh_tile;
+  SweepShared sh;
+  sh.staged = sweep_smem;
+  sh.cnt = (unsigned int(*)[256])((UK *)sweep_smem + TILE);
+  sh.gdelta = (long long *)(sh.cnt + kSortWarps);
+  sh.wsum = (unsigned int *)(sh.gdelta + 256);
+  sh.next_tile = &sh_tile;
+  const int tid = threadIdx.x;
+  const long long dstart = (long long)bins_in[tid];
+#pragma unroll
+  for (int w = 0; w < kSortWarps; w++) sh.cnt[w][tid] = 0;
+  if (tid == 0) sh_tile = (int)atomicAdd(ticket, 1u);
+  while (true) {
+    __syncthreads();
+    const int tile = sh_tile;
+    if (tile >= n_tiles) break;
+    if ((unsigned int)(tile + 1) * TILE <= n)
+      sweep_tile<UK, kFloat, ITEMS, CH, true>(in, out, n, shift, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
+    else
+      sweep_partial_tile<UK, kFloat, ITEMS, CH>(in, out, n, shift, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
+  }
+}
+
+// one CTA per digit position: where each digit starts in the output (exclusive scan of the position's histogram)
+__global__ void __launch_bounds__(kSortBlock) digit_starts_kernel(const unsigned long long *__restrict__ ghist, unsigned long long *__restrict__ bins /*[P][2][256]*/) {
+  __shared__ unsigned long long part[kSortWarps];
+  const int p = blockIdx.x, d = threadIdx.x, lane = d & 31, warp = d >> 5;
+  const unsigned long long c = ghist[p * 256 + d];
+  unsigned long long incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) part[warp] = incl;
+  __syncthreads();
+  unsigned long long wbase = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; w++)
+    if (w < warp) wbase += part[w];
+  bins[(size_t)p * 512 + d] = wbase + incl - c;
+}
+
+template <int BYTES> struct SweepShape;                  // keys per thread, keys per batch of the second read, resident CTAs per SM
+template <> struct SweepShape<8> { static constexpr int items = 24, batch = 8, ctas = 3; };
+template <> struct SweepShape<4> { static constexpr int items = 32, batch = 16, ctas = 4; };
+
+static int g_sort_algo = 0;          // 0: one sweep per position for 4- and 8-byte keys (default); 1: count + scatter per position
 void set_sort_algo(int a) { g_sort_algo = a; }
+
+// all non-trivial positions of a 4- or 8-byte key, one sweep each
+template <typename UK, int kFloat>
+static int onesweep_passes(cudaStream_t st, int sm_count, UK *&src, UK *&dst, int64_t n, const unsigned long long *ghist, const unsigned long long *host_hist) {
+  constexpr int P = sizeof(UK);
+  using Shape = SweepShape<sizeof(UK)>;
+  constexpr int ITEMS = Shape::items, TILE = kSortBlock * ITEMS;
+  auto kern = onesweep_kernel<UK, kFloat, ITEMS, Shape::batch, Shape::ctas>;
+  const size_t smem = sizeof(UK) * TILE + sizeof(unsigned int) * 256 * kSortWarps + sizeof(long long) * 256 + 64;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSortBlock, smem));
+  if (occ < 1) { set_error("nl_sort: the one-sweep kernel does not fit an SM"); return NL_ERR_CUDA; }
+  const long long portion = (g_sweep_portion / TILE > 0 ? g_sweep_portion / TILE : 1) * TILE;
+  const long long max_tiles = ((n < portion ? n : portion) + TILE - 1) / TILE;
+  const size_t desc_bytes = 256 + (size_t)max_tiles * 256 * sizeof(unsigned int);
+  unsigned int *scratch = nullptr;
+  unsigned long long *bins = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&scratch, desc_bytes, st));
+  CUDA_TRY(cudaMallocAsync((void **)&bins, sizeof(unsigned long long) * P * 512, st));
+  digit_starts_kernel<<<P, kSortBlock, 0, st>>>(ghist, bins);
+  count_launch();
+  for (int p = 0; p < P; p++) {
+    bool trivial = false;
+    for (int d = 0; d < 256; d++)
+      if (host_hist[p * 256 + d] == (unsigned long long)n) trivial = true;   // every key has the same digit here
+    if (trivial) continue;
+    int q = 0;
+    for (long long lo = 0; lo < n; lo += portion, q++) {
+      const long long len = (n - lo < portion) ? (n - lo) : portion;
+      const int n_tiles = (int)((len + TILE - 1) / TILE);
+      CUDA_TRY(cudaMemsetAsync(scratch, 0, 256 + (size_t)n_tiles * 256 * sizeof(unsigned int), st));
+      const int grid = (int)((long long)sm_count * occ < n_tiles ? (long long)sm_count * occ : n_tiles);
+      unsigned long long *b_in = bins + (size_t)p * 512 + (q & 1) * 256, *b_out = bins + (size_t)p * 512 + ((q + 1) & 1) * 256;
+      kern<<<grid, kSortBlock, smem, st>>>(src + lo, dst, (unsigned int)len, 8 * p, b_in, (lo + len < n) ? b_out : nullptr, scratch + 64, scratch, n_tiles);
+      CUDA_TRY(cudaGetLastError());
+      count_launch();
+    }
+    UK *t = src; src = dst; dst = t;
+  }
+  CUDA_TRY(cudaFreeAsync(scratch, st));
+  CUDA_TRY(cudaFreeAsync(bins, st));
+  return NL_OK;
+}
 
 template <typename UK, int kFloat>
 static int sort_impl(cudaStream_t st, int sm_count, void *keys_v, void *tmp_v, int64_t n) {
   constexpr int P = sizeof(UK);
-  // keys per thread and tile in the scatter: 16 KB of keys per tile for either key width
-  constexpr int ITEMS = (sizeof(UK) == 4) ? NL_SORT_ITEMS32 : kSortItems;
-  constexpr int TILE = kSortBlock * ITEMS;
   UK *a = (UK *)keys_v, *b = (UK *)tmp_v;
-  int n_chunks = sm_count * NL_SORT_MIN_CTAS * 2;        // two full waves of resident CTAs
-  long long chunk = (n + n_chunks - 1) / n_chunks;
-  chunk = (chunk + TILE - 1) / TILE * TILE;
-  n_chunks = (int)((n + chunk - 1) / chunk);
-
+  if (n <= 1) return NL_OK;
   unsigned long long *ghist = nullptr;
-  unsigned int *hist = nullptr;
-  long long *offs = nullptr;
   CUDA_TRY(cudaMallocAsync((void **)&ghist, sizeof(unsigned long long) * P * 256, st));
-  CUDA_TRY(cudaMallocAsync((void **)&hist, sizeof(unsigned int) * 256 * (size_t)n_chunks, st));
-  CUDA_TRY(cudaMallocAsync((void **)&offs, sizeof(long long) * 256 * (size_t)n_chunks, st));
-  // one-sweep scratch: the ticket (first 256 bytes) + one descriptor per tile and digit, re-zeroed per position
-  const long long n_tiles_sweep = (n + TILE - 1) / TILE;
-  const size_t sweep_bytes = 256 + (size_t)n_tiles_sweep * 256 * sizeof(unsigned int);
-  unsigned int *sweep = nullptr;
-  CUDA_TRY(cudaMallocAsync((void **)&sweep, sweep_bytes, st));
   CUDA_TRY(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * P * 256, st));
   sort_histogram_kernel<UK, kFloat><<<sm_count * 8, kSortBlock, 0, st>>>(a, n, ghist);
   CUDA_TRY(cudaGetLastError());
@@ -437,31 +551,40 @@ static int sort_impl(cudaStream_t st, int sm_count, void *keys_v, void *tmp_v, i
   CUDA_TRY(cudaStreamSynchronize(st));
 
   UK *src = a, *dst = b;
+  if constexpr (sizeof(UK) >= 4) {
+    if (g_sort_algo == 0) {
+      const int rc = onesweep_passes<UK, kFloat>(st, sm_count, src, dst, n, ghist, host);
+      if (rc != NL_OK) return rc;
+      if (src != a) CUDA_TRY(cudaMemcpyAsync(a, src, sizeof(UK) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+      CUDA_TRY(cudaFreeAsync(ghist, st));
+      return NL_OK;
+    }
+  }
+  // count + scatter per position (1- and 2-byte keys; nl_tune("sort_algo", 1))
+  // keys per thread and tile in the scatter: 16 KB of keys per tile for either key width
+  constexpr int ITEMS = (sizeof(UK) == 4) ? NL_SORT_ITEMS32 : kSortItems;
+  constexpr int TILE = kSortBlock * ITEMS;
+  int n_chunks = sm_count * NL_SORT_MIN_CTAS * 2;        // two full waves of resident CTAs
+  long long chunk = (n + n_chunks - 1) / n_chunks;
+  chunk = (chunk + TILE - 1) / TILE * TILE;
+  n_chunks = (int)((n + chunk - 1) / chunk);
+  unsigned int *hist = nullptr;
+  long long *offs = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&hist, sizeof(unsigned int) * 256 * (size_t)n_chunks, st));
+  CUDA_TRY(cudaMallocAsync((void **)&offs, sizeof(long long) * 256 * (size_t)n_chunks, st));
   for (int p = 0; p < P; p++) {
     bool trivial = false;
     for (int d = 0; d < 256; d++)
       if (host[p * 256 + d] == (unsigned long long)n) trivial = true;   // every key has the same digit here
     if (trivial) continue;
-    if (g_sort_algo != 0) {
-      CUDA_TRY(cudaMemsetAsync(sweep, 0, sweep_bytes, st));
-      const int grid = (int)((long long)sm_count * NL_SORT_MIN_CTAS < n_tiles_sweep ? (long long)sm_count * NL_SORT_MIN_CTAS : n_tiles_sweep);
-      if (g_sort_algo == 2)
-        onesweep_kernel<UK, kFloat, ITEMS, true><<<grid, kSortBlock, 0, st>>>(src, dst, n, 8 * p, ghist + p * 256, sweep + 64, sweep, (int)n_tiles_sweep);
-      else
-        onesweep_kernel<UK, kFloat, ITEMS, false><<<grid, kSortBlock, 0, st>>>(src, dst, n, 8 * p, ghist + p * 256, sweep + 64, sweep, (int)n_tiles_sweep);
-      CUDA_TRY(cudaGetLastError());
-      count_launch(1);
-    } else {
-      chunk_histogram_kernel<UK, kFloat><<<n_chunks, kSortBlock, 0, st>>>(src, n, chunk, 8 * p, hist);
-      chunk_offsets_kernel<<<256, kSortBlock, 0, st>>>(ghist + p * 256, hist, n_chunks, offs);
-      scatter_kernel<UK, kFloat, ITEMS><<<n_chunks, kSortBlock, 0, st>>>(src, dst, n, chunk, 8 * p, offs);
-      CUDA_TRY(cudaGetLastError());
-      count_launch(3);
-    }
+    chunk_histogram_kernel<UK, kFloat><<<n_chunks, kSortBlock, 0, st>>>(src, n, chunk, 8 * p, hist);
+    chunk_offsets_kernel<<<256, kSortBlock, 0, st>>>(ghist + p * 256, hist, n_chunks, offs);
+    scatter_kernel<UK, kFloat, ITEMS><<<n_chunks, kSortBlock, 0, st>>>(src, dst, n, chunk, 8 * p, offs);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(3);
     UK *t = src; src = dst; dst = t;
   }
   if (src != a) CUDA_TRY(cudaMemcpyAsync(a, src, sizeof(UK) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-  CUDA_TRY(cudaFreeAsync(sweep, st));
   CUDA_TRY(cudaFreeAsync(ghist, st));
   CUDA_TRY(cudaFreeAsync(hist, st));
   CUDA_TRY(cudaFreeAsync(offs, st));

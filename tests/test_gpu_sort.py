@@ -66,3 +66,42 @@ def test_sort_is_stable_for_equal_keys_and_handles_duplicates(rt):
     assert np.array_equal(dev_sort(rt, x), np.sort(x))
     x = np.full(10_000, 7, dtype=np.int32)          # every digit position is trivial: zero passes
     assert np.array_equal(dev_sort(rt, x), x)
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64, np.float32, np.float64, np.uint32, np.uint64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("algo", [0, 1])
+def test_both_radix_forms(rt, dtype, algo):
+    """nl_tune("sort_algo"): one sweep per digit position (default) and count + scatter give NumPy's order."""
+    rng = np.random.default_rng(5)
+    n = 1_234_567
+    if np.dtype(dtype).kind == "f":
+        x = ((rng.random(n) - 0.5) * 1e9).astype(dtype)
+        x[x == 0] = 1
+    else:
+        info = np.iinfo(dtype)
+        x = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    abi.check(rt.lib.nl_tune(b"sort_algo", algo))
+    try:
+        got = dev_sort(rt, x)
+    finally:
+        abi.check(rt.lib.nl_tune(b"sort_algo", 0))
+    assert got.tobytes() == np.sort(x).tobytes()
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.uint32], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [8191, 8192, 8193, 100_003, 1_000_000])
+def test_one_sweep_chains_its_launches(rt, dtype, n):
+    """Above 2^28 keys the one-sweep form runs in several launches per position, each continuing where the previous
+    one stopped (the last tile leaves the running digit offsets behind); a 2^13-key portion exercises that chain —
+    portions smaller than a tile included."""
+    rng = np.random.default_rng(n)
+    info = np.iinfo(dtype)
+    x = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    x[: n // 3] &= 0xFF                      # skewed digits: long runs of one digit in the upper positions
+    for log2 in (13, 16):
+        abi.check(rt.lib.nl_tune(b"sort_portion_log2", log2))
+        try:
+            got = dev_sort(rt, x)
+        finally:
+            abi.check(rt.lib.nl_tune(b"sort_portion_log2", 0))
+        assert got.tobytes() == np.sort(x).tobytes()

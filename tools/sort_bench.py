@@ -33,10 +33,10 @@ for dtype, kind, label in ((np.int64, 1, "i64 full range"), (np.int64, 0, "i64 i
         rt.sync()
         best = min(best, rt.elapsed_ms(e0, e1))
         launches = rt.lib.nl_launch_count() - before
-    per_pass = 1 if algo else 3
-    passes = (launches - 1) // per_pass
+    per_pass = 3 if algo else max(1, -(-n // (1 << 28)))       # one launch per 2^28-key portion and position
+    passes = (launches - 1 - (0 if algo else 1)) // per_pass
     es = np.dtype(dtype).itemsize
-    traffic = n * es * (1 + (2 if algo else 3) * passes + (2 if passes % 2 else 0))
+    traffic = n * es * (1 + (3 if algo else 2) * passes + (2 if passes % 2 else 0))
     head = rt.download(x, 4096)
     assert np.all(head[:-1] <= head[1:])
     print(f"{label:16s} n=2^{log2n}: {best:8.3f} ms  {n / best / 1e6:7.2f} Gkeys/s  {passes} passes  {traffic / best / 1e6:7.0f} GB/s of pass traffic")
