@@ -386,6 +386,20 @@ NL_API int nl_gather(int dev, int stream, int dtype, void *out, const int64_t *i
  * sort; digit positions on which all keys agree cost no pass.  Synchronises the stream once. */
 NL_API int nl_sort(int dev, int stream, int dtype, void *keys, void *tmp, int64_t count);
 
+/* The two device steps of a sort across GPUs (sample sort; the reference sorts the whole array with one host call,
+ * thunk_methods.cpp:37-62).  Keys are compared through nl_sort's order-preserving bijection of their bit patterns
+ * ("order keys", widened to 64 bits: signed integers with the sign bit flipped, floats with NaNs last).
+ *   nl_sort_sample  order keys of `n_samples` regularly spaced elements of `keys` -> host_keys.
+ *   nl_sort_split   cuts `keys` at `n_splitters` (<= 15) ascending order keys: `out` receives the keys grouped, stably,
+ *                   into n_splitters + 1 runs — run j holds the keys in (splitter[j-1], splitter[j]] — and
+ *                   host_counts[j] the length of run j (one counting pass + one sweep of nl_sort's kernel with the run
+ *                   number as its digit).
+ * Both are stream-ordered: the host arrays are valid after the stream has been synchronised, and with page-locked
+ * host arrays (nl_host_alloc) the calls return at once, so several devices work side by side. */
+NL_API int nl_sort_sample(int dev, int stream, int dtype, const void *keys, int64_t count, int n_samples, uint64_t *host_keys);
+NL_API int nl_sort_split(int dev, int stream, int dtype, const void *keys, void *out, int64_t count, const uint64_t *splitters,
+                         int n_splitters, int64_t *host_counts);
+
 /* ======================= communicator (NCCL over NVLink) ================== */
 
 #define NL_UNIQUE_ID_BYTES 128

@@ -1,46 +1,28 @@
 // device_sort.cpp — see device_sort.hpp.
 //
-// One GPU: copy the shard, nl_sort() it (LSD radix sort, nl_sort.cu).
-// Several GPUs: sample sort over NVLink —
-//   1. every GPU radix-sorts a copy of its shard;
-//   2. the host reads a few regularly spaced samples of every sorted shard and picks G - 1
-//      splitters (in the kernels' key order, so NaNs stay last);
-//   3. every sorted shard is cut at the splitters (binary search over single-element reads);
-//   4. piece j of every shard goes to GPU j by peer copy, in shard order;
-//   5. every GPU sorts what it received — bucket j now holds exactly the elements between
-//      splitters j - 1 and j, so the buckets in order are the sorted array;
-//   6. the buckets are re-cut into the engine's regular partition (peer copies again), so the
-//      result can meet any other column of the same length in a fused pipeline.
+// One GPU: copy the shard, nl_sort() it (LSD radix sort, one sweep per digit position, nl_sort.cu).
+// Several GPUs: sample sort over NVLink, every key radix-sorted ONCE —
+//   1. one small kernel per GPU reads regularly spaced samples of its (unsorted) shard; the host sorts them and picks
+//      G - 1 splitters (in the kernels' key order, so NaNs stay last);
+//   2. every GPU cuts its shard at the splitters into G runs (nl_sort_split: a counting pass + ONE sweep of the sort's
+//      own kernel with "number of splitters below the key" as the digit) — all GPUs side by side;
+//   3. run j of every shard goes to GPU j by peer copy, in shard order;
+//   4. every GPU sorts what it received — bucket j holds exactly the elements between splitters j - 1 and j, so the
+//      buckets in order are the sorted array;
+//   5. the buckets are re-cut into the engine's regular partition (peer copies again), so the result can meet any
+//      other column of the same length in a fused pipeline.
+// (Round 1 sorted every shard first, found the cuts with ~1,500 single-element reads + synchronisations, and sorted
+// every bucket again.)
 #include "device_sort.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 namespace {
-
-// the kernels' order-preserving bijection (nl_sort.cu: order_key), for the host-side splitters
-uint64_t host_order_key(uint64_t bits, int dtype) {
-  switch (dtype) {
-    case NL_I8: return (uint64_t)((uint8_t)bits ^ 0x80u);
-    case NL_I16: return (uint64_t)((uint16_t)bits ^ 0x8000u);
-    case NL_U8: return (uint64_t)(uint8_t)bits;
-    case NL_U16: return (uint64_t)(uint16_t)bits;
-    case NL_U32: return (uint64_t)(uint32_t)bits;
-    case NL_U64: return bits;
-    case NL_I32: return (uint64_t)((uint32_t)bits ^ 0x80000000u);
-    case NL_I64: return bits ^ 0x8000000000000000ull;
-    case NL_F32: {
-      const uint32_t b = (uint32_t)bits;
-      const uint32_t k = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
-      return (uint64_t)(uint32_t)(k - 0x007fffffu);
-    }
-    default: {
-      const uint64_t k = bits ^ ((bits >> 63) ? ~0ull : 0x8000000000000000ull);
-      return k - 0x000fffffffffffffull;
-    }
-  }
-}
 
 struct Buf {
   int dev = -1;
@@ -59,16 +41,6 @@ int sync_devices(int G) {
   for (int g = 0; g < G && rc == NL_OK; g++) rc = nl_stream_sync(g, 0);
   Py_END_ALLOW_THREADS
   return rc;
-}
-
-// element `i` of a device buffer as its order key
-int read_key(const Buf &b, size_t es, int dtype, int64_t i, uint64_t *key) {
-  uint64_t bits = 0;
-  int rc = nl_memcpy_d2h(b.dev, 0, &bits, (const char *)b.ptr + (size_t)i * es, es);
-  if (rc == NL_OK) rc = nl_stream_sync(b.dev, 0);
-  if (rc != NL_OK) return rc;
-  *key = host_order_key(bits, dtype);
-  return NL_OK;
 }
 
 // copy the global element range [lo, hi) of the concatenation of `src` into dst (on dst_dev)
@@ -134,6 +106,28 @@ Storage *storage_repartition(Storage *in) {
   return regular_from_runs(in->dtype, runs, in->cardinality());
 }
 
+namespace {
+
+// a sorted copy of one shard (tmp freed before returning); the caller synchronises
+int sorted_copy(const Shard &sh, int dtype, size_t es, Buf *out) {
+  out->dev = sh.dev;
+  out->count = sh.count;
+  if (sh.count == 0) return NL_OK;
+  void *tmp = nullptr;
+  int rc = nl_malloc(sh.dev, (size_t)sh.count * es, &out->ptr);
+  if (rc == NL_OK) rc = nl_malloc(sh.dev, (size_t)sh.count * es, &tmp);
+  if (rc == NL_OK) rc = nl_memcpy_d2d(sh.dev, 0, out->ptr, sh.ptr, (size_t)sh.count * es);
+  if (rc == NL_OK) {
+    Py_BEGIN_ALLOW_THREADS
+    rc = nl_sort(sh.dev, 0, dtype, out->ptr, tmp, sh.count);
+    Py_END_ALLOW_THREADS
+  }
+  if (tmp) nl_free(sh.dev, tmp);
+  return rc;
+}
+
+}  // namespace
+
 Storage *device_sort(Storage *in) {
   if (nljit_ensure_runtime() < 0) return nullptr;
   const int G = nljit_device_count();
@@ -146,111 +140,122 @@ Storage *device_sort(Storage *in) {
   // evaluation no longer ends with idle devices: peers read these shards over NVLink below
   if (G > 1 && (rc = sync_devices(G)) != NL_OK) return fail(rc, "jit: device synchronisation failed");
 
-  // 1. a sorted copy of every shard
-  std::vector<Buf> sorted((size_t)in->shards.size());
-  for (size_t g = 0; g < in->shards.size(); g++) {
-    const Shard &sh = in->shards[g];
-    sorted[g].dev = sh.dev;
-    sorted[g].count = sh.count;
-    if (sh.count == 0) continue;
-    void *tmp = nullptr;
-    rc = nl_malloc(sh.dev, (size_t)sh.count * es, &sorted[g].ptr);
-    if (rc == NL_OK) rc = nl_malloc(sh.dev, (size_t)sh.count * es, &tmp);
-    if (rc == NL_OK) rc = nl_memcpy_d2d(sh.dev, 0, sorted[g].ptr, sh.ptr, (size_t)sh.count * es);
-    if (rc == NL_OK) {
-      Py_BEGIN_ALLOW_THREADS
-      rc = nl_sort(sh.dev, 0, dtype, sorted[g].ptr, tmp, sh.count);
-      Py_END_ALLOW_THREADS
-    }
-    if (tmp) nl_free(sh.dev, tmp);
-    if (rc != NL_OK) { free_bufs(sorted); return fail(rc, "jit: device sort failed"); }
-  }
+  const size_t S = in->shards.size();
   int nonempty = 0;
-  for (const Buf &b : sorted) nonempty += b.count > 0;
+  for (const Shard &sh : in->shards) nonempty += sh.count > 0;
   if (G == 1 || nonempty <= 1) {
-    // one sorted run: it only has to be laid out as a regular column
-    rc = sync_devices(G);
+    // one run: sort a copy, then lay it out as a regular column
+    std::vector<Buf> sorted(S);
+    for (size_t g = 0; g < S && rc == NL_OK; g++) rc = sorted_copy(in->shards[g], dtype, es, &sorted[g]);
+    if (rc == NL_OK) rc = sync_devices(G);
     Storage *out = (rc == NL_OK) ? regular_from_runs(dtype, sorted, total) : fail(rc, "jit: device sort failed");
     free_bufs(sorted);
     return out;
   }
+  if (G - 1 > 15) return fail(NL_ERR_UNSUPPORTED, "jit: sort() across more than 16 devices");
 
-  // 2. splitters from regularly spaced samples
-  const int kSamples = 64;
+  // NL_DEBUG_SORT=1: wall-clock time of every step on stderr
+  const bool trace = getenv("NL_DEBUG_SORT") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[jit sort] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
+  // page-locked scratch for what the devices report: samples and run lengths
+  const int kSamples = 256;
+  uint64_t *host_samples = nullptr;
+  int64_t *host_counts = nullptr;
+  rc = nl_host_alloc(sizeof(uint64_t) * S * kSamples + sizeof(int64_t) * S * (size_t)(G + 1), (void **)&host_samples);
+  if (rc != NL_OK) return fail(rc, "jit: page-locked allocation failed");
+  host_counts = (int64_t *)(host_samples + S * kSamples);
+  lap("page-locked scratch");
+  std::vector<Buf> grouped(S), bucket((size_t)G);
+  auto cleanup = [&]() { free_bufs(grouped); free_bufs(bucket); nl_host_free(host_samples); };
+
+  // 1. splitters from regularly spaced samples of every shard
+  for (size_t g = 0; g < S && rc == NL_OK; g++)
+    if (in->shards[g].count > 0)
+      rc = nl_sort_sample(in->shards[g].dev, 0, dtype, in->shards[g].ptr, in->shards[g].count, kSamples, host_samples + g * kSamples);
+  if (rc == NL_OK) rc = sync_devices(G);
+  if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device sort failed (sampling)"); }
   std::vector<uint64_t> samples;
-  for (const Buf &b : sorted) {
-    for (int i = 0; i < kSamples && b.count > 0; i++) {
-      uint64_t key;
-      rc = read_key(b, es, dtype, (int64_t)(((__int128)b.count * i) / kSamples), &key);
-      if (rc != NL_OK) { free_bufs(sorted); return fail(rc, "jit: device sort failed (sampling)"); }
-      samples.push_back(key);
-    }
-  }
+  for (size_t g = 0; g < S; g++)
+    if (in->shards[g].count > 0) samples.insert(samples.end(), host_samples + g * kSamples, host_samples + (g + 1) * kSamples);
   std::sort(samples.begin(), samples.end());
   std::vector<uint64_t> splitter((size_t)G - 1);
   for (int j = 1; j < G; j++) splitter[(size_t)j - 1] = samples[(samples.size() * (size_t)j) / (size_t)G];
+  lap("samples and splitters");
 
-  // 3. cut[g][j] = first element of sorted shard g whose key is > splitter j - 1 (cut[g][0] = 0)
-  std::vector<std::vector<int64_t>> cut(sorted.size(), std::vector<int64_t>((size_t)G + 1, 0));
-  for (size_t g = 0; g < sorted.size(); g++) {
-    cut[g][(size_t)G] = sorted[g].count;
-    for (int j = 1; j < G; j++) {
-      int64_t lo = cut[g][(size_t)j - 1], hi = sorted[g].count;
-      while (lo < hi) {
-        const int64_t mid = lo + (hi - lo) / 2;
-        uint64_t key;
-        rc = read_key(sorted[g], es, dtype, mid, &key);
-        if (rc != NL_OK) { free_bufs(sorted); return fail(rc, "jit: device sort failed (partition)"); }
-        if (key <= splitter[(size_t)j - 1]) lo = mid + 1; else hi = mid;
-      }
-      cut[g][(size_t)j] = lo;
-    }
+  // 2. every shard grouped into G runs, all devices side by side
+  for (size_t g = 0; g < S && rc == NL_OK; g++) {
+    const Shard &sh = in->shards[g];
+    grouped[g].dev = sh.dev;
+    grouped[g].count = sh.count;
+    for (int j = 0; j <= G; j++) host_counts[g * (size_t)(G + 1) + (size_t)j] = 0;
+    if (sh.count == 0) continue;
+    rc = nl_malloc(sh.dev, (size_t)sh.count * es, &grouped[g].ptr);
+    if (rc == NL_OK) rc = nl_sort_split(sh.dev, 0, dtype, sh.ptr, grouped[g].ptr, sh.count, splitter.data(), G - 1, host_counts + g * (size_t)(G + 1));
   }
+  if (rc == NL_OK) rc = sync_devices(G);
+  if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device sort failed (partition)"); }
+  lap("cut at the splitters");
+  // cut[g][j] = where run j of shard g starts
+  std::vector<std::vector<int64_t>> cut(S, std::vector<int64_t>((size_t)G + 1, 0));
+  for (size_t g = 0; g < S; g++)
+    for (int j = 0; j < G; j++) cut[g][(size_t)j + 1] = cut[g][(size_t)j] + host_counts[g * (size_t)(G + 1) + (size_t)j];
 
-  // 4. bucket j on device j: piece j of every shard, in shard order
-  std::vector<Buf> bucket((size_t)G);
+  // 3. bucket j on device j: run j of every shard, in shard order
   for (int j = 0; j < G; j++) {
     bucket[(size_t)j].dev = j;
-    for (size_t g = 0; g < sorted.size(); g++) bucket[(size_t)j].count += cut[g][(size_t)j + 1] - cut[g][(size_t)j];
+    for (size_t g = 0; g < S; g++) bucket[(size_t)j].count += cut[g][(size_t)j + 1] - cut[g][(size_t)j];
     if (bucket[(size_t)j].count == 0) continue;
     rc = nl_malloc(j, (size_t)bucket[(size_t)j].count * es, &bucket[(size_t)j].ptr);
-    if (rc != NL_OK) { free_bufs(sorted); free_bufs(bucket); return fail(rc, "jit: device allocation failed"); }
+    if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device allocation failed"); }
   }
   rc = sync_devices(G);
   for (int j = 0; j < G && rc == NL_OK; j++) {
     int64_t at = 0;
-    for (size_t g = 0; g < sorted.size() && rc == NL_OK; g++) {
+    for (size_t g = 0; g < S && rc == NL_OK; g++) {
       const int64_t n = cut[g][(size_t)j + 1] - cut[g][(size_t)j];
       if (n == 0) continue;
-      const char *from = (const char *)sorted[g].ptr + (size_t)cut[g][(size_t)j] * es;
+      const char *from = (const char *)grouped[g].ptr + (size_t)cut[g][(size_t)j] * es;
       char *to = (char *)bucket[(size_t)j].ptr + (size_t)at * es;
-      rc = (sorted[g].dev == j) ? nl_memcpy_d2d(j, 0, to, from, (size_t)n * es) : nl_memcpy_peer(j, 0, to, sorted[g].dev, from, (size_t)n * es);
+      rc = (grouped[g].dev == j) ? nl_memcpy_d2d(j, 0, to, from, (size_t)n * es) : nl_memcpy_peer(j, 0, to, grouped[g].dev, from, (size_t)n * es);
       at += n;
     }
   }
   if (rc == NL_OK) rc = sync_devices(G);
-  free_bufs(sorted);
-  if (rc != NL_OK) { free_bufs(bucket); return fail(rc, "jit: device sort failed (exchange)"); }
+  lap("exchange");
+  free_bufs(grouped);
+  if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device sort failed (exchange)"); }
+  lap("grouped shards freed");
 
-  // 5. sort the buckets
+  // 4. sort the buckets
   for (int j = 0; j < G; j++) {
     Buf &b = bucket[(size_t)j];
     if (b.count <= 1) continue;
     void *tmp = nullptr;
     rc = nl_malloc(j, (size_t)b.count * es, &tmp);
+    lap("  scratch for a bucket");
     if (rc == NL_OK) {
       Py_BEGIN_ALLOW_THREADS
       rc = nl_sort(j, 0, dtype, b.ptr, tmp, b.count);
       Py_END_ALLOW_THREADS
     }
+    lap("  nl_sort enqueued");
     if (tmp) nl_free(j, tmp);
-    if (rc != NL_OK) { free_bufs(bucket); return fail(rc, "jit: device sort failed"); }
+    if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device sort failed"); }
   }
   rc = sync_devices(G);
-  if (rc != NL_OK) { free_bufs(bucket); return fail(rc, "jit: device sort failed"); }
+  if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device sort failed"); }
 
-  // 6. regular partition
+  lap("bucket sorts");
+
+  // 5. regular partition
   Storage *out = regular_from_runs(dtype, bucket, total);
-  free_bufs(bucket);
+  cleanup();
+  lap("regular partition");
   return out;
 }

@@ -110,6 +110,10 @@ int launch_cast(void *stream, int sm_count, void *dst, int dst_dtype, const void
 int launch_checksum(void *stream, int sm_count, const void *ptr, size_t nbytes, unsigned long long *out);
 // nl_sort.cu
 int launch_sort(void *stream, int sm_count, int dtype, void *keys, void *tmp, int64_t n);
+int launch_sort_sample(void *stream, int dtype, const void *keys, int64_t n, int k, unsigned long long *host_out);
+int launch_sort_split(void *stream, int sm_count, int dtype, const void *keys, void *out, int64_t n, const unsigned long long *splitters, int m,
+                      int64_t *host_counts);
+constexpr int kSortMaxSplitters = 15;
 int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t name_len, int *is_static);
 void set_static_kernels_enabled(int on);
 void set_compact_pipe_enabled(int on);

@@ -4,6 +4,7 @@
 // streams per device; the "tasks" are kernel launches, dependencies are stream
 // order and events.  NCCL is bound lazily with dlopen so the library loads (and
 // the host-only entry points work) on a machine without GPUs or NCCL.
+#include <chrono>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>   // types and enums only; symbols are resolved with dlsym
@@ -13,7 +14,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <unordered_map>
 
 #include "nl_internal.h"
 #include "nl_step.h"
@@ -55,6 +58,10 @@ struct Device {
   unsigned long long epoch = 0;               // fused reductions launched on this device so far
   unsigned long long *box_host_table[256] = {nullptr};   // host copy of box_table (to post an abort from the host)
   unsigned long long *status = nullptr;       // pinned host word (device-mapped): raised by a kernel that gave up on a peer
+  // column blocks above kCacheMin bytes, kept by size class when nl_free() returns them (see nl_malloc)
+  std::multimap<size_t, void *> cache_free;
+  std::unordered_map<void *, size_t> cache_class;   // every live or cached large block -> its class size
+  size_t cache_bytes = 0;
 };
 
 constexpr int kMaxWorld = 256;
@@ -222,12 +229,36 @@ int nl_init(int n_devices, const int *device_ids) {
   return NL_OK;
 }
 
+constexpr size_t kCacheMin = 1u << 20;
+static std::mutex g_cache_mu;
+
+static size_t size_class(size_t bytes) {
+  size_t p = 1;
+  while ((p << 1) <= bytes) p <<= 1;
+  const size_t granule = (p >> 3) > (2u << 20) ? (p >> 3) : (size_t)(2u << 20);
+  return (bytes + granule - 1) / granule * granule;
+}
+
+static void cache_release_all(Device &d) {     // caller holds g_cache_mu and has set the device
+  for (auto &kv : d.cache_free) {
+    cudaFreeAsync(kv.second, d.stream[0]);
+    d.cache_class.erase(kv.second);
+  }
+  d.cache_free.clear();
+  d.cache_bytes = 0;
+}
+
 int nl_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   nl_comm_destroy();          // communicator, IPC mappings, mailboxes and epochs: nothing stale survives into a later nl_init
   for (int d = 0; d < g_ndev; d++) {
     Device &dv = g_dev[d];
     cudaSetDevice(dv.id);
+    {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      cache_release_all(dv);
+      dv.cache_class.clear();
+    }
     cudaDeviceSynchronize();
     if (dv.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(dv.comm);
     dv.comm = nullptr;
@@ -316,24 +347,76 @@ int nl_graph_destroy(nl_graph graph) {
   return NL_OK;
 }
 
+// Large blocks are recycled by size class on top of the stream-ordered pool.  Measured on 2 x B200 with peer access
+// between the pools (tools/jit_sort_bench.py, NL_DEBUG_ALLOC=1): a request that no free block of the pool fits — a
+// bucket of 1 GiB + 1 MB after a 1 GiB block was freed — is REFUSED by cudaMallocAsync with 178 GB free at the driver;
+// the trim-and-retry below then works but costs 14 ms, and so does every later allocation that has to map fresh
+// memory.  Thunk storage, filter outputs and sort buckets come and go at every evaluate with sizes that differ by a
+// few elements, so: sizes above 1 MiB are rounded up to 1/8 of their power of two (<= 12.5 % slack), nl_free() parks
+// the block under its class, and the next request of the class takes it.  Both calls are compute-stream ordered
+// (stream 0), so a parked block's last use precedes its next one.  nl_pool_trim() and an allocation failure empty the
+// cache.
 int nl_malloc(int dev, size_t bytes, void **ptr_out) {
   int rc = check_dev(dev, 0);
   if (rc) return rc;
   if (!ptr_out) { set_error("nl_malloc: null ptr_out"); return NL_ERR_INVALID; }
+  static const bool trace = getenv("NL_DEBUG_ALLOC") != nullptr;    // slow or refused allocations on stderr
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  Device &d = g_dev[dev];
+  size_t want = bytes ? bytes : 1;
+  const bool cached = want > kCacheMin;
+  if (cached) {
+    want = size_class(want);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = d.cache_free.find(want);
+    if (it != d.cache_free.end()) {
+      *ptr_out = it->second;
+      d.cache_free.erase(it);
+      d.cache_bytes -= want;
+      return NL_OK;
+    }
+  }
   // stream-ordered on the compute stream: usable there at once; other streams order themselves
   // after it with nl_stream_wait()
-  cudaError_t e = cudaMallocAsync(ptr_out, bytes ? bytes : 1, g_dev[dev].stream[0]);
+  const auto t0 = std::chrono::steady_clock::now();
+  cudaError_t e = cudaMallocAsync(ptr_out, want, d.stream[0]);
+  if (trace) {
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ms > 0.5) {
+      cudaMemPool_t pool;
+      uint64_t reserved = 0, used = 0;
+      if (cudaDeviceGetDefaultMemPool(&pool, d.id) == cudaSuccess) {
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+      }
+      fprintf(stderr, "[nl_malloc] device %d: %zu bytes took %.2f ms (pool: %.1f MiB reserved, %.1f MiB in use)\n", dev, want, ms, reserved / 1048576.0,
+              used / 1048576.0);
+    }
+  }
   if (e == cudaErrorMemoryAllocation) {
-    // the pool may be holding blocks of the wrong sizes: give them back and retry once
+    // the pool (or the cache above it) may be holding blocks of the wrong sizes: give them back and retry once
     cudaGetLastError();
+    if (trace) {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      fprintf(stderr, "[nl_malloc] device %d: %zu bytes refused (driver: %.1f of %.1f MiB free, %.1f MiB parked); trimming the pool and retrying\n", dev, want,
+              free_b / 1048576.0, total_b / 1048576.0, d.cache_bytes / 1048576.0);
+    }
+    {
+      std::lock_guard<std::mutex> lk(g_cache_mu);
+      cache_release_all(d);
+    }
     cudaDeviceSynchronize();
     cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, g_dev[dev].id) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    e = cudaMallocAsync(ptr_out, bytes ? bytes : 1, g_dev[dev].stream[0]);
+    if (cudaDeviceGetDefaultMemPool(&pool, d.id) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    e = cudaMallocAsync(ptr_out, want, d.stream[0]);
   }
-  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); set_error("out of device memory allocating %zu bytes", bytes); return NL_ERR_NOMEM; }
+  if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); set_error("out of device memory allocating %zu bytes", want); return NL_ERR_NOMEM; }
   CUDA_TRY(e);
+  if (cached) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    d.cache_class[*ptr_out] = want;
+  }
   return NL_OK;
 }
 
@@ -341,6 +424,10 @@ int nl_pool_trim(int dev) {
   int rc = check_dev(dev, 0);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    cache_release_all(g_dev[dev]);
+  }
   CUDA_TRY(cudaDeviceSynchronize());
   cudaMemPool_t pool;
   CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, g_dev[dev].id));
@@ -353,9 +440,21 @@ int nl_free(int dev, void *ptr) {
   if (rc) return rc;
   if (!ptr) return NL_OK;
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  Device &d = g_dev[dev];
+  {
+    // a large block waits under its size class for the next request (nl_malloc); in compute-stream order its next
+    // user comes after everything already enqueued there
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = d.cache_class.find(ptr);
+    if (it != d.cache_class.end()) {
+      d.cache_free.emplace(it->second, ptr);
+      d.cache_bytes += it->second;
+      return NL_OK;
+    }
+  }
   // freed in compute-stream order: kernels already enqueued there still see the buffer; work on
   // the copy streams must have been ordered before this point by the caller
-  CUDA_TRY(cudaFreeAsync(ptr, g_dev[dev].stream[0]));
+  CUDA_TRY(cudaFreeAsync(ptr, d.stream[0]));
   return NL_OK;
 }
 
@@ -706,6 +805,33 @@ int nl_sort(int dev, int stream, int dtype, void *keys, void *tmp, int64_t count
   if (count <= 1) return NL_OK;
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
   return launch_sort(g_dev[dev].stream[stream], g_dev[dev].sm_count, dtype, keys, tmp, count);
+}
+
+int nl_sort_sample(int dev, int stream, int dtype, const void *keys, int64_t count, int n_samples, uint64_t *host_keys) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (count <= 0 || !keys || n_samples <= 0 || !host_keys) { set_error("nl_sort_sample: bad argument"); return NL_ERR_INVALID; }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_sort_sample(g_dev[dev].stream[stream], dtype, keys, count, n_samples, (unsigned long long *)host_keys);
+}
+
+int nl_sort_split(int dev, int stream, int dtype, const void *keys, void *out, int64_t count, const uint64_t *splitters, int n_splitters,
+                  int64_t *host_counts) {
+  int rc = check_dev(dev, stream);
+  if (rc) return rc;
+  if (count < 0 || (count > 0 && (!keys || !out)) || n_splitters < 0 || n_splitters > kSortMaxSplitters || (n_splitters > 0 && !splitters) || !host_counts) {
+    set_error("nl_sort_split: bad argument (at most %d splitters)", kSortMaxSplitters);
+    return NL_ERR_INVALID;
+  }
+  for (int j = 1; j < n_splitters; j++)
+    if (splitters[j] < splitters[j - 1]) { set_error("nl_sort_split: the splitters must ascend"); return NL_ERR_INVALID; }
+  if (count == 0) {
+    for (int j = 0; j <= n_splitters; j++) host_counts[j] = 0;
+    return NL_OK;
+  }
+  CUDA_TRY(cudaSetDevice(g_dev[dev].id));
+  return launch_sort_split(g_dev[dev].stream[stream], g_dev[dev].sm_count, dtype, keys, out, count, (const unsigned long long *)splitters, n_splitters,
+                           host_counts);
 }
 
 // ======================================================================= communicator

@@ -45,7 +45,6 @@ namespace nl {
 #endif
 constexpr int kSortBlock = 256;
 constexpr int kSortItems = 8;                          // keys per thread per tile
-constexpr int kSortTile = kSortBlock * kSortItems;     // 2048
 constexpr int kSortWarps = kSortBlock / 32;
 
 template <typename UK, int kFloat>
@@ -291,6 +290,26 @@ __device__ __forceinline__ unsigned int match_digit(unsigned int d) {
   return same_bit<0>(d) & same_bit<1>(d) & same_bit<2>(d) & same_bit<3>(d) & same_bit<4>(d) & same_bit<5>(d) & same_bit<6>(d) & same_bit<7>(d);
 }
 
+// What a sweep groups the keys by: one 8-bit digit of the order key (the radix passes), or the number of splitters
+// below the key (the multi-GPU sample sort cuts a shard into one run per destination GPU with the same kernel).
+template <typename UK>
+struct RadixDigit {
+  int shift;
+  __device__ __forceinline__ unsigned int operator()(UK ordered) const { return (unsigned int)(ordered >> shift) & 0xff; }
+};
+constexpr int kMaxSplitters = 15;
+template <typename UK>
+struct SplitDigit {
+  UK s[kMaxSplitters];           // ascending order keys; bucket j holds the keys in (s[j-1], s[j]]
+  int m;
+  __device__ __forceinline__ unsigned int operator()(UK ordered) const {
+    unsigned int d = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxSplitters; j++) d += (j < m && s[j] < ordered) ? 1u : 0u;
+    return d;
+  }
+};
+
 struct SweepShared {             // views into the CTA's dynamic shared memory
   void *staged;                  // the tile regrouped by digit
   unsigned int (*cnt)[256];      // per warp: digit counts, then the warp's next slot of each digit
@@ -299,8 +318,8 @@ struct SweepShared {             // views into the CTA's dynamic shared memory
   int *next_tile;
 };
 
-template <typename UK, int kFloat, int ITEMS, int CH, bool FULL>
-__device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, int shift, long long dstart,
+template <typename UK, int kFloat, int ITEMS, int CH, bool FULL, typename Digit>
+__device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, const Digit &digit, long long dstart,
                                            unsigned long long *__restrict__ bins_out, unsigned int *__restrict__ desc, unsigned int *__restrict__ ticket,
                                            int tile, int n_tiles, const SweepShared &sh) {
   constexpr int WARPS = kSortWarps, TILE = kSortBlock * ITEMS, W = kSweepWindow;
@@ -324,7 +343,7 @@ __device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__rest
     }
 #pragma unroll
     for (int i = 0; i < CH; i++) {
-      const unsigned int d = (unsigned int)(order_key<UK, kFloat>(key[i]) >> shift) & 0xff;
+      const unsigned int d = digit(order_key<UK, kFloat>(key[i]));
       if (FULL || (warp * (32 * ITEMS) + (i0 + i) * 32 + lane < valid)) atomicAdd(&cw[d], 1u);
     }
   }
@@ -372,7 +391,7 @@ __device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__rest
     }
 #pragma unroll
     for (int i = 0; i < CH; i++) {
-      const unsigned int d = (unsigned int)(order_key<UK, kFloat>(key[i]) >> shift) & 0xff;
+      const unsigned int d = digit(order_key<UK, kFloat>(key[i]));
       const bool ok = FULL || (warp * (32 * ITEMS) + (i0 + i) * 32 + lane < valid);
       unsigned int m = match_digit(d);
       if (!FULL) m &= __ballot_sync(0xffffffffu, ok);
@@ -420,21 +439,21 @@ __device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__rest
     const int pos = i * kSortBlock + tid;
     if (FULL || pos < valid) {
       const UK k = staged[pos];
-      const unsigned int d = (unsigned int)(order_key<UK, kFloat>(k) >> shift) & 0xff;
+      const unsigned int d = digit(order_key<UK, kFloat>(k));
       out[sh.gdelta[d] + (long long)pos] = k;
     }
   }
 }
 
-template <typename UK, int kFloat, int ITEMS, int CH>
-__device__ __noinline__ void sweep_partial_tile(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, int shift, long long dstart,
+template <typename UK, int kFloat, int ITEMS, int CH, typename Digit>
+__device__ __noinline__ void sweep_partial_tile(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, const Digit &digit, long long dstart,
                                                 unsigned long long *__restrict__ bins_out, unsigned int *__restrict__ desc, unsigned int *__restrict__ ticket,
                                                 int tile, int n_tiles, const SweepShared &sh) {
-  sweep_tile<UK, kFloat, ITEMS, CH, false>(in, out, n, shift, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
+  sweep_tile<UK, kFloat, ITEMS, CH, false>(in, out, n, digit, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
 }
 
-template <typename UK, int kFloat, int ITEMS, int CH, int MINCTAS>
-__global__ void __launch_bounds__(kSortBlock, MINCTAS) onesweep_kernel(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, int shift,
+template <typename UK, int kFloat, int ITEMS, int CH, int MINCTAS, typename Digit>
+__global__ void __launch_bounds__(kSortBlock, MINCTAS) onesweep_kernel(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, const __grid_constant__ Digit digit,
                                                                        const unsigned long long *__restrict__ bins_in /*[256]: where each digit continues in out*/,
                                                                        unsigned long long *__restrict__ bins_out /*[256] for the next launch, or null*/,
                                                                        unsigned int *__restrict__ desc /*[n_tiles][256], zeroed*/,
@@ -458,9 +477,9 @@ __global__ void __launch_bounds__(kSortBlock, MINCTAS) onesweep_kernel(const UK 
     const int tile = sh_tile;
     if (tile >= n_tiles) break;
     if ((unsigned int)(tile + 1) * TILE <= n)
-      sweep_tile<UK, kFloat, ITEMS, CH, true>(in, out, n, shift, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
+      sweep_tile<UK, kFloat, ITEMS, CH, true>(in, out, n, digit, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
     else
-      sweep_partial_tile<UK, kFloat, ITEMS, CH>(in, out, n, shift, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
+      sweep_partial_tile<UK, kFloat, ITEMS, CH>(in, out, n, digit, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
   }
 }
 
@@ -487,17 +506,20 @@ __global__ void __launch_bounds__(kSortBlock) digit_starts_kernel(const unsigned
 template <int BYTES> struct SweepShape;                  // keys per thread, keys per batch of the second read, resident CTAs per SM
 template <> struct SweepShape<8> { static constexpr int items = 24, batch = 8, ctas = 3; };
 template <> struct SweepShape<4> { static constexpr int items = 32, batch = 16, ctas = 4; };
+template <> struct SweepShape<2> { static constexpr int items = 32, batch = 16, ctas = 4; };
+template <> struct SweepShape<1> { static constexpr int items = 32, batch = 16, ctas = 4; };
 
-static int g_sort_algo = 0;          // 0: one sweep per position for 4- and 8-byte keys (default); 1: count + scatter per position
+static int g_sort_algo = 0;          // 0: one sweep per position (default); 1: count + scatter per position
 void set_sort_algo(int a) { g_sort_algo = a; }
 
-// all non-trivial positions of a 4- or 8-byte key, one sweep each
-template <typename UK, int kFloat>
-static int onesweep_passes(cudaStream_t st, int sm_count, UK *&src, UK *&dst, int64_t n, const unsigned long long *ghist, const unsigned long long *host_hist) {
-  constexpr int P = sizeof(UK);
+// one sweep of `n` keys src -> dst, grouped by `digit`, in launches of at most one portion; bins[0..255] = where each
+// group starts in dst (bins[256..511] is the second half of the double buffer the launches hand over through)
+template <typename UK, int kFloat, typename Digit>
+static int run_sweep(cudaStream_t st, int sm_count, const UK *src, UK *dst, int64_t n, const Digit &digit, unsigned long long *bins, unsigned int **scratch_io,
+                     size_t *scratch_bytes_io) {
   using Shape = SweepShape<sizeof(UK)>;
   constexpr int ITEMS = Shape::items, TILE = kSortBlock * ITEMS;
-  auto kern = onesweep_kernel<UK, kFloat, ITEMS, Shape::batch, Shape::ctas>;
+  auto kern = onesweep_kernel<UK, kFloat, ITEMS, Shape::batch, Shape::ctas, Digit>;
   const size_t smem = sizeof(UK) * TILE + sizeof(unsigned int) * 256 * kSortWarps + sizeof(long long) * 256 + 64;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -505,10 +527,35 @@ static int onesweep_passes(cudaStream_t st, int sm_count, UK *&src, UK *&dst, in
   if (occ < 1) { set_error("nl_sort: the one-sweep kernel does not fit an SM"); return NL_ERR_CUDA; }
   const long long portion = (g_sweep_portion / TILE > 0 ? g_sweep_portion / TILE : 1) * TILE;
   const long long max_tiles = ((n < portion ? n : portion) + TILE - 1) / TILE;
-  const size_t desc_bytes = 256 + (size_t)max_tiles * 256 * sizeof(unsigned int);
+  const size_t need = 256 + (size_t)max_tiles * 256 * sizeof(unsigned int);
+  if (*scratch_bytes_io < need) {
+    if (*scratch_io) CUDA_TRY(cudaFreeAsync(*scratch_io, st));
+    *scratch_io = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)scratch_io, need, st));
+    *scratch_bytes_io = need;
+  }
+  unsigned int *scratch = *scratch_io;
+  int q = 0;
+  for (long long lo = 0; lo < n; lo += portion, q++) {
+    const long long len = (n - lo < portion) ? (n - lo) : portion;
+    const int n_tiles = (int)((len + TILE - 1) / TILE);
+    CUDA_TRY(cudaMemsetAsync(scratch, 0, 256 + (size_t)n_tiles * 256 * sizeof(unsigned int), st));
+    const int grid = (int)((long long)sm_count * occ < n_tiles ? (long long)sm_count * occ : n_tiles);
+    unsigned long long *b_in = bins + (q & 1) * 256, *b_out = bins + ((q + 1) & 1) * 256;
+    kern<<<grid, kSortBlock, smem, st>>>(src + lo, dst, (unsigned int)len, digit, b_in, (lo + len < n) ? b_out : nullptr, scratch + 64, scratch, n_tiles);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+  }
+  return NL_OK;
+}
+
+// all non-trivial positions of a key, one sweep each
+template <typename UK, int kFloat>
+static int onesweep_passes(cudaStream_t st, int sm_count, UK *&src, UK *&dst, int64_t n, const unsigned long long *ghist, const unsigned long long *host_hist) {
+  constexpr int P = sizeof(UK);
   unsigned int *scratch = nullptr;
+  size_t scratch_bytes = 0;
   unsigned long long *bins = nullptr;
-  CUDA_TRY(cudaMallocAsync((void **)&scratch, desc_bytes, st));
   CUDA_TRY(cudaMallocAsync((void **)&bins, sizeof(unsigned long long) * P * 512, st));
   digit_starts_kernel<<<P, kSortBlock, 0, st>>>(ghist, bins);
   count_launch();
@@ -517,20 +564,88 @@ static int onesweep_passes(cudaStream_t st, int sm_count, UK *&src, UK *&dst, in
     for (int d = 0; d < 256; d++)
       if (host_hist[p * 256 + d] == (unsigned long long)n) trivial = true;   // every key has the same digit here
     if (trivial) continue;
-    int q = 0;
-    for (long long lo = 0; lo < n; lo += portion, q++) {
-      const long long len = (n - lo < portion) ? (n - lo) : portion;
-      const int n_tiles = (int)((len + TILE - 1) / TILE);
-      CUDA_TRY(cudaMemsetAsync(scratch, 0, 256 + (size_t)n_tiles * 256 * sizeof(unsigned int), st));
-      const int grid = (int)((long long)sm_count * occ < n_tiles ? (long long)sm_count * occ : n_tiles);
-      unsigned long long *b_in = bins + (size_t)p * 512 + (q & 1) * 256, *b_out = bins + (size_t)p * 512 + ((q + 1) & 1) * 256;
-      kern<<<grid, kSortBlock, smem, st>>>(src + lo, dst, (unsigned int)len, 8 * p, b_in, (lo + len < n) ? b_out : nullptr, scratch + 64, scratch, n_tiles);
-      CUDA_TRY(cudaGetLastError());
-      count_launch();
-    }
+    RadixDigit<UK> digit;
+    digit.shift = 8 * p;
+    const int rc = run_sweep<UK, kFloat>(st, sm_count, src, dst, n, digit, bins + (size_t)p * 512, &scratch, &scratch_bytes);
+    if (rc != NL_OK) return rc;
     UK *t = src; src = dst; dst = t;
   }
-  CUDA_TRY(cudaFreeAsync(scratch, st));
+  if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
+  CUDA_TRY(cudaFreeAsync(bins, st));
+  return NL_OK;
+}
+
+// ---- the two device steps of the multi-GPU sample sort (csrc/jit/device_sort.cpp) -------------------------------
+// order keys of k regularly spaced elements, widened to 64 bits
+template <typename UK, int kFloat>
+__global__ void sample_kernel(const UK *__restrict__ keys, long long n, int k, unsigned long long *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) out[i] = (unsigned long long)order_key<UK, kFloat>(keys[(long long)(((__int128)n * i) / k)]);
+}
+
+// how many keys fall into each of the m + 1 buckets the splitters cut: per-thread counts packed 8 bits a bucket
+template <typename UK, int kFloat>
+__global__ void __launch_bounds__(kSortBlock) split_count_kernel(const UK *__restrict__ keys, long long n, const __grid_constant__ SplitDigit<UK> digit,
+                                                                   unsigned long long *__restrict__ ghist /*[256], zeroed*/) {
+  __shared__ unsigned int h[16];
+  if (threadIdx.x < 16) h[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned long long lo = 0, hi = 0;      // buckets 0..7 and 8..15, 8 bits each
+  int pending = 0;
+  auto flush = [&]() {
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const unsigned int cl = (unsigned int)(lo >> (8 * b)) & 0xff, ch = (unsigned int)(hi >> (8 * b)) & 0xff;
+      if (cl) atomicAdd(&h[b], cl);
+      if (ch) atomicAdd(&h[8 + b], ch);
+    }
+    lo = hi = 0;
+    pending = 0;
+  };
+  for (long long i = (long long)blockIdx.x * kSortBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kSortBlock) {
+    const unsigned int d = digit(order_key<UK, kFloat>(keys[i]));
+    const unsigned long long one = 1ull << (8 * (d & 7));
+    if (d < 8) lo += one; else hi += one;
+    if (++pending == 255) flush();
+  }
+  flush();
+  __syncthreads();
+  if (threadIdx.x < 16 && h[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+template <typename UK, int kFloat>
+static int sample_impl(cudaStream_t st, const void *keys, int64_t n, int k, unsigned long long *host_out) {
+  unsigned long long *dev = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&dev, sizeof(unsigned long long) * (size_t)k, st));
+  sample_kernel<UK, kFloat><<<(k + 255) / 256, 256, 0, st>>>((const UK *)keys, n, k, dev);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+  CUDA_TRY(cudaMemcpyAsync(host_out, dev, sizeof(unsigned long long) * (size_t)k, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaFreeAsync(dev, st));
+  return NL_OK;
+}
+
+template <typename UK, int kFloat>
+static int split_impl(cudaStream_t st, int sm_count, const void *keys, void *out, int64_t n, const unsigned long long *splitters, int m, int64_t *host_counts) {
+  SplitDigit<UK> digit;
+  for (int j = 0; j < kMaxSplitters; j++) digit.s[j] = (j < m) ? (UK)splitters[j] : (UK)0;
+  digit.m = m;
+  unsigned long long *ghist = nullptr, *bins = nullptr;
+  CUDA_TRY(cudaMallocAsync((void **)&ghist, sizeof(unsigned long long) * 256, st));
+  CUDA_TRY(cudaMallocAsync((void **)&bins, sizeof(unsigned long long) * 512, st));
+  CUDA_TRY(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * 256, st));
+  split_count_kernel<UK, kFloat><<<sm_count * 8, kSortBlock, 0, st>>>((const UK *)keys, n, digit, ghist);
+  digit_starts_kernel<<<1, kSortBlock, 0, st>>>(ghist, bins);
+  CUDA_TRY(cudaGetLastError());
+  count_launch(2);
+  static_assert(sizeof(int64_t) == sizeof(unsigned long long), "the counts are copied as they are");
+  CUDA_TRY(cudaMemcpyAsync(host_counts, ghist, sizeof(unsigned long long) * (size_t)(m + 1), cudaMemcpyDeviceToHost, st));
+  unsigned int *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  const int rc = run_sweep<UK, kFloat>(st, sm_count, (const UK *)keys, (UK *)out, n, digit, bins, &scratch, &scratch_bytes);
+  if (rc != NL_OK) return rc;
+  if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
+  CUDA_TRY(cudaFreeAsync(ghist, st));
   CUDA_TRY(cudaFreeAsync(bins, st));
   return NL_OK;
 }
@@ -551,16 +666,14 @@ static int sort_impl(cudaStream_t st, int sm_count, void *keys_v, void *tmp_v, i
   CUDA_TRY(cudaStreamSynchronize(st));
 
   UK *src = a, *dst = b;
-  if constexpr (sizeof(UK) >= 4) {
-    if (g_sort_algo == 0) {
-      const int rc = onesweep_passes<UK, kFloat>(st, sm_count, src, dst, n, ghist, host);
-      if (rc != NL_OK) return rc;
-      if (src != a) CUDA_TRY(cudaMemcpyAsync(a, src, sizeof(UK) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-      CUDA_TRY(cudaFreeAsync(ghist, st));
-      return NL_OK;
-    }
+  if (g_sort_algo == 0) {
+    const int rc = onesweep_passes<UK, kFloat>(st, sm_count, src, dst, n, ghist, host);
+    if (rc != NL_OK) return rc;
+    if (src != a) CUDA_TRY(cudaMemcpyAsync(a, src, sizeof(UK) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaFreeAsync(ghist, st));
+    return NL_OK;
   }
-  // count + scatter per position (1- and 2-byte keys; nl_tune("sort_algo", 1))
+  // count + scatter per position (nl_tune("sort_algo", 1))
   // keys per thread and tile in the scatter: 16 KB of keys per tile for either key width
   constexpr int ITEMS = (sizeof(UK) == 4) ? NL_SORT_ITEMS32 : kSortItems;
   constexpr int TILE = kSortBlock * ITEMS;
@@ -607,6 +720,37 @@ int launch_sort(void *stream, int sm_count, int dtype, void *keys, void *tmp, in
     case NL_U64: return sort_impl<unsigned long long, 2>(st, sm_count, keys, tmp, n);
     default: set_error("nl_sort: unsupported dtype %d", dtype); return NL_ERR_UNSUPPORTED;
   }
+}
+
+#define NL_SORT_DISPATCH(CALL)                                                              \
+  switch (dtype) {                                                                         \
+    /* (key kind: 0 signed integer, 1 float, 2 unsigned integer) */                        \
+    case NL_I32: return CALL(uint32_t, 0);                                                 \
+    case NL_I64: return CALL(unsigned long long, 0);                                       \
+    case NL_F32: return CALL(uint32_t, 1);                                                 \
+    case NL_F64: return CALL(unsigned long long, 1);                                       \
+    case NL_I8: return CALL(uint8_t, 0);                                                   \
+    case NL_I16: return CALL(uint16_t, 0);                                                 \
+    case NL_U8: return CALL(uint8_t, 2);                                                   \
+    case NL_U16: return CALL(uint16_t, 2);                                                 \
+    case NL_U32: return CALL(uint32_t, 2);                                                 \
+    case NL_U64: return CALL(unsigned long long, 2);                                       \
+    default: set_error("nl_sort: unsupported dtype %d", dtype); return NL_ERR_UNSUPPORTED; \
+  }
+
+int launch_sort_sample(void *stream, int dtype, const void *keys, int64_t n, int k, unsigned long long *host_out) {
+  cudaStream_t st = (cudaStream_t)stream;
+#define NL_CALL(UK, KF) sample_impl<UK, KF>(st, keys, n, k, host_out)
+  NL_SORT_DISPATCH(NL_CALL)
+#undef NL_CALL
+}
+
+int launch_sort_split(void *stream, int sm_count, int dtype, const void *keys, void *out, int64_t n, const unsigned long long *splitters, int m,
+                      int64_t *host_counts) {
+  cudaStream_t st = (cudaStream_t)stream;
+#define NL_CALL(UK, KF) split_impl<UK, KF>(st, sm_count, keys, out, n, splitters, m, host_counts)
+  NL_SORT_DISPATCH(NL_CALL)
+#undef NL_CALL
 }
 
 }  // namespace nl

@@ -105,3 +105,40 @@ def test_one_sweep_chains_its_launches(rt, dtype, n):
         finally:
             abi.check(rt.lib.nl_tune(b"sort_portion_log2", 0))
         assert got.tobytes() == np.sort(x).tobytes()
+
+
+def order_keys(x):
+    """nl_sort's order-preserving bijection, widened to 64 bits (integers only here)."""
+    dt = x.dtype
+    u = x.view(np.dtype(f"u{dt.itemsize}")).astype(np.uint64)
+    if dt.kind == "i":
+        u ^= np.uint64(1 << (8 * dt.itemsize - 1))
+    return u
+
+
+@pytest.mark.parametrize("dtype", [np.int8, np.uint16, np.int32, np.int64, np.uint64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [1, 1000, 8192, 300_001])
+@pytest.mark.parametrize("m", [1, 7, 15])
+def test_split_groups_stably_at_the_splitters(rt, dtype, n, m):
+    """nl_sort_sample / nl_sort_split: the device steps of the sort across GPUs."""
+    rng = np.random.default_rng(n + m)
+    info = np.iinfo(dtype)
+    x = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    d, out = rt.upload(x), rt.empty(dtype, n)
+    k = 64
+    samples = (C.c_uint64 * k)()
+    abi.check(rt.lib.nl_sort_sample(d.dev, 0, abi.nl_dtype_of(dtype), C.c_void_p(d.ptr), n, k, samples))
+    rt.sync()
+    assert np.array_equal(np.array(samples[:], dtype=np.uint64), order_keys(x[(np.arange(k) * n) // k]))
+    spl = np.sort(order_keys(rng.integers(info.min, info.max, size=m, dtype=dtype, endpoint=True)))
+    if m > 1:
+        spl[1] = spl[0]                     # an empty run in the middle
+    counts = (C.c_int64 * (m + 1))()
+    abi.check(rt.lib.nl_sort_split(d.dev, 0, abi.nl_dtype_of(dtype), C.c_void_p(d.ptr), C.c_void_p(out.ptr), n,
+                                   spl.ctypes.data_as(C.POINTER(C.c_uint64)), m, counts))
+    rt.sync()
+    run = np.searchsorted(spl, order_keys(x), side="left")      # number of splitters below the key
+    want = x[np.argsort(run, kind="stable")]
+    assert list(counts) == np.bincount(run, minlength=m + 1).tolist()
+    assert np.array_equal(rt.download(out), want)
+    d.free(); out.free()
