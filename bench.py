@@ -497,6 +497,17 @@ def _reduce_device(rt, abi, Expr, op, dtype, ptr, n, sizes):
     return v
 
 
+def _sum_of_squares(rt, abi, Expr, dtype, ptr, n, sizes):
+    res = rt.empty(dtype, 1)
+    e = Expr(dtype)
+    a = e.array()
+    e.materialize(e.sum(e.mul(a, e.ref(a))))
+    rt.launch(abi.compile_plan(e), [res.ptr], [ptr], 0, n, sizes.ptr)
+    v = rt.download(res)[0]
+    res.free()
+    return v
+
+
 def sort_properties(rt, abi, Expr, lib, x, n, dt, sum_before, sizes):
     """Full-size checks of the device sort: no inversion anywhere (count of y[i+1] < y[i] is zero) and,
     for integers, the wrapping sum is unchanged (same multiset)."""
@@ -894,7 +905,7 @@ def run_extra(args, rt, lib, ranks, peak, timed, threads):
     if G == 1 and not args.no_sort:
         n6 = 1 << args.log2n_sort
         for dt, kind, nm, sid in ((np.int64, 1, "i64 full range", "sort i64"), (np.float64, 3, "f64 in [0,1)", "sort f64"),
-                                  (np.int64, 0, "i64 in [1,100) like Tests/", "sort i64 1..99")):
+                                  (np.int32, 1, "i32 full range", "sort i32"), (np.int64, 0, "i64 in [1,100) like Tests/", "sort i64 1..99")):
             x = rt.empty(dt, n6)
             tmp = rt.empty(dt, n6)
             best, passes, sum_before, before = None, 0, None, None
@@ -902,7 +913,9 @@ def run_extra(args, rt, lib, ranks, peak, timed, threads):
                 rt.fill(x, 0, 5 + rep, kind)
                 if np.dtype(dt).kind == "i":
                     sum_before = _reduce_device(rt, abi, Expr, abi.OP_SUM, dt, x.ptr, n6, sizes)
-                before = device_checksum(rt, lib, x.ptr, 8 * n6, csum)
+                # 8-byte keys: sum / xor of the 64-bit words; 4-byte keys pair up differently after the sort, so their
+                # second permutation-invariant figure is the wrapping sum of squares
+                before = device_checksum(rt, lib, x.ptr, 8 * n6, csum) if np.dtype(dt).itemsize == 8 else _sum_of_squares(rt, abi, Expr, dt, x.ptr, n6, sizes)
                 rt.sync()
                 l0 = lib.nl_launch_count()
                 e0, e1 = rt.event(), rt.event()
@@ -913,9 +926,9 @@ def run_extra(args, rt, lib, ranks, peak, timed, threads):
                 ms1 = rt.elapsed_ms(e0, e1)
                 best = ms1 if best is None else min(best, ms1)
                 passes = lib.nl_launch_count() - l0
-            after = device_checksum(rt, lib, x.ptr, 8 * n6, csum)
+            after = device_checksum(rt, lib, x.ptr, 8 * n6, csum) if np.dtype(dt).itemsize == 8 else _sum_of_squares(rt, abi, Expr, dt, x.ptr, n6, sizes)
             props = sort_properties(rt, abi, Expr, lib, x, n6, dt, sum_before, sizes)
-            props["same_multiset_checksums"] = before[:2] == after[:2]
+            props["same_multiset_checksums"] = (before[:2] == after[:2]) if np.dtype(dt).itemsize == 8 else bool(before == after)
             good = props["inversions"] == 0 and props["same_multiset_checksums"] and props.get("sum_unchanged", True)
             out.append({"id": sid, "config": f"sort() device radix sort, {nm}", "dtype": np.dtype(dt).name, "elements_per_gpu": n6,
                         "ms_per_step": round(best, 4), "Gkeys/s": round(n6 / best / 1e6, 2), "kernel_launches": int(passes),
@@ -923,6 +936,28 @@ def run_extra(args, rt, lib, ranks, peak, timed, threads):
                         "parity": ("bit-exact by properties: " if good else "MISMATCH: ") + "zero inversions over all keys and unchanged sum/xor checksums (sorted permutation of the input)"})
             x.free(); tmp.free()
     sizes.free(); csum.free()
+    # sort() ACROSS the GPUs is the one-process mode of the jit drop-in (sample sort over NVLink, csrc/jit/device_sort.cpp):
+    # rank 0 runs it in a process of its own over all G devices while the ranks — one GPU each — wait with empty pools
+    if G > 1 and not args.no_sort:
+        abi.check(lib.nl_pool_trim(0))
+        ranks.barrier()
+        if ranks.rank == 0:
+            try:
+                env = dict(os.environ, NL_DEVICES=str(G))
+                for k_ in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "CUDA_VISIBLE_DEVICES"):
+                    env.pop(k_, None)
+                tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "jit_sort_bench.py")
+                res = subprocess.run([sys.executable, tool, str(min(args.log2n_sort, 27)), "int64", "--json"], env=env, stdout=subprocess.PIPE,
+                                     stderr=subprocess.PIPE, text=True, timeout=600)
+                line = [l for l in res.stdout.splitlines() if l.startswith("{")]
+                if res.returncode == 0 and line:
+                    row = json.loads(line[-1])
+                    out.append(row)
+                else:
+                    out.append({"id": f"sort x{G}", "parity": "unchecked", "error": (res.stderr or res.stdout)[-400:]})
+            except Exception as exc:
+                out.append({"id": f"sort x{G}", "parity": "unchecked", "error": f"{type(exc).__name__}: {exc}"})
+        ranks.barrier()
     return out
 
 
