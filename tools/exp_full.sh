@@ -1,2 +1,3 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest4.log 2>&1; tail -3 gpurun_out/r2_pytest4.log
-python bench.py > gpurun_out/r2_bench_n1_v3.json 2> gpurun_out/r2_bench_n1_v3.err; tail -c 1500 gpurun_out/r2_bench_n1_v3.json
+python tools/sort_bench.py 28 0 > gpurun_out/r2_sort_bench.txt 2>&1; cat gpurun_out/r2_sort_bench.txt
+ncu --set full --clock-control none --import-source on --kernel-name-base function -k onesweep_kernel -s 9 -c 1 -f -o gpurun_out/r2_sort_onesweep python tools/sort_bench.py 27 0 > gpurun_out/r2_sort_ncu.log 2>&1; tail -2 gpurun_out/r2_sort_ncu.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2_sort_launches.csv python tools/sort_bench.py 28 0 > /dev/null 2>&1; tail -3 gpurun_out/r2_sort_launches.csv
