@@ -63,6 +63,16 @@ __device__ __forceinline__ UK order_key(UK bits) {
   }
 }
 
+// the float order key back to the float's bit pattern
+template <typename UK>
+__device__ __forceinline__ UK float_bits_of_order_key(UK ordered) {
+  constexpr int B = sizeof(UK) * 8;
+  constexpr UK SIGN = (UK)1 << (B - 1);
+  constexpr UK NEG_INF = (sizeof(UK) == 8) ? (UK)0x000FFFFFFFFFFFFFull : (UK)0x007FFFFFu;
+  const UK k = (UK)(ordered + NEG_INF);
+  return (k & SIGN) ? (UK)(k ^ SIGN) : (UK)~k;
+}
+
 template <typename UK, int kFloat>
 __global__ void __launch_bounds__(kSortBlock) sort_histogram_kernel(const UK *__restrict__ keys, long long n,
                                                                      unsigned long long *__restrict__ ghist /*[sizeof(UK)][256]*/) {
@@ -304,8 +314,10 @@ struct SplitDigit {
   int m;
   __device__ __forceinline__ unsigned int operator()(UK ordered) const {
     unsigned int d = 0;
-#pragma unroll
-    for (int j = 0; j < kMaxSplitters; j++) d += (j < m && s[j] < ordered) ? 1u : 0u;
+    // m is uniform and the splitters sit in the kernel's parameter bank: a real loop of m compares (a sort over two
+    // GPUs pays one compare per key, not fifteen predicated ones)
+#pragma unroll 1
+    for (int j = 0; j < m; j++) d += (s[j] < ordered) ? 1u : 0u;
     return d;
   }
 };
@@ -318,7 +330,10 @@ struct SweepShared {             // views into the CTA's dynamic shared memory
   int *next_tile;
 };
 
-template <typename UK, int kFloat, int ITEMS, int CH, bool FULL, typename Digit>
+// kIn: how a loaded key becomes its order key (0 signed integer, 1 float, 2 it already is one).  kOut: what is written —
+// 0 the loaded bits, 1 the order key, 2 the float bits of a loaded order key.  A float sort of several positions
+// converts its keys in the first sweep and back in the last one; the sweeps between them run as unsigned integers.
+template <typename UK, int kIn, int kOut, int ITEMS, int CH, bool FULL, typename Digit>
 __device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, const Digit &digit, long long dstart,
                                            unsigned long long *__restrict__ bins_out, unsigned int *__restrict__ desc, unsigned int *__restrict__ ticket,
                                            int tile, int n_tiles, const SweepShared &sh) {
@@ -343,7 +358,7 @@ __device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__rest
     }
 #pragma unroll
     for (int i = 0; i < CH; i++) {
-      const unsigned int d = digit(order_key<UK, kFloat>(key[i]));
+      const unsigned int d = digit(order_key<UK, kIn>(key[i]));
       if (FULL || (warp * (32 * ITEMS) + (i0 + i) * 32 + lane < valid)) atomicAdd(&cw[d], 1u);
     }
   }
@@ -391,7 +406,8 @@ __device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__rest
     }
 #pragma unroll
     for (int i = 0; i < CH; i++) {
-      const unsigned int d = digit(order_key<UK, kFloat>(key[i]));
+      const UK ordered = order_key<UK, kIn>(key[i]);
+      const unsigned int d = digit(ordered);
       const bool ok = FULL || (warp * (32 * ITEMS) + (i0 + i) * 32 + lane < valid);
       unsigned int m = match_digit(d);
       if (!FULL) m &= __ballot_sync(0xffffffffu, ok);
@@ -399,7 +415,7 @@ __device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__rest
       if (ok) before = cw[d];
       __syncwarp();
       if (ok && (m & lt) == 0) cw[d] = before + __popc(m);
-      if (ok) staged[before + __popc(m & lt)] = key[i];
+      if (ok) staged[before + __popc(m & lt)] = (kOut == 1) ? ordered : key[i];
       __syncwarp();
     }
   }
@@ -439,20 +455,20 @@ __device__ __forceinline__ void sweep_tile(const UK *__restrict__ in, UK *__rest
     const int pos = i * kSortBlock + tid;
     if (FULL || pos < valid) {
       const UK k = staged[pos];
-      const unsigned int d = digit(order_key<UK, kFloat>(k));
-      out[sh.gdelta[d] + (long long)pos] = k;
+      const unsigned int d = digit((kOut == 1) ? k : order_key<UK, kIn>(k));
+      out[sh.gdelta[d] + (long long)pos] = (kOut == 2) ? float_bits_of_order_key<UK>(k) : k;
     }
   }
 }
 
-template <typename UK, int kFloat, int ITEMS, int CH, typename Digit>
+template <typename UK, int kIn, int kOut, int ITEMS, int CH, typename Digit>
 __device__ __noinline__ void sweep_partial_tile(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, const Digit &digit, long long dstart,
                                                 unsigned long long *__restrict__ bins_out, unsigned int *__restrict__ desc, unsigned int *__restrict__ ticket,
                                                 int tile, int n_tiles, const SweepShared &sh) {
-  sweep_tile<UK, kFloat, ITEMS, CH, false>(in, out, n, digit, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
+  sweep_tile<UK, kIn, kOut, ITEMS, CH, false>(in, out, n, digit, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
 }
 
-template <typename UK, int kFloat, int ITEMS, int CH, int MINCTAS, typename Digit>
+template <typename UK, int kIn, int kOut, int ITEMS, int CH, int MINCTAS, typename Digit>
 __global__ void __launch_bounds__(kSortBlock, MINCTAS) onesweep_kernel(const UK *__restrict__ in, UK *__restrict__ out, unsigned int n, const __grid_constant__ Digit digit,
                                                                        const unsigned long long *__restrict__ bins_in /*[256]: where each digit continues in out*/,
                                                                        unsigned long long *__restrict__ bins_out /*[256] for the next launch, or null*/,
@@ -477,9 +493,9 @@ __global__ void __launch_bounds__(kSortBlock, MINCTAS) onesweep_kernel(const UK 
     const int tile = sh_tile;
     if (tile >= n_tiles) break;
     if ((unsigned int)(tile + 1) * TILE <= n)
-      sweep_tile<UK, kFloat, ITEMS, CH, true>(in, out, n, digit, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
+      sweep_tile<UK, kIn, kOut, ITEMS, CH, true>(in, out, n, digit, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
     else
-      sweep_partial_tile<UK, kFloat, ITEMS, CH>(in, out, n, digit, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
+      sweep_partial_tile<UK, kIn, kOut, ITEMS, CH>(in, out, n, digit, dstart, bins_out, desc, ticket, tile, n_tiles, sh);
   }
 }
 
@@ -514,12 +530,12 @@ void set_sort_algo(int a) { g_sort_algo = a; }
 
 // one sweep of `n` keys src -> dst, grouped by `digit`, in launches of at most one portion; bins[0..255] = where each
 // group starts in dst (bins[256..511] is the second half of the double buffer the launches hand over through)
-template <typename UK, int kFloat, typename Digit>
+template <typename UK, int kIn, int kOut, typename Digit>
 static int run_sweep(cudaStream_t st, int sm_count, const UK *src, UK *dst, int64_t n, const Digit &digit, unsigned long long *bins, unsigned int **scratch_io,
                      size_t *scratch_bytes_io) {
   using Shape = SweepShape<sizeof(UK)>;
   constexpr int ITEMS = Shape::items, TILE = kSortBlock * ITEMS;
-  auto kern = onesweep_kernel<UK, kFloat, ITEMS, Shape::batch, Shape::ctas, Digit>;
+  auto kern = onesweep_kernel<UK, kIn, kOut, ITEMS, Shape::batch, Shape::ctas, Digit>;
   const size_t smem = sizeof(UK) * TILE + sizeof(unsigned int) * 256 * kSortWarps + sizeof(long long) * 256 + 64;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
@@ -559,14 +575,30 @@ static int onesweep_passes(cudaStream_t st, int sm_count, UK *&src, UK *&dst, in
   CUDA_TRY(cudaMallocAsync((void **)&bins, sizeof(unsigned long long) * P * 512, st));
   digit_starts_kernel<<<P, kSortBlock, 0, st>>>(ghist, bins);
   count_launch();
+  int todo[P], n_todo = 0;
   for (int p = 0; p < P; p++) {
     bool trivial = false;
     for (int d = 0; d < 256; d++)
       if (host_hist[p * 256 + d] == (unsigned long long)n) trivial = true;   // every key has the same digit here
-    if (trivial) continue;
+    if (!trivial) todo[n_todo++] = p;
+  }
+  for (int i = 0; i < n_todo; i++) {
+    const int p = todo[i];
     RadixDigit<UK> digit;
     digit.shift = 8 * p;
-    const int rc = run_sweep<UK, kFloat>(st, sm_count, src, dst, n, digit, bins + (size_t)p * 512, &scratch, &scratch_bytes);
+    unsigned long long *b = bins + (size_t)p * 512;
+    int rc = NL_OK;
+    bool done = false;
+    if constexpr (kFloat == 1) {
+      // floats: order keys are made in the first sweep and turned back in the last one
+      if (n_todo > 1) {
+        if (i == 0) rc = run_sweep<UK, 1, 1>(st, sm_count, src, dst, n, digit, b, &scratch, &scratch_bytes);
+        else if (i == n_todo - 1) rc = run_sweep<UK, 2, 2>(st, sm_count, src, dst, n, digit, b, &scratch, &scratch_bytes);
+        else rc = run_sweep<UK, 2, 0>(st, sm_count, src, dst, n, digit, b, &scratch, &scratch_bytes);
+        done = true;
+      }
+    }
+    if (!done) rc = run_sweep<UK, kFloat, 0>(st, sm_count, src, dst, n, digit, b, &scratch, &scratch_bytes);
     if (rc != NL_OK) return rc;
     UK *t = src; src = dst; dst = t;
   }
@@ -642,7 +674,7 @@ static int split_impl(cudaStream_t st, int sm_count, const void *keys, void *out
   CUDA_TRY(cudaMemcpyAsync(host_counts, ghist, sizeof(unsigned long long) * (size_t)(m + 1), cudaMemcpyDeviceToHost, st));
   unsigned int *scratch = nullptr;
   size_t scratch_bytes = 0;
-  const int rc = run_sweep<UK, kFloat>(st, sm_count, (const UK *)keys, (UK *)out, n, digit, bins, &scratch, &scratch_bytes);
+  const int rc = run_sweep<UK, kFloat, 0>(st, sm_count, (const UK *)keys, (UK *)out, n, digit, bins, &scratch, &scratch_bytes);
   if (rc != NL_OK) return rc;
   if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
   CUDA_TRY(cudaFreeAsync(ghist, st));
