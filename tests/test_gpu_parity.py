@@ -589,3 +589,33 @@ def test_sort_new_integer_types(rt, dtype, n):
     d = rt.upload(x)
     rt.sort(d)
     assert rt.download(d).tobytes() == np.sort(x).tobytes()
+
+
+def test_large_blocks_are_recycled_by_size_class(rt, nl):
+    """nl_malloc / nl_free: a block above 1 MiB comes back for the next request of its size class (sizes that differ by
+    a few elements — filter outputs, sort buckets — must not make the pool map fresh memory at every evaluate), a
+    live block is never handed out twice, small blocks and nl_pool_trim() bypass / empty the cache."""
+    def alloc(nbytes):
+        p = C.c_void_p()
+        abi.check(nl.nl_malloc(0, nbytes, C.byref(p)))
+        return p.value
+    abi.check(nl.nl_pool_trim(0))
+    a = alloc((3 << 20) + 8)
+    abi.check(nl.nl_free(0, C.c_void_p(a)))
+    b = alloc((3 << 20) + 4096)                 # same class (granule 2 MiB at this size): the parked block
+    assert b == a
+    c = alloc((3 << 20) + 8)                    # the class's block is live: a different one
+    assert c != b
+    abi.check(nl.nl_free(0, C.c_void_p(b)))
+    abi.check(nl.nl_free(0, C.c_void_p(c)))
+    assert {alloc(3 << 20), alloc(3 << 20)} == {b, c}
+    abi.check(nl.nl_free(0, C.c_void_p(b)))
+    abi.check(nl.nl_free(0, C.c_void_p(c)))
+    x = rt.upload(np.arange(1 << 19, dtype=np.int64))          # 4 MiB: takes a parked block; its content must be its own
+    assert np.array_equal(rt.download(x), np.arange(1 << 19, dtype=np.int64))
+    x.free()
+    abi.check(nl.nl_pool_trim(0))               # empties the cache (and the pool): everything still works afterwards
+    d = alloc((3 << 20) + 8)
+    abi.check(nl.nl_free(0, C.c_void_p(d)))
+    s = alloc(1000)                             # small blocks go straight to the stream-ordered pool
+    abi.check(nl.nl_free(0, C.c_void_p(s)))

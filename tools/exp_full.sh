@@ -1,2 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_bench_n2_v2.json 2> gpurun_out/r2_bench_n2_v2.err
-tail -c 2500 gpurun_out/r2_bench_n2_v2.json; tail -5 gpurun_out/r2_bench_n2_v2.err
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_2gpu_v2.log 2>&1; tail -3 gpurun_out/r2_pytest_2gpu_v2.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
