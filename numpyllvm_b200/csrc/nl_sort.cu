@@ -521,9 +521,9 @@ __global__ void __launch_bounds__(kSortBlock) digit_starts_kernel(const unsigned
 
 template <int BYTES> struct SweepShape;                  // keys per thread, keys per batch of the second read, resident CTAs per SM
 template <> struct SweepShape<8> { static constexpr int items = 24, batch = 8, ctas = 3; };
-template <> struct SweepShape<4> { static constexpr int items = 32, batch = 16, ctas = 4; };
-template <> struct SweepShape<2> { static constexpr int items = 32, batch = 16, ctas = 4; };
-template <> struct SweepShape<1> { static constexpr int items = 32, batch = 16, ctas = 4; };
+template <> struct SweepShape<4> { static constexpr int items = 32, batch = 8, ctas = 4; };
+template <> struct SweepShape<2> { static constexpr int items = 32, batch = 8, ctas = 4; };
+template <> struct SweepShape<1> { static constexpr int items = 32, batch = 8, ctas = 4; };
 
 static int g_sort_algo = 0;          // 0: one sweep per position (default); 1: count + scatter per position
 void set_sort_algo(int a) { g_sort_algo = a; }

@@ -887,16 +887,17 @@ int main(int argc, char **argv) {
     B.init(n);
     B.run_cub();
     RUN(B, 256, 16, 2, 3, 4);
-    RUNV(5, B, 256, 16, 8, 4, 4);
-    RUNV(5, B, 256, 16, 8, 5, 4);
-    RUNV(5, B, 256, 16, 16, 4, 4);
     RUNV(5, B, 256, 24, 8, 3, 4);
+    RUNV(5, B, 256, 24, 4, 3, 4);
+    RUNV(5, B, 256, 24, 12, 3, 4);
+    RUNV(5, B, 256, 24, 8, 3, 2);
+    RUNV(5, B, 256, 24, 8, 3, 3);
+    RUNV(5, B, 256, 20, 4, 3, 4);
+    RUNV(5, B, 256, 20, 4, 4, 4);
+    RUNV(5, B, 256, 28, 4, 3, 4);
     RUNV(5, B, 256, 32, 8, 3, 4);
-    RUNV(5, B, 256, 32, 16, 2, 4);
-    RUNV(5, B, 512, 16, 8, 2, 4);
-    RUNV(5, B, 512, 16, 16, 2, 4);
-    RUNV(5, B, 512, 8, 8, 4, 4);
-    RUNV(5, B, 1024, 8, 8, 1, 4);
+    RUNV(5, B, 384, 16, 8, 2, 4);
+    RUNV(5, B, 384, 16, 8, 3, 4);
     RUNV(3, B, 256, 16, 1, 3, 8);
     CK(cudaFree(B.src)); CK(cudaFree(B.a)); CK(cudaFree(B.b));
   }
@@ -905,11 +906,13 @@ int main(int argc, char **argv) {
     Bench<unsigned int> B;
     B.init(n);
     B.run_cub();
-    RUNV(4, B, 256, 32, 2, 3, 4);
     RUNV(5, B, 256, 32, 16, 4, 4);
-    RUNV(5, B, 256, 32, 8, 5, 4);
-    RUNV(5, B, 512, 32, 8, 2, 4);
-    RUNV(5, B, 512, 16, 8, 3, 4);
+    RUNV(5, B, 256, 32, 8, 4, 4);
+    RUNV(5, B, 256, 32, 16, 4, 2);
+    RUNV(5, B, 256, 40, 8, 3, 4);
+    RUNV(5, B, 256, 48, 16, 3, 4);
+    RUNV(5, B, 384, 32, 16, 2, 4);
+    RUNV(5, B, 512, 16, 16, 3, 4);
   }
   return 0;
 }
