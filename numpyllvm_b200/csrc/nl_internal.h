@@ -34,6 +34,7 @@ struct KParams {
   unsigned long long *tile_desc;  // decoupled look-back descriptors, n_tiles entries, zeroed
   unsigned int *tile_ticket;      // dynamic tile counter, zeroed
   unsigned int *sm_rank;          // per SM (%smid): CTAs of this launch that have started there, zeroed (compaction)
+  unsigned int *done_ctas;        // super-tile kernel: CTAs that have left their loop; the last one cleans up for the next launch
   unsigned long long *red_partials;  // one 8-byte partial per CTA
   unsigned int *red_ticket;       // self-resetting
   uint32_t step[NL_MAX_STEPS];

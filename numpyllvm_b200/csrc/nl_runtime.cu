@@ -43,6 +43,7 @@ constexpr size_t kTileDescOff = kSmRankOff + 1024;                  // 8 B x n_t
 struct Scratch {
   char *base = nullptr;
   size_t bytes = 0;
+  bool compact_clean = false;    // ticket, ranks and EVERY descriptor are zero (the super-tile kernel leaves them so)
 };
 
 struct Device {
@@ -69,6 +70,7 @@ constexpr size_t kMailboxBytes = 2 * (size_t)kMaxWorld * 16 + 64;   // [2 pariti
 static unsigned long long g_peer_timeout_ns = 10ull * 1000 * 1000 * 1000;   // bound on a kernel's wait for a peer (nl_tune "peer_timeout_ms")
 void set_peer_timeout_ms(int ms) { g_peer_timeout_ns = (unsigned long long)(ms > 0 ? ms : 10000) * 1000ull * 1000ull; }
 static bool g_peer_ready = false;
+static bool g_trust_self_clean = true;    // nl_tune("compact_self_clean", 0): clear the compaction arena in front of every launch, as round 1 did
 static void *g_ipc_mapped[NL_MAX_DEVICES][kMaxWorld];          // IPC mappings to close at destroy
 
 // NVTX range around every pipeline launch (what PrintPipeline's progress lines were for, debug_printer.cpp:131-160;
@@ -122,8 +124,9 @@ static int ensure_scratch(Device &d, int stream, size_t need) {
   }
   size_t want = need + (need >> 2) + (1u << 20);
   CUDA_TRY(cudaMalloc((void **)&s.base, want));
-  CUDA_TRY(cudaMemsetAsync(s.base, 0, kTileDescOff, d.stream[stream]));
+  CUDA_TRY(cudaMemsetAsync(s.base, 0, want, d.stream[stream]));
   s.bytes = want;
+  s.compact_clean = true;
   return NL_OK;
 }
 
@@ -702,9 +705,20 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
   kp.red_partials = (unsigned long long *)(sb + kRedPartialsOff);
   kp.tile_ticket = (unsigned int *)(sb + kTileTicketOff);
   kp.sm_rank = (unsigned int *)(sb + kSmRankOff);
+  kp.done_ctas = (unsigned int *)(sb + kTileTicketOff + 128);
   kp.tile_desc = (unsigned long long *)(sb + kTileDescOff);
-  if (compact)
-    CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE, d.stream[stream]));
+  if (compact) {
+    Scratch &sc = d.scratch[stream];
+    if (kp.super_k > 0) {
+      // the super-tile kernel cleans up after itself (nl_compact_super.cuh): nothing to clear unless another
+      // compaction kernel left its descriptors behind
+      if (!sc.compact_clean || !g_trust_self_clean) CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (sc.compact_clean ? (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE : sc.bytes - kTileDescOff), d.stream[stream]));
+      sc.compact_clean = true;
+    } else {
+      CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE, d.stream[stream]));
+      sc.compact_clean = false;
+    }
+  }
 
   LaunchInfo info;
   if (fuse_finish) d.epoch++;
@@ -1098,6 +1112,8 @@ int nl_tune(const char *key, int value) {
   } else if (!strcmp(key, "sort_algo")) {
     if (value < 0 || value > 1) { set_error("nl_tune(sort_algo): 0 one sweep per position (default), 1 count + scatter"); return NL_ERR_INVALID; }
     set_sort_algo(value);
+  } else if (!strcmp(key, "compact_self_clean")) {
+    g_trust_self_clean = value != 0;
   } else if (!strcmp(key, "sort_portion_log2")) {
     if (value != 0 && (value < 13 || value > 28)) { set_error("nl_tune(sort_portion_log2): 13 .. 28 (0: default 28)"); return NL_ERR_INVALID; }
     set_sort_portion_log2(value ? value : 28);
@@ -1108,7 +1124,7 @@ int nl_tune(const char *key, int value) {
   } else if (!strcmp(key, "reset")) {
     set_peer_timeout_ms(0);
     set_compact_pipe_enabled(1); set_compact_prefer_pipe(0); set_compact_pipe_dynamic(0); set_compact_pipe_side(1);
-    set_compact_pipe_lag(0); set_max_ctas_per_sm(0); set_poll_sleep_ns(0); set_sort_algo(0); set_sort_portion_log2(28);
+    set_compact_pipe_lag(0); set_max_ctas_per_sm(0); set_poll_sleep_ns(0); set_sort_algo(0); set_sort_portion_log2(28); g_trust_self_clean = true;
   } else {
     set_error("nl_tune: unknown key '%s'", key);
     return NL_ERR_INVALID;
