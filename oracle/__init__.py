@@ -22,12 +22,26 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
+    """Compile the C restatement when a source is newer than the library.  Several ranks of one bench run may get
+    here at the same moment (a header touched after the last build): the check and the build sit behind a file lock,
+    and make writes to a private name that is renamed into place, so nobody ever loads a half-written file."""
+    import fcntl
     srcs = [os.path.join(_DIR, f) for f in ("nl_oracle.c", "nl_oracle_eval.inc", "nl_oracle.h")]
     srcs.append(os.path.join(_DIR, "..", "include", "nl_abi.h"))
-    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs if os.path.exists(s))
-    if force or stale:
-        subprocess.run(["make", "-C", _DIR, "-B" if force else "-s", "libnloracle.so"], check=True,
-                       stdout=subprocess.DEVNULL)
+
+    def stale():
+        return (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs if os.path.exists(s))
+    if not (force or stale()):
+        return _SO
+    with open(os.path.join(_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or stale():
+                tmp = f"libnloracle.{os.getpid()}.tmp.so"
+                subprocess.run(["make", "-C", _DIR, "-B", "-s", tmp], check=True, stdout=subprocess.DEVNULL)
+                os.replace(os.path.join(_DIR, tmp), _SO)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 
