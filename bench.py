@@ -471,7 +471,10 @@ def run_e2e_jit(args, ranks, n):
         out = step()
         del out
     jit.synchronize()
-    dt = ranks.max(time.perf_counter() - t0)
+    mine = time.perf_counter() - t0
+    dt = ranks.max(mine)
+    # every rank's own time: on a box whose GPUs sit behind two sockets the ranks far from the host buffers are the slow ones
+    by_rank = [round(1e3 * ranks.max(mine if ranks.rank == r else 0.0) / k, 1) for r in range(G)] if G > 1 else None
     ranks.barrier()
     ok = ranks.max(0.0 if ok else 1.0) == 0.0
     res = {"value": round(G * (12 * n_e + 4) * k / dt / 1e9, 2), "unit": "GB/s",
@@ -481,6 +484,8 @@ def run_e2e_jit(args, ranks, n):
            "overlap": "upload (copy stream), kernel (compute stream) and download (copy-back stream) pipelined in 32 MiB chunks",
            "bound": "PCIe: 8 bytes up and 4 bytes down per element for 12 algorithmic bytes",
            "parity": verdict(ok, f"all {n_e} elements of the host result on every rank")}
+    if by_rank:
+        res["ms_per_step_by_rank"] = by_rank
     if note:
         res["note"] = note
     return res
