@@ -144,8 +144,29 @@ Storage *device_sort(Storage *in) {
   const size_t S = in->shards.size();
   int nonempty = 0;
   for (const Shard &sh : in->shards) nonempty += sh.count > 0;
-  if (G == 1 || nonempty <= 1) {
-    // one run: sort a copy, then lay it out as a regular column
+  if (G == 1) {
+    // one device: the copy the sort works on IS the result column (one shard of exactly `total` elements)
+    Storage *out = storage_new(dtype, total);
+    if (storage_alloc_shards(out) < 0) { storage_decref(out); return nullptr; }
+    const Shard &src = in->shards[0];
+    Shard &dst = out->shards[0];
+    if (total > 0) {
+      void *tmp = nullptr;
+      rc = nl_memcpy_d2d(dst.dev, 0, dst.ptr, src.ptr, (size_t)total * es);
+      if (rc == NL_OK && total > 1) rc = nl_malloc(dst.dev, (size_t)total * es, &tmp);
+      if (rc == NL_OK && total > 1) {
+        Py_BEGIN_ALLOW_THREADS
+        rc = nl_sort(dst.dev, 0, dtype, dst.ptr, tmp, total);
+        Py_END_ALLOW_THREADS
+      }
+      if (tmp) nl_free(dst.dev, tmp);
+      if (rc == NL_OK) rc = sync_devices(G);
+      if (rc != NL_OK) { storage_decref(out); return fail(rc, "jit: device sort failed"); }
+    }
+    return out;
+  }
+  if (nonempty <= 1) {
+    // one run on one of several devices: sort a copy, then lay it out as a regular column
     std::vector<Buf> sorted(S);
     for (size_t g = 0; g < S && rc == NL_OK; g++) rc = sorted_copy(in->shards[g], dtype, es, &sorted[g]);
     if (rc == NL_OK) rc = sync_devices(G);

@@ -70,6 +70,7 @@ constexpr size_t kMailboxBytes = 2 * (size_t)kMaxWorld * 16 + 64;   // [2 pariti
 static unsigned long long g_peer_timeout_ns = 10ull * 1000 * 1000 * 1000;   // bound on a kernel's wait for a peer (nl_tune "peer_timeout_ms")
 void set_peer_timeout_ms(int ms) { g_peer_timeout_ns = (unsigned long long)(ms > 0 ? ms : 10000) * 1000ull * 1000ull; }
 static bool g_peer_ready = false;
+static bool g_logical = false;            // two devices of the runtime share a GPU (NL_LOGICAL_DEVICES)
 static bool g_trust_self_clean = true;    // nl_tune("compact_self_clean", 0): clear the compaction arena in front of every launch, as round 1 did
 static void *g_ipc_mapped[NL_MAX_DEVICES][kMaxWorld];          // IPC mappings to close at destroy
 
@@ -189,6 +190,10 @@ extern "C" {
 int nl_init(int n_devices, const int *device_ids) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_ndev > 0) return NL_OK;   // idempotent
+  // logical devices share one CUDA context: a kernel of one device may wait in its mailbox for a kernel of another,
+  // and loading that second kernel lazily at its first launch would wait for the first one (CUDA's lazy module
+  // loading may synchronise the context) — load everything when the context is created
+  if (!device_ids && getenv("NL_LOGICAL_DEVICES")) setenv("CUDA_MODULE_LOADING", "EAGER", 0);
   int visible = 0;
   cudaError_t e = cudaGetDeviceCount(&visible);
   if (e != cudaSuccess || visible == 0) {
@@ -196,9 +201,26 @@ int nl_init(int n_devices, const int *device_ids) {
     cudaGetLastError();
     return NL_ERR_NO_DEVICE;
   }
+  // NL_LOGICAL_DEVICES=k: k devices of the runtime laid over the visible GPUs round-robin.  Every logical device has
+  // its own streams, scratch arena and mailbox, so the multi-shard paths — the in-kernel exchange between devices,
+  // the count scan of filters, repartition, the sort across devices — run on a box with ONE GPU exactly as they do
+  // between GPUs (peer stores land in the same HBM instead of crossing NVLink; NCCL, which refuses two ranks on
+  // one GPU, is left out: the fused finish is the only one).  For the tests; tests/test_gpu_logical_devices.py.
+  static int logical_ids[NL_MAX_DEVICES];
+  if (!device_ids) {
+    const char *env = getenv("NL_LOGICAL_DEVICES");
+    const int k = env ? atoi(env) : 0;
+    if (k > 0) {
+      if (n_devices <= 0) n_devices = k;
+      if (n_devices > NL_MAX_DEVICES) n_devices = NL_MAX_DEVICES;
+      for (int d = 0; d < n_devices; d++) logical_ids[d] = d % visible;
+      device_ids = logical_ids;
+    }
+  }
   if (n_devices <= 0) n_devices = visible;
   if (n_devices > NL_MAX_DEVICES) n_devices = NL_MAX_DEVICES;
   if (n_devices > visible && !device_ids) { set_error("%d devices requested, %d visible", n_devices, visible); return NL_ERR_INVALID; }
+  g_logical = false;
   for (int d = 0; d < n_devices; d++) {
     Device &dv = g_dev[d];
     dv.id = device_ids ? device_ids[d] : d;
@@ -216,11 +238,13 @@ int nl_init(int n_devices, const int *device_ids) {
     uint64_t keep = UINT64_MAX;
     CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     CUDA_TRY(cudaMalloc((void **)&dv.gather, sizeof(int64_t) * 256));
+    for (int o = 0; o < d; o++)
+      if (g_dev[o].id == dv.id) g_logical = true;
   }
   // NVLink peer access between the local devices (shard concat, peer copies)
   for (int a = 0; a < n_devices; a++)
     for (int b = 0; b < n_devices; b++) {
-      if (a == b) continue;
+      if (a == b || g_dev[a].id == g_dev[b].id) continue;
       int can = 0;
       if (cudaDeviceCanAccessPeer(&can, g_dev[a].id, g_dev[b].id) == cudaSuccess && can) {
         cudaSetDevice(g_dev[a].id);
@@ -229,6 +253,17 @@ int nl_init(int n_devices, const int *device_ids) {
       }
     }
   g_ndev = n_devices;
+  if (g_logical) {
+    // two devices of the runtime on one GPU: a cudaMalloc between the launch on one and the launch on the other would
+    // wait for the first kernel, which waits in its mailbox for the second — so the scratch arenas exist up front
+    // (between real GPUs an allocation on one device never waits for a kernel on another)
+    for (int d = 0; d < n_devices; d++) {
+      CUDA_TRY(cudaSetDevice(g_dev[d].id));
+      const int rc = ensure_scratch(g_dev[d], 0, kTileDescOff + ((size_t)64 << 20));
+      if (rc) { g_ndev = 0; return rc; }
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
   return NL_OK;
 }
 
@@ -868,14 +903,19 @@ int nl_comm_init(const void *id, int world_size, int first_rank) {
   int rc = load_nccl();
   if (rc) return rc;
   if (g_world) { set_error("communicator already initialised"); return NL_ERR_INVALID; }
-  ncclUniqueId uid;
-  memcpy(&uid, id, sizeof(uid));
-  NCCL_TRY(g_nccl.GroupStart());
-  for (int d = 0; d < g_ndev; d++) {
-    CUDA_TRY(cudaSetDevice(g_dev[d].id));
-    NCCL_TRY(g_nccl.CommInitRank(&g_dev[d].comm, world_size, uid, first_rank + d));
+  if (g_logical) {
+    // logical devices on one GPU: NCCL refuses two ranks per GPU; the mailboxes below are the communicator
+    if (g_ndev != world_size) { set_error("nl_comm_init: logical devices (NL_LOGICAL_DEVICES) only within one process"); return NL_ERR_INVALID; }
+  } else {
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int d = 0; d < g_ndev; d++) {
+      CUDA_TRY(cudaSetDevice(g_dev[d].id));
+      NCCL_TRY(g_nccl.CommInitRank(&g_dev[d].comm, world_size, uid, first_rank + d));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
   }
-  NCCL_TRY(g_nccl.GroupEnd());
   g_world = world_size;
   g_first_rank = first_rank;
   g_peer_ready = false;
@@ -905,7 +945,7 @@ static int ensure_mailbox(int d) {
 static int setup_local_mailboxes() {
   for (int d = 0; d < g_ndev; d++)
     for (int e = 0; e < g_ndev; e++) {
-      if (d == e) continue;
+      if (d == e || g_dev[d].id == g_dev[e].id) continue;
       int can = 0;
       CUDA_TRY(cudaDeviceCanAccessPeer(&can, g_dev[d].id, g_dev[e].id));
       if (!can) return NL_OK;                      // no P2P between some pair: stay on the NCCL finish
@@ -914,7 +954,7 @@ static int setup_local_mailboxes() {
     int rc = ensure_mailbox(d);
     if (rc) return rc;
     for (int e = 0; e < g_ndev; e++) {
-      if (d == e) continue;
+      if (d == e || g_dev[d].id == g_dev[e].id) continue;
       cudaError_t err = cudaDeviceEnablePeerAccess(g_dev[e].id, 0);
       if (err == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
       else if (err != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(err)); return NL_ERR_CUDA; }
@@ -926,7 +966,7 @@ static int setup_local_mailboxes() {
     cudaMemPool_t pool;
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, g_dev[d].id));
     for (int e = 0; e < g_ndev; e++) {
-      if (d == e) continue;
+      if (d == e || g_dev[d].id == g_dev[e].id) continue;
       cudaMemAccessDesc desc;
       memset(&desc, 0, sizeof(desc));
       desc.location.type = cudaMemLocationTypeDevice;
@@ -1040,6 +1080,7 @@ int nl_finish_reduce(int reduce_op, int dtype, void *const *scalar, int stream) 
   if (rop_of(reduce_op) < 0 || !scalar) { set_error("nl_finish_reduce: bad argument"); return NL_ERR_INVALID; }
   if (g_world <= 1 && g_ndev == 1) return NL_OK;     // a single shard: its partial is the result
   if (!g_world) { set_error("nl_finish_reduce: %d local devices but no communicator (call nl_comm_init)", g_ndev); return NL_ERR_NCCL; }
+  if (g_logical) { set_error("nl_finish_reduce: no NCCL communicator between logical devices of one GPU (use the fused finish)"); return NL_ERR_NCCL; }
   ncclDataType_t t;
   switch (dtype) {
     case NL_I32: t = ncclInt32; break;
@@ -1064,6 +1105,7 @@ int nl_finish_filter(const int64_t *const *count, int64_t *const *offsets, int s
   if (!count || !offsets) { set_error("nl_finish_filter: null"); return NL_ERR_INVALID; }
   const int world = (g_world > 0) ? g_world : 1;
   if (world == 1 && g_ndev > 1) { set_error("nl_finish_filter: %d local devices but no communicator", g_ndev); return NL_ERR_NCCL; }
+  if (g_logical) { set_error("nl_finish_filter: no NCCL communicator between logical devices of one GPU (use the fused exchange)"); return NL_ERR_NCCL; }
   if (world > 1) {
     NCCL_TRY(g_nccl.GroupStart());
     for (int d = 0; d < g_ndev; d++)

@@ -1,5 +1,2 @@
-for rep in 1 2; do
-for c in c4_1 c4_10; do for sc in 1 0; do echo -n "self_clean=$sc "; timeout 120 python tools/profile_one.py $c --log2n 27 --reps 40 --warmup 10 --tune compact_self_clean=$sc | tail -1; done; done
-done
-for c in c4_1 c4_50; do for sc in 1 0; do echo -n "self_clean=$sc "; timeout 120 python tools/profile_one.py $c --log2n 30 --reps 20 --warmup 5 --tune compact_self_clean=$sc | tail -1; done; done
-for c in c4_1; do for sc in 1 0; do echo -n "self_clean=$sc "; timeout 120 python tools/profile_one.py $c --log2n 22 --reps 100 --warmup 10 --tune compact_self_clean=$sc | tail -1; done; done
+timeout 1200 python -m pytest tests/test_gpu_logical_devices.py -x -q 2>&1 | tail -15
+NL_DEVICES=1 python tools/jit_sort_bench.py 27 int64 | tail -1
