@@ -595,6 +595,7 @@ def run_extra(args, rt, lib, ranks, peak, timed, threads):
             rt.launch(plan, [cols[6].ptr], [x.ptr for x in cols[:6]], 0, n1, sizes.ptr)
         ms, _ = timed(c1, 30, 6)
         extra = {"l2": "3 rotating column sets (1.68 GB) > 126 MB L2"}
+        wants = []
         if check:
             ok = True
             for s in range(3):
@@ -604,7 +605,8 @@ def run_extra(args, rt, lib, ranks, peak, timed, threads):
                     cols = [oracle.fill(np.float64, s0, m, 100 + 10 * s + j, 2) for j in range(6)]
                     # nlo_fast_mul6_f64: ((in0*in1)*in2) * ((in3*in4)*in5), the association of the plan above
                     return words_checksum(oracle.fast_mul6_f64(cols, np.empty(m), 8, 1))
-                ok &= got == combine_checksums(oracle_stream(n1, c1_chunk, threads))[1:]
+                wants.append(combine_checksums(oracle_stream(n1, c1_chunk, threads))[1:])
+                ok &= got == wants[-1]
             extra["parity"] = verdict(ok, f"64-bit checksums of all {n1} elements of all 3 result columns")
         report("C1", "C1 Tests/multiplication.py (d*e*f)*(a*b*c)", "f64", n1, 56 * n1, ms, extra, k=30)
         # the same launches replayed from a CUDA graph (one graph = the three column sets in turn)
@@ -614,8 +616,14 @@ def run_extra(args, rt, lib, ranks, peak, timed, threads):
                 c1(None)
             graph = C.c_void_p()
             abi.check(lib.nl_graph_end(0, C.byref(graph)))
+            for s in range(3):                                  # the replays must produce the columns again
+                abi.check(lib.nl_memset(0, 0, C.c_void_p(sets[s][6].ptr), 0, 8 * n1))
             ms, _ = timed(lambda _: abi.check(lib.nl_graph_launch(graph)), 10, 3)
-            report("C1 graph", "C1 replayed from a CUDA graph (nl_graph_*: 3 launches per replay)", "f64", n1, 56 * n1 * 3, ms, {"launches_per_step": 3}, k=10)
+            gextra = {"launches_per_step": 3}
+            if check and wants:
+                okg = all(device_checksum(rt, lib, sets[s][6].ptr, 8 * n1, csum) == wants[s] for s in range(3))
+                gextra["parity"] = verdict(okg, f"the replays rebuilt all 3 zeroed result columns: 64-bit checksums of all {n1} elements each")
+            report("C1 graph", "C1 replayed from a CUDA graph (nl_graph_*: 3 launches per replay)", "f64", n1, 56 * n1 * 3, ms, gextra, k=10)
             lib.nl_graph_destroy(graph)
         except Exception as exc:
             out.append({"id": "C1 graph", "config": "C1 replayed from a CUDA graph", "error": f"{type(exc).__name__}: {exc}"})

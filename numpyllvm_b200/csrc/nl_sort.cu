@@ -7,14 +7,16 @@
 //   sort_histogram_kernel   one read of the keys: the 256-bin histogram of EVERY digit position.
 //                           A position where all keys share one digit needs no pass at all
 //                           (the reference's test data, ints in [1,100), sorts in ONE pass).
-//   per remaining position: chunk_histogram_kernel (per-CTA-chunk digit counts)
-//                           chunk_offsets_kernel   (where each chunk's run of each digit starts)
-//                           scatter_kernel         (stable in-tile ranking with warp match,
-//                                                   keys regrouped by digit in shared memory so
-//                                                   that global stores form runs)
+//   per remaining position  onesweep_kernel (default): the keys are read once from HBM and written once — a tile's
+//                           digit counts are chained to its predecessors' with a decoupled look-back; see the
+//                           comment above the kernel for the form that won the measurements (16 B per 8-byte key).
+//                           nl_tune("sort_algo", 1): chunk_histogram_kernel (per-CTA-chunk digit counts) +
+//                           chunk_offsets_kernel (where each chunk's run of each digit starts) + scatter_kernel
+//                           (in-tile ranking, keys regrouped by digit in shared memory) — round 1's form, 24 B.
+//   nl_sort_sample / nl_sort_split   the device steps of the sort across GPUs (csrc/jit/device_sort.cpp): regularly
+//                           spaced samples, and one sweep of the same kernel whose "digit" is the number of splitters
+//                           below the key.
 //
-// Traffic per executed pass: 8 B read (counts) + 8 B read + 8 B write (scatter) per 8-byte key for this form;
-// 4- and 8-byte keys take the one-sweep form below instead (8 B read + 8 B write).
 // Keys are compared through an order-preserving bijection of their bit patterns (sign flip for
 // ints; the usual float flip, rotated so that negative NaNs also land at the end like NumPy's
 // sort puts every NaN last); the stored values are the original bits.
