@@ -399,6 +399,14 @@ NL_API int nl_sort(int dev, int stream, int dtype, void *keys, void *tmp, int64_
 NL_API int nl_sort_sample(int dev, int stream, int dtype, const void *keys, int64_t count, int n_samples, uint64_t *host_keys);
 NL_API int nl_sort_split(int dev, int stream, int dtype, const void *keys, void *out, int64_t count, const uint64_t *splitters,
                          int n_splitters, int64_t *host_counts);
+/* The same in two steps, so that the runs can go straight to their destinations — buffers on OTHER GPUs included: the
+ * sweep stores run j, stably, to run_dst[j] (device addresses: local memory or peer memory mapped into this device,
+ * nl_comm_init), i.e. the exchange of a sort across GPUs happens inside the kernel, over NVLink, while it regroups.
+ * run_dst[j] may be null for an empty run. */
+NL_API int nl_sort_split_count(int dev, int stream, int dtype, const void *keys, int64_t count, const uint64_t *splitters,
+                               int n_splitters, int64_t *host_counts);
+NL_API int nl_sort_split_scatter(int dev, int stream, int dtype, const void *keys, int64_t count, const uint64_t *splitters,
+                                 int n_splitters, void *const *run_dst);
 
 /* ======================= communicator (NCCL over NVLink) ================== */
 

@@ -244,6 +244,8 @@ _SIGNATURES = {
     "nl_sort": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int64]),
     "nl_sort_sample": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, C.c_int64, C.c_int, C.POINTER(C.c_uint64)]),
     "nl_sort_split": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int64, C.POINTER(C.c_uint64), C.c_int, _I64P]),
+    "nl_sort_split_count": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, C.c_int64, C.POINTER(C.c_uint64), C.c_int, _I64P]),
+    "nl_sort_split_scatter": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, C.c_int64, C.POINTER(C.c_uint64), C.c_int, C.POINTER(_VP)]),
     "nl_gather": (C.c_int, [C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int64, C.POINTER(_VP), C.POINTER(C.c_int64), C.c_int, C.c_int64, _VP]),
     "nl_comm_unique_id": (C.c_int, [_VP]),
     "nl_comm_init": (C.c_int, [_VP, C.c_int, C.c_int]),

@@ -4,9 +4,10 @@
 // Several GPUs: sample sort over NVLink, every key radix-sorted ONCE —
 //   1. one small kernel per GPU reads regularly spaced samples of its (unsorted) shard; the host sorts them and picks
 //      G - 1 splitters (in the kernels' key order, so NaNs stay last);
-//   2. every GPU cuts its shard at the splitters into G runs (nl_sort_split: a counting pass + ONE sweep of the sort's
-//      own kernel with "number of splitters below the key" as the digit) — all GPUs side by side;
-//   3. run j of every shard goes to GPU j by peer copy, in shard order;
+//   2. every GPU counts how many of its keys fall between the splitters (nl_sort_split_count), all GPUs side by side;
+//   3. every GPU cuts its shard with ONE sweep of the sort's own kernel — "number of splitters below the key" as the
+//      digit — that stores run j straight into its place in GPU j's bucket (nl_sort_split_scatter): the exchange
+//      happens inside the kernel, over NVLink peer memory, while it regroups;
 //   4. every GPU sorts what it received — bucket j holds exactly the elements between splitters j - 1 and j, so the
 //      buckets in order are the sorted array;
 //   5. the buckets are re-cut into the engine's regular partition (peer copies again), so the result can meet any
@@ -193,8 +194,8 @@ Storage *device_sort(Storage *in) {
   if (rc != NL_OK) return fail(rc, "jit: page-locked allocation failed");
   host_counts = (int64_t *)(host_samples + S * kSamples);
   lap("page-locked scratch");
-  std::vector<Buf> grouped(S), bucket((size_t)G);
-  auto cleanup = [&]() { free_bufs(grouped); free_bufs(bucket); nl_host_free(host_samples); };
+  std::vector<Buf> bucket((size_t)G);
+  auto cleanup = [&]() { free_bufs(bucket); nl_host_free(host_samples); };
 
   // 1. splitters from regularly spaced samples of every shard
   for (size_t g = 0; g < S && rc == NL_OK; g++)
@@ -210,49 +211,43 @@ Storage *device_sort(Storage *in) {
   for (int j = 1; j < G; j++) splitter[(size_t)j - 1] = samples[(samples.size() * (size_t)j) / (size_t)G];
   lap("samples and splitters");
 
-  // 2. every shard grouped into G runs, all devices side by side
+  // 2. how many keys of every shard fall between the splitters (one counting pass per GPU, all side by side)
   for (size_t g = 0; g < S && rc == NL_OK; g++) {
     const Shard &sh = in->shards[g];
-    grouped[g].dev = sh.dev;
-    grouped[g].count = sh.count;
     for (int j = 0; j <= G; j++) host_counts[g * (size_t)(G + 1) + (size_t)j] = 0;
     if (sh.count == 0) continue;
-    rc = nl_malloc(sh.dev, (size_t)sh.count * es, &grouped[g].ptr);
-    if (rc == NL_OK) rc = nl_sort_split(sh.dev, 0, dtype, sh.ptr, grouped[g].ptr, sh.count, splitter.data(), G - 1, host_counts + g * (size_t)(G + 1));
+    rc = nl_sort_split_count(sh.dev, 0, dtype, sh.ptr, sh.count, splitter.data(), G - 1, host_counts + g * (size_t)(G + 1));
   }
   if (rc == NL_OK) rc = sync_devices(G);
-  if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device sort failed (partition)"); }
-  lap("cut at the splitters");
-  // cut[g][j] = where run j of shard g starts
-  std::vector<std::vector<int64_t>> cut(S, std::vector<int64_t>((size_t)G + 1, 0));
-  for (size_t g = 0; g < S; g++)
-    for (int j = 0; j < G; j++) cut[g][(size_t)j + 1] = cut[g][(size_t)j] + host_counts[g * (size_t)(G + 1) + (size_t)j];
+  if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device sort failed (counting)"); }
+  lap("counts at the splitters");
 
-  // 3. bucket j on device j: run j of every shard, in shard order
+  // 3. bucket j on device j = run j of every shard, in shard order.  The sweep that cuts a shard stores every run
+  //    straight into its place in the destination GPU's bucket — the exchange happens inside the kernel, over NVLink,
+  //    while it regroups (first version of the round: grouped locally, then peer copies — one more pass over every key)
+  std::vector<std::vector<int64_t>> at(S, std::vector<int64_t>((size_t)G, 0));    // where run j of shard g starts in bucket j
   for (int j = 0; j < G; j++) {
     bucket[(size_t)j].dev = j;
-    for (size_t g = 0; g < S; g++) bucket[(size_t)j].count += cut[g][(size_t)j + 1] - cut[g][(size_t)j];
+    for (size_t g = 0; g < S; g++) {
+      at[g][(size_t)j] = bucket[(size_t)j].count;
+      bucket[(size_t)j].count += host_counts[g * (size_t)(G + 1) + (size_t)j];
+    }
     if (bucket[(size_t)j].count == 0) continue;
     rc = nl_malloc(j, (size_t)bucket[(size_t)j].count * es, &bucket[(size_t)j].ptr);
     if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device allocation failed"); }
   }
-  rc = sync_devices(G);
-  for (int j = 0; j < G && rc == NL_OK; j++) {
-    int64_t at = 0;
-    for (size_t g = 0; g < S && rc == NL_OK; g++) {
-      const int64_t n = cut[g][(size_t)j + 1] - cut[g][(size_t)j];
-      if (n == 0) continue;
-      const char *from = (const char *)grouped[g].ptr + (size_t)cut[g][(size_t)j] * es;
-      char *to = (char *)bucket[(size_t)j].ptr + (size_t)at * es;
-      rc = (grouped[g].dev == j) ? nl_memcpy_d2d(j, 0, to, from, (size_t)n * es) : nl_memcpy_peer(j, 0, to, grouped[g].dev, from, (size_t)n * es);
-      at += n;
-    }
+  rc = sync_devices(G);                 // the buckets exist before a peer writes into them
+  for (size_t g = 0; g < S && rc == NL_OK; g++) {
+    const Shard &sh = in->shards[g];
+    if (sh.count == 0) continue;
+    void *dst[16];
+    for (int j = 0; j < G; j++)
+      dst[j] = bucket[(size_t)j].ptr ? (void *)((char *)bucket[(size_t)j].ptr + (size_t)at[g][(size_t)j] * es) : nullptr;
+    rc = nl_sort_split_scatter(sh.dev, 0, dtype, sh.ptr, sh.count, splitter.data(), G - 1, dst);
   }
   if (rc == NL_OK) rc = sync_devices(G);
-  lap("exchange");
-  free_bufs(grouped);
   if (rc != NL_OK) { cleanup(); return fail(rc, "jit: device sort failed (exchange)"); }
-  lap("grouped shards freed");
+  lap("cut + exchange (one sweep)");
 
   // 4. sort the buckets — one host thread per device: nl_sort() synchronises its stream once (it reads the histogram
   //    that tells it which digit positions to skip), and G of those waits in a row were a third of the sort at 8 GPUs

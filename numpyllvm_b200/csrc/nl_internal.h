@@ -112,8 +112,8 @@ int launch_checksum(void *stream, int sm_count, const void *ptr, size_t nbytes, 
 // nl_sort.cu
 int launch_sort(void *stream, int sm_count, int dtype, void *keys, void *tmp, int64_t n);
 int launch_sort_sample(void *stream, int dtype, const void *keys, int64_t n, int k, unsigned long long *host_out);
-int launch_sort_split(void *stream, int sm_count, int dtype, const void *keys, void *out, int64_t n, const unsigned long long *splitters, int m,
-                      int64_t *host_counts);
+int launch_sort_split(void *stream, int sm_count, int mode, int dtype, const void *keys, void *out, int64_t n, const unsigned long long *splitters, int m,
+                      int64_t *host_counts, void *const *run_dst);
 constexpr int kSortMaxSplitters = 15;
 int describe_pipeline_kernel(const nl_plan *plan, bool vec16, char *name, size_t name_len, int *is_static);
 void set_static_kernels_enabled(int on);

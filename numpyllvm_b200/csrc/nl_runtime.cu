@@ -864,23 +864,38 @@ int nl_sort_sample(int dev, int stream, int dtype, const void *keys, int64_t cou
   return launch_sort_sample(g_dev[dev].stream[stream], dtype, keys, count, n_samples, (unsigned long long *)host_keys);
 }
 
-int nl_sort_split(int dev, int stream, int dtype, const void *keys, void *out, int64_t count, const uint64_t *splitters, int n_splitters,
-                  int64_t *host_counts) {
+static int sort_split_any(const char *what, int mode, int dev, int stream, int dtype, const void *keys, void *out, int64_t count, const uint64_t *splitters,
+                          int n_splitters, int64_t *host_counts, void *const *run_dst) {
   int rc = check_dev(dev, stream);
   if (rc) return rc;
-  if (count < 0 || (count > 0 && (!keys || !out)) || n_splitters < 0 || n_splitters > kSortMaxSplitters || (n_splitters > 0 && !splitters) || !host_counts) {
-    set_error("nl_sort_split: bad argument (at most %d splitters)", kSortMaxSplitters);
+  if (count < 0 || (count > 0 && !keys) || n_splitters < 0 || n_splitters > kSortMaxSplitters || (n_splitters > 0 && !splitters) ||
+      (mode == 0 && count > 0 && !out) || (mode != 2 && !host_counts) || (mode == 2 && !run_dst)) {
+    set_error("%s: bad argument (at most %d splitters)", what, kSortMaxSplitters);
     return NL_ERR_INVALID;
   }
   for (int j = 1; j < n_splitters; j++)
-    if (splitters[j] < splitters[j - 1]) { set_error("nl_sort_split: the splitters must ascend"); return NL_ERR_INVALID; }
+    if (splitters[j] < splitters[j - 1]) { set_error("%s: the splitters must ascend", what); return NL_ERR_INVALID; }
   if (count == 0) {
-    for (int j = 0; j <= n_splitters; j++) host_counts[j] = 0;
+    if (mode != 2)
+      for (int j = 0; j <= n_splitters; j++) host_counts[j] = 0;
     return NL_OK;
   }
   CUDA_TRY(cudaSetDevice(g_dev[dev].id));
-  return launch_sort_split(g_dev[dev].stream[stream], g_dev[dev].sm_count, dtype, keys, out, count, (const unsigned long long *)splitters, n_splitters,
-                           host_counts);
+  return launch_sort_split(g_dev[dev].stream[stream], g_dev[dev].sm_count, mode, dtype, keys, out, count, (const unsigned long long *)splitters, n_splitters,
+                           host_counts, run_dst);
+}
+
+int nl_sort_split(int dev, int stream, int dtype, const void *keys, void *out, int64_t count, const uint64_t *splitters, int n_splitters,
+                  int64_t *host_counts) {
+  return sort_split_any("nl_sort_split", 0, dev, stream, dtype, keys, out, count, splitters, n_splitters, host_counts, nullptr);
+}
+
+int nl_sort_split_count(int dev, int stream, int dtype, const void *keys, int64_t count, const uint64_t *splitters, int n_splitters, int64_t *host_counts) {
+  return sort_split_any("nl_sort_split_count", 1, dev, stream, dtype, keys, nullptr, count, splitters, n_splitters, host_counts, nullptr);
+}
+
+int nl_sort_split_scatter(int dev, int stream, int dtype, const void *keys, int64_t count, const uint64_t *splitters, int n_splitters, void *const *run_dst) {
+  return sort_split_any("nl_sort_split_scatter", 2, dev, stream, dtype, keys, nullptr, count, splitters, n_splitters, nullptr, run_dst);
 }
 
 // ======================================================================= communicator

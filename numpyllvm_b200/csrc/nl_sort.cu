@@ -659,26 +659,54 @@ static int sample_impl(cudaStream_t st, const void *keys, int64_t n, int k, unsi
   return NL_OK;
 }
 
-template <typename UK, int kFloat>
-static int split_impl(cudaStream_t st, int sm_count, const void *keys, void *out, int64_t n, const unsigned long long *splitters, int m, int64_t *host_counts) {
+template <typename UK>
+static SplitDigit<UK> make_split_digit(const unsigned long long *splitters, int m) {
   SplitDigit<UK> digit;
   for (int j = 0; j < kMaxSplitters; j++) digit.s[j] = (j < m) ? (UK)splitters[j] : (UK)0;
   digit.m = m;
+  return digit;
+}
+
+// mode 0: count + sweep into `out` (runs back to back); 1: count only; 2: sweep only, run j goes to run_dst[j]
+template <typename UK, int kFloat>
+static int split_impl(cudaStream_t st, int sm_count, int mode, const void *keys, void *out, int64_t n, const unsigned long long *splitters, int m,
+                      int64_t *host_counts, void *const *run_dst) {
+  const SplitDigit<UK> digit = make_split_digit<UK>(splitters, m);
   unsigned long long *ghist = nullptr, *bins = nullptr;
   CUDA_TRY(cudaMallocAsync((void **)&ghist, sizeof(unsigned long long) * 256, st));
   CUDA_TRY(cudaMallocAsync((void **)&bins, sizeof(unsigned long long) * 512, st));
-  CUDA_TRY(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * 256, st));
-  split_count_kernel<UK, kFloat><<<sm_count * 8, kSortBlock, 0, st>>>((const UK *)keys, n, digit, ghist);
-  digit_starts_kernel<<<1, kSortBlock, 0, st>>>(ghist, bins);
-  CUDA_TRY(cudaGetLastError());
-  count_launch(2);
-  static_assert(sizeof(int64_t) == sizeof(unsigned long long), "the counts are copied as they are");
-  CUDA_TRY(cudaMemcpyAsync(host_counts, ghist, sizeof(unsigned long long) * (size_t)(m + 1), cudaMemcpyDeviceToHost, st));
-  unsigned int *scratch = nullptr;
-  size_t scratch_bytes = 0;
-  const int rc = run_sweep<UK, kFloat, 0>(st, sm_count, (const UK *)keys, (UK *)out, n, digit, bins, &scratch, &scratch_bytes);
-  if (rc != NL_OK) return rc;
-  if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
+  if (mode != 2) {
+    CUDA_TRY(cudaMemsetAsync(ghist, 0, sizeof(unsigned long long) * 256, st));
+    split_count_kernel<UK, kFloat><<<sm_count * 8, kSortBlock, 0, st>>>((const UK *)keys, n, digit, ghist);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+    static_assert(sizeof(int64_t) == sizeof(unsigned long long), "the counts are copied as they are");
+    CUDA_TRY(cudaMemcpyAsync(host_counts, ghist, sizeof(unsigned long long) * (size_t)(m + 1), cudaMemcpyDeviceToHost, st));
+  }
+  if (mode == 0) {
+    digit_starts_kernel<<<1, kSortBlock, 0, st>>>(ghist, bins);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+  } else if (mode == 2) {
+    // where each run starts, in elements relative to run 0's destination: the sweep adds a tile's offset inside its
+    // run and stores through `out + offset` — whichever GPU that address belongs to (one unified address space)
+    unsigned long long rel[512];
+    memset(rel, 0, sizeof(rel));
+    void *base = nullptr;
+    for (int j = 0; j <= m && !base; j++) base = run_dst[j];
+    if (!base) { set_error("nl_sort_split_scatter: every run_dst is null"); return NL_ERR_INVALID; }
+    for (int j = 0; j <= m; j++)
+      if (run_dst[j]) rel[j] = (unsigned long long)(((long long)(intptr_t)run_dst[j] - (long long)(intptr_t)base) / (long long)sizeof(UK));
+    CUDA_TRY(cudaMemcpyAsync(bins, rel, sizeof(rel), cudaMemcpyHostToDevice, st));   // pageable source: consumed when the call returns
+    out = base;
+  }
+  if (mode != 1) {
+    unsigned int *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    const int rc = run_sweep<UK, kFloat, 0>(st, sm_count, (const UK *)keys, (UK *)out, n, digit, bins, &scratch, &scratch_bytes);
+    if (rc != NL_OK) return rc;
+    if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
+  }
   CUDA_TRY(cudaFreeAsync(ghist, st));
   CUDA_TRY(cudaFreeAsync(bins, st));
   return NL_OK;
@@ -779,10 +807,10 @@ int launch_sort_sample(void *stream, int dtype, const void *keys, int64_t n, int
 #undef NL_CALL
 }
 
-int launch_sort_split(void *stream, int sm_count, int dtype, const void *keys, void *out, int64_t n, const unsigned long long *splitters, int m,
-                      int64_t *host_counts) {
+int launch_sort_split(void *stream, int sm_count, int mode, int dtype, const void *keys, void *out, int64_t n, const unsigned long long *splitters, int m,
+                      int64_t *host_counts, void *const *run_dst) {
   cudaStream_t st = (cudaStream_t)stream;
-#define NL_CALL(UK, KF) split_impl<UK, KF>(st, sm_count, keys, out, n, splitters, m, host_counts)
+#define NL_CALL(UK, KF) split_impl<UK, KF>(st, sm_count, mode, keys, out, n, splitters, m, host_counts, run_dst)
   NL_SORT_DISPATCH(NL_CALL)
 #undef NL_CALL
 }

@@ -142,3 +142,36 @@ def test_split_groups_stably_at_the_splitters(rt, dtype, n, m):
     assert list(counts) == np.bincount(run, minlength=m + 1).tolist()
     assert np.array_equal(rt.download(out), want)
     d.free(); out.free()
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.uint64], ids=lambda d: np.dtype(d).name)
+@pytest.mark.parametrize("n", [1000, 300_001])
+def test_split_in_two_steps_scatters_the_runs_to_their_destinations(rt, dtype, n):
+    """nl_sort_split_count + nl_sort_split_scatter: every run goes to an address of its own (across GPUs these are
+    the buckets on the destination devices; here separate buffers, one of them missing because its run is empty)."""
+    rng = np.random.default_rng(n)
+    info = np.iinfo(dtype)
+    x = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    m = 5
+    spl = np.sort(order_keys(rng.integers(info.min, info.max, size=m, dtype=dtype, endpoint=True)))
+    spl[0] = 0                                   # run 0 is empty for unsigned keys, almost empty for signed ones
+    spl[3] = spl[2]                              # an empty run in the middle
+    d = rt.upload(x)
+    counts = (C.c_int64 * (m + 1))()
+    p_spl = spl.ctypes.data_as(C.POINTER(C.c_uint64))
+    abi.check(rt.lib.nl_sort_split_count(d.dev, 0, abi.nl_dtype_of(dtype), C.c_void_p(d.ptr), n, p_spl, m, counts))
+    rt.sync()
+    run = np.searchsorted(spl, order_keys(x), side="left")
+    assert list(counts) == np.bincount(run, minlength=m + 1).tolist()
+    bufs = [rt.empty(dtype, c + 3) if c else None for c in counts]       # every run 3 elements into its own buffer
+    es = np.dtype(dtype).itemsize
+    dst = (C.c_void_p * (m + 1))(*[C.c_void_p(b.ptr + 3 * es) if b else C.c_void_p(None) for b in bufs])
+    abi.check(rt.lib.nl_sort_split_scatter(d.dev, 0, abi.nl_dtype_of(dtype), C.c_void_p(d.ptr), n, p_spl, m, dst))
+    rt.sync()
+    for j, b in enumerate(bufs):
+        if b is None:
+            assert not (run == j).any()
+            continue
+        assert np.array_equal(rt.download(b)[3:], x[run == j])           # stable within the run
+        b.free()
+    d.free()

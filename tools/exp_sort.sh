@@ -1,2 +1,4 @@
-build/sort_lab 28 > gpurun_out/sort_lab4.txt 2>&1
-cat gpurun_out/sort_lab4.txt
+python -m pytest tests/test_gpu_sort.py tests/test_jit_gpu.py -x -q 2>&1 | tail -3
+NL_DEBUG_SORT=1 python tools/jit_sort_bench.py 27 int64 2>&1 | tail -9
+python tools/jit_sort_bench.py 27 float64 2>&1 | tail -1
+python tools/jit_sort_bench.py 28 int32 2>&1 | tail -1
