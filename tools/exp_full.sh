@@ -1,2 +1,3 @@
-for c in c4_1 c4_10 c4_50 c4_90 c4d_10 c4d_50; do for pf in 1 0; do echo -n "prefetch=$pf "; timeout 120 python tools/profile_one.py $c --log2n 30 --reps 45 --warmup 10 --tune super_prefetch=$pf | tail -1; done; done
-for c in c4_1 c4_50; do for pf in 1 0; do echo -n "prefetch=$pf "; timeout 120 python tools/profile_one.py $c --log2n 27 --reps 45 --warmup 10 --tune super_prefetch=$pf | tail -1; done; done
+for rep in 1 2; do for sc in 1 0; do echo -n "self_clean=$sc "; timeout 120 python tools/profile_one.py c4_1 --log2n 30 --reps 200 --warmup 25 --tune compact_self_clean=$sc | tail -1; done; done
+for sc in 1 0; do echo -n "self_clean=$sc "; timeout 120 python tools/profile_one.py c4_50 --log2n 30 --reps 100 --warmup 25 --tune compact_self_clean=$sc | tail -1; done
+nvidia-smi --query-gpu=clocks.sm,power.draw,temperature.gpu --format=csv,noheader
