@@ -114,6 +114,8 @@ static int check_peer_status(Device &d) {
   return NL_ERR_NCCL;
 }
 
+void release_cached_blocks(Device &d);     // below, next to nl_malloc's cache
+
 static int ensure_scratch(Device &d, int stream, size_t need) {
   Scratch &s = d.scratch[stream];
   if (s.bytes >= need) return NL_OK;
@@ -124,7 +126,14 @@ static int ensure_scratch(Device &d, int stream, size_t need) {
     s.bytes = 0;
   }
   size_t want = need + (need >> 2) + (1u << 20);
-  CUDA_TRY(cudaMalloc((void **)&s.base, want));
+  cudaError_t e = cudaMalloc((void **)&s.base, want);
+  if (e == cudaErrorMemoryAllocation) {
+    // parked column blocks (nl_malloc's cache) and the pool's free blocks may hold the memory: give them back, retry
+    cudaGetLastError();
+    release_cached_blocks(d);
+    e = cudaMalloc((void **)&s.base, want);
+  }
+  CUDA_TRY(e);
   CUDA_TRY(cudaMemsetAsync(s.base, 0, want, d.stream[stream]));
   s.bytes = want;
   s.compact_clean = true;
@@ -285,6 +294,18 @@ static void cache_release_all(Device &d) {     // caller holds g_cache_mu and ha
   d.cache_free.clear();
   d.cache_bytes = 0;
 }
+
+}  // extern "C"
+void nl::release_cached_blocks(Device &d) {
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    cache_release_all(d);
+  }
+  cudaDeviceSynchronize();
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, d.id) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+}
+extern "C" {
 
 int nl_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -746,9 +767,14 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
     Scratch &sc = d.scratch[stream];
     if (kp.super_k > 0) {
       // the super-tile kernel cleans up after itself (nl_compact_super.cuh): nothing to clear unless another
-      // compaction kernel left its descriptors behind
-      if (!sc.compact_clean || !g_trust_self_clean) CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (sc.compact_clean ? (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE : sc.bytes - kTileDescOff), d.stream[stream]));
-      sc.compact_clean = true;
+      // compaction kernel left its descriptors behind.  While the stream is being captured into a graph nothing runs,
+      // so the captured sequence always carries its own memset and the arena's state stays what it was.
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      CUDA_TRY(cudaStreamIsCapturing(d.stream[stream], &cap));
+      const bool capturing = cap != cudaStreamCaptureStatusNone;
+      if (!sc.compact_clean || !g_trust_self_clean || capturing)
+        CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (sc.compact_clean ? (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE : sc.bytes - kTileDescOff), d.stream[stream]));
+      if (!capturing) sc.compact_clean = true;
     } else {
       CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE, d.stream[stream]));
       sc.compact_clean = false;

@@ -619,3 +619,41 @@ def test_large_blocks_are_recycled_by_size_class(rt, nl):
     abi.check(nl.nl_free(0, C.c_void_p(d)))
     s = alloc(1000)                             # small blocks go straight to the stream-ordered pool
     abi.check(nl.nl_free(0, C.c_void_p(s)))
+
+
+def test_compaction_arena_stays_consistent_across_kernels_and_graph_capture(nl, rt):
+    """The super-tile compaction kernel leaves ticket and descriptors clean for the next launch; the other compaction
+    kernels do not, and a launch that is only CAPTURED into a graph cleans nothing.  Interleave all three and replay."""
+    n_big, n_small = 3_000_001, 5_000
+    x = oracle.fill(np.float64, 0, n_big, 9, 3)
+    dx, out, sizes = rt.upload(x), rt.empty(np.float64, n_big), rt.empty(np.int64, 4)
+
+    def plan_for(t):
+        e = Expr(np.float64)
+        a = e.array()
+        e.materialize(e.filter(a, e.gt(e.ref(a), e.scalar(t))))
+        return abi.compile_plan(e)
+
+    def run(t, n):
+        rt.launch(plan_for(t), [out.ptr], [dx.ptr, None], 0, n, sizes.ptr)
+        k = int(rt.download(sizes, 1)[0])
+        assert np.array_equal(rt.download(out, k), x[:n][x[:n] > t])
+
+    run(0.5, n_big)                      # super-tile kernel
+    assert "compact_super" in rt.last_launch()[0]
+    run(0.5, n_small)                    # plain kernel: leaves its descriptors behind
+    assert "compact_super" not in rt.last_launch()[0]
+    abi.check(nl.nl_graph_begin(0))      # captured, not run: must not count as a clean-up
+    rt.launch(plan_for(0.25), [out.ptr], [dx.ptr, None], 0, n_big, sizes.ptr)
+    g = C.c_void_p()
+    abi.check(nl.nl_graph_end(0, C.byref(g)))
+    run(0.9, n_big)                      # super-tile kernel right after: the arena was still dirty
+    run(0.1, n_big)
+    for _ in range(3):
+        abi.check(nl.nl_graph_launch(g))
+        k = int(rt.download(sizes, 1)[0])
+        assert np.array_equal(rt.download(out, k), x[x > 0.25])
+        run(0.7, n_small)                # dirty again between the replays
+    abi.check(nl.nl_graph_destroy(g))
+    for a in (dx, out, sizes):
+        a.free()
