@@ -163,6 +163,9 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) compact_super_kernel(const _
     __syncthreads();
 
     // ---- store pass: values come back from L2 ----
+    // (Letting warps 1..7 fetch, recompute and rank their first two-pass tile while warp 0 walks the look-back chain —
+    // 14 % of the stall samples sit at that barrier — was measured and dropped: 2-3 % slower on dense input, and the
+    // reordered store pass alone cost the family kernels up to 10 %, round 2.)
     t.keep_in_l2 = false;
     const long long base_out = p.start + sh.prefix;
 #pragma unroll
