@@ -458,7 +458,7 @@ NL_API int nl_set_static_kernels(int mode);
  *                        tile histograms, 16 B per 8-byte key and position); 1 count + scatter per position (24 B; always
  *                        used for 1- and 2-byte keys)
  *   "compact_self_clean" 0: clear the compaction arena (ticket, descriptors) with a memset in front of every launch; default 1:
- *                        the super-tile kernel leaves it clean for the next launch itself
+ *                        two arenas alternate and every super-tile launch zeroes the one its predecessor used
  *   "sort_portion_log2"  keys per launch of the one-sweep form (13..28; 0: default 28) — the tests shrink it to chain launches
  *   "poll_sleep_ns"      back-off between two polls of a look-back descriptor in the super-tile kernel (default 0)
  *   "peer_timeout_ms"    how long a fused multi-GPU finish waits for a peer's mailbox slot before it gives up

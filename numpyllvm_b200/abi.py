@@ -175,7 +175,7 @@ class Expr:
 
 # ---------------------------------------------------------------------------
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libnlkernels.so")
+LIB_PATH = os.environ.get("NL_KERNELS_LIB") or os.path.join(_PKG_DIR, "libnlkernels.so")     # (the override is for A/B builds)
 _lib = None
 
 

@@ -20,7 +20,8 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-BUILD = os.path.join(ROOT, "build")
+SUFFIX = os.environ.get("NL_BUILD_SUFFIX", "")     # A/B builds: build<suffix>/ and libnlkernels<suffix>.so (use with NL_EXTRA_NVCC_FLAGS)
+BUILD = os.path.join(ROOT, "build" + SUFFIX)
 INCLUDE = os.path.join(ROOT, "include")
 
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -66,7 +67,7 @@ def _headers(d):
 def build_kernels(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     """nvcc -> numpyllvm_b200/libnlkernels.so"""
     os.makedirs(BUILD, exist_ok=True)
-    out = os.path.join(PKG, "libnlkernels.so")
+    out = os.path.join(PKG, "libnlkernels" + SUFFIX + ".so")
     hdrs = _headers(CSRC) + _headers(INCLUDE) + [os.path.abspath(__file__)]
     objs, jobs = [], []
     for src in KERNEL_SOURCES:

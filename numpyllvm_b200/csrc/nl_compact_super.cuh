@@ -66,6 +66,22 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) compact_super_kernel(const _
       if (p.out_space[o] == NL_IDX_LOOP) p.out_sizes[o] = p.end;
   }
 
+  // Two arenas (ticket, per-SM ranks, descriptors) alternate between consecutive launches on a stream: this launch
+  // works in one and, while it starts, zeroes what the previous launch left in the other — all CTAs share the work, no
+  // memset launch stands in front of a filter (3-4 us of a 0.2 ms kernel when 8 GPUs share a 2^30-element filter), and
+  // nothing happens at the kernel's end.  (A first form had the LAST CTA to finish zero the launch's own arena: 65,536
+  // descriptors stored by one CTA after everybody else had left, and the extra code at the loop's exit, cost the 2^30
+  // filters 3-4 %.)  The host clears an arena itself after a compaction kernel that does not take part, while a
+  // launch is captured into a graph, and after a (re)allocation: nl_runtime.cu.
+  if (p.clean_count > 0) {
+    for (long long i = (long long)blockIdx.x * kBlock + tid; i < p.clean_count; i += (long long)gridDim.x * kBlock)
+      p.clean_desc[i * kDescStride] = 0ull;
+    if (blockIdx.x == 0) {
+      p.clean_rank[tid & 255] = 0u;
+      if (tid == 0) *p.clean_ticket = 0u;
+    }
+  }
+
   TileT t;
   t.rsum = 0;
   t.rext = T(0);
@@ -198,26 +214,6 @@ __global__ void __launch_bounds__(kBlock, kMinCtas) compact_super_kernel(const _
     // started fourth on its SM then retires: three per SM keep the window at 57 MB (0.85 -> 0.94 of
     // the roofline at 90 %), while sparse inputs keep all four (0.90 vs 0.80 at 1 %).
     if (dense && may_retire) break;
-  }
-
-  // The kernel cleans up after itself: when the last CTA has left its loop nobody reads a descriptor, the ticket or the
-  // per-SM ranks any more, and that CTA zeroes them for the next launch — no memset launch in front of every filter
-  // (3-4 us of a 0.2 ms kernel when 8 GPUs share a 2^30-element filter; the host still clears the arena when another
-  // compaction kernel, which does not clean up, ran in between: nl_runtime.cu).
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    sh.last = (atomicAdd(p.done_ctas, 1u) == gridDim.x - 1) ? 1 : 0;
-    __threadfence();
-  }
-  __syncthreads();
-  if (sh.last) {
-    for (long long i = tid; i < p.n_tiles; i += kBlock) p.tile_desc[i * kDescStride] = 0ull;
-    p.sm_rank[tid & 255] = 0u;
-    if (tid == 0) {
-      *p.tile_ticket = 0u;
-      *p.done_ctas = 0u;
-    }
   }
 }
 

@@ -34,7 +34,11 @@ struct KParams {
   unsigned long long *tile_desc;  // decoupled look-back descriptors, n_tiles entries, zeroed
   unsigned int *tile_ticket;      // dynamic tile counter, zeroed
   unsigned int *sm_rank;          // per SM (%smid): CTAs of this launch that have started there, zeroed (compaction)
-  unsigned int *done_ctas;        // super-tile kernel: CTAs that have left their loop; the last one cleans up for the next launch
+  // super-tile kernel: the arena (ticket, ranks, descriptors) the PREVIOUS launch used; this launch zeroes it while it starts
+  unsigned long long *clean_desc;
+  unsigned int *clean_ticket;
+  unsigned int *clean_rank;
+  int64_t clean_count;            // descriptors to zero in clean_desc (0: nothing to clean)
   unsigned long long *red_partials;  // one 8-byte partial per CTA
   unsigned int *red_ticket;       // self-resetting
   uint32_t step[NL_MAX_STEPS];

@@ -43,7 +43,10 @@ constexpr size_t kTileDescOff = kSmRankOff + 1024;                  // 8 B x n_t
 struct Scratch {
   char *base = nullptr;
   size_t bytes = 0;
-  bool compact_clean = false;    // ticket, ranks and EVERY descriptor are zero (the super-tile kernel leaves them so)
+  // compaction arenas: two of them (ticket + ranks + descriptors each) alternate between consecutive super-tile launches
+  int arena = 0;                 // the one the next super-tile launch works in
+  bool arena_clean[2] = {false, false};   // ticket, ranks and EVERY descriptor of the arena are zero
+  int64_t arena_dirty[2] = {0, 0};        // descriptors its last user left behind (what the next launch zeroes)
 };
 
 struct Device {
@@ -136,7 +139,9 @@ static int ensure_scratch(Device &d, int stream, size_t need) {
   CUDA_TRY(e);
   CUDA_TRY(cudaMemsetAsync(s.base, 0, want, d.stream[stream]));
   s.bytes = want;
-  s.compact_clean = true;
+  s.arena = 0;
+  s.arena_clean[0] = s.arena_clean[1] = true;
+  s.arena_dirty[0] = s.arena_dirty[1] = 0;
   return NL_OK;
 }
 
@@ -396,6 +401,10 @@ int nl_graph_launch(nl_graph graph) {
   Device &d = g_dev[graph->dev];
   CUDA_TRY(cudaSetDevice(d.id));
   CUDA_TRY(cudaGraphLaunch(graph->exec, d.stream[0]));
+  // a captured compaction launch works in arena 0 behind a memset of its own: whatever the replay leaves there is
+  // not what the bookkeeping of the plain launches knows
+  d.scratch[0].arena_clean[0] = false;
+  d.scratch[0].arena_dirty[0] = -1;
   return NL_OK;
 }
 
@@ -753,32 +762,62 @@ static int launch_impl(const nl_plan *plan, void *const *outputs, const void *co
   const int64_t tile = pipeline_tile_elems(plan, vec16, end - start, &kp, d.sm_count);   // also selects the staged compaction pipeline
   kp.n_tiles = (end - start + tile - 1) / tile;
   const bool compact = (plan->flags & NL_PLAN_HAS_COMPACT) != 0;
-  const size_t need = kTileDescOff + (compact ? (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE : 0);
-  rc = ensure_scratch(d, stream, need);
+  // two arenas of (ticket, ranks, descriptors) behind the reduction scratch
+  const size_t arena_head = kTileDescOff - kTileTicketOff;
+  const size_t arena_need = arena_head + (compact ? (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE : 0);
+  rc = ensure_scratch(d, stream, kTileTicketOff + 2 * arena_need + 256);
   if (rc) return rc;
-  char *sb = d.scratch[stream].base;
+  Scratch &sc = d.scratch[stream];
+  char *sb = sc.base;
+  const size_t arena_bytes = ((sc.bytes - kTileTicketOff) / 2) & ~(size_t)255;
   kp.red_ticket = (unsigned int *)(sb + kRedTicketOff);
   kp.red_partials = (unsigned long long *)(sb + kRedPartialsOff);
-  kp.tile_ticket = (unsigned int *)(sb + kTileTicketOff);
-  kp.sm_rank = (unsigned int *)(sb + kSmRankOff);
-  kp.done_ctas = (unsigned int *)(sb + kTileTicketOff + 128);
-  kp.tile_desc = (unsigned long long *)(sb + kTileDescOff);
+  int cur = 0;
+  kp.clean_count = 0;
+  kp.clean_desc = nullptr;
+  kp.clean_ticket = kp.clean_rank = nullptr;
   if (compact) {
-    Scratch &sc = d.scratch[stream];
-    if (kp.super_k > 0) {
-      // the super-tile kernel cleans up after itself (nl_compact_super.cuh): nothing to clear unless another
-      // compaction kernel left its descriptors behind.  While the stream is being captured into a graph nothing runs,
-      // so the captured sequence always carries its own memset and the arena's state stays what it was.
-      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-      CUDA_TRY(cudaStreamIsCapturing(d.stream[stream], &cap));
-      const bool capturing = cap != cudaStreamCaptureStatusNone;
-      if (!sc.compact_clean || !g_trust_self_clean || capturing)
-        CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (sc.compact_clean ? (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE : sc.bytes - kTileDescOff), d.stream[stream]));
-      if (!capturing) sc.compact_clean = true;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(d.stream[stream], &cap));
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    const bool alternate = kp.super_k > 0 && g_trust_self_clean && !capturing;
+    cur = alternate ? sc.arena : 0;
+    char *ab = sb + kTileTicketOff + (size_t)cur * arena_bytes;
+    if (alternate) {
+      // the super-tile kernel zeroes the OTHER arena — what the previous launch left there — while it starts
+      // (nl_compact_super.cuh); the host only steps in when this launch's arena is not known to be clean
+      if (!sc.arena_clean[cur]) CUDA_TRY(cudaMemsetAsync(ab, 0, arena_bytes, d.stream[stream]));
+      const int other = 1 - cur;
+      char *ob = sb + kTileTicketOff + (size_t)other * arena_bytes;
+      if (!sc.arena_clean[other]) {
+        const int64_t cap_desc = (int64_t)((arena_bytes - arena_head) / (8 * NL_DESC_STRIDE));
+        kp.clean_count = (sc.arena_dirty[other] < 0 || sc.arena_dirty[other] > cap_desc) ? cap_desc : sc.arena_dirty[other];
+        if (kp.clean_count < 1) kp.clean_count = 1;                // (ticket and ranks are cleaned with the descriptors)
+        kp.clean_ticket = (unsigned int *)ob;
+        kp.clean_rank = (unsigned int *)(ob + (kSmRankOff - kTileTicketOff));
+        kp.clean_desc = (unsigned long long *)(ob + arena_head);
+      }
+      sc.arena_clean[other] = true;
+      sc.arena_clean[cur] = false;
+      sc.arena_dirty[cur] = kp.n_tiles;
+      sc.arena = other;
     } else {
-      CUDA_TRY(cudaMemsetAsync(sb + kTileTicketOff, 0, (kTileDescOff - kTileTicketOff) + (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE, d.stream[stream]));
-      sc.compact_clean = false;
+      // the other compaction kernels, a launch that is only captured into a graph (nothing runs now, and a replay
+      // must find its arena clean every time), nl_tune("compact_self_clean", 0): arena 0, cleared in front
+      CUDA_TRY(cudaMemsetAsync(ab, 0, arena_head + (size_t)kp.n_tiles * 8 * NL_DESC_STRIDE, d.stream[stream]));
+      if (!capturing) {
+        // (the memset above covers this launch's descriptors only: what an earlier launch left beyond them stays)
+        if (sc.arena_clean[0]) sc.arena_dirty[0] = kp.n_tiles;
+        else if (sc.arena_dirty[0] >= 0 && sc.arena_dirty[0] < kp.n_tiles) sc.arena_dirty[0] = kp.n_tiles;
+        sc.arena_clean[0] = false;
+      }
     }
+  }
+  {
+    char *ab = sb + kTileTicketOff + (size_t)cur * arena_bytes;
+    kp.tile_ticket = (unsigned int *)ab;
+    kp.sm_rank = (unsigned int *)(ab + (kSmRankOff - kTileTicketOff));
+    kp.tile_desc = (unsigned long long *)(ab + arena_head);
   }
 
   LaunchInfo info;
