@@ -1,1 +1,1 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py > gpurun_out/r2_bench_n1_v6.json 2> gpurun_out/r2_bench_n1_v6.err; tail -c 1100 gpurun_out/r2_bench_n1_v6.json
