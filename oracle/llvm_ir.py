@@ -162,10 +162,10 @@ def compile_pipeline(expr: abi.Expr):
             a = b.alloca(acc_t)
             if is_float:
                 init = float("-inf") if nd.op == abi.OP_MAX else float("inf")
+            elif dt.kind == "u":
+                init = 0 if nd.op == abi.OP_MAX else (1 << 64) - 1         # unsigned columns (extension): unsigned order
             else:
-                info_ = np.iinfo(dt)
                 init = _I64_MIN if nd.op == abi.OP_MAX else (1 << 63) - 1   # thunk_methods.cpp:83-91 (LLONG_MIN)
-                del info_
             b.store(ir.Constant(acc_t, init), a)
             extra[idx] = a
     b.branch(cond)
@@ -185,7 +185,9 @@ def compile_pipeline(expr: abi.Expr):
     def widen(v):
         if is_float:
             return b.fpext(v, acc_t) if v.type != acc_t else v
-        return b.sext(v, i64) if v.type != i64 else v
+        if v.type == i64:
+            return v
+        return b.zext(v, i64) if dt.kind == "u" else b.sext(v, i64)
 
     def perform(idx):
         """PerformOperation (compiler.cpp:202-269)."""
@@ -315,7 +317,7 @@ def run(expr: abi.Expr, inputs: Sequence[Optional[np.ndarray]], size: int, threa
                 o = np.zeros(n_el, dtype=out_dtype[k])                       # llvm_initialize_sum_data
             else:   # the identity a chunk without any hit leaves behind (intended max/min)
                 ident = (-np.inf if root_op == abi.OP_MAX else np.inf) if expr.dtype.kind == "f" else (
-                    np.iinfo(expr.dtype).min if root_op == abi.OP_MAX else np.iinfo(expr.dtype).max)
+                    np.iinfo(expr.dtype).min if root_op == abi.OP_MAX else np.iinfo(expr.dtype).max)   # (signed and unsigned alike)
                 o = np.full(n_el, ident, dtype=out_dtype[k])
             del acc_dt
         else:
