@@ -90,3 +90,26 @@ def test_reference_tests_filter_sum_int64(rt, n):
     xa = e.array()
     e.materialize(e.filter(xa, e.ge(e.mul(e.ref(xa), e.scalar(2)), e.scalar(50))))
     same(llvm_ir.run(e, [a, None, None], n), run_pipeline(rt, e, [a, None, None], n))
+
+
+@pytest.mark.parametrize("n", [1023, 100003])
+@pytest.mark.parametrize("dtype", [np.int8, np.int16, np.uint8, np.uint16, np.uint32, np.uint64, np.int32], ids=lambda d: np.dtype(d).name)
+def test_narrow_and_unsigned_columns(rt, n, dtype):
+    # the column types getLLVMType maps (i8, i16, i32) and the unsigned ones it left "todo"
+    rng = np.random.default_rng(n)
+    info = np.iinfo(dtype)
+    a = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    b = rng.integers(info.min, info.max, size=n, dtype=dtype, endpoint=True)
+    e = Expr(dtype)
+    xa, xb = e.array(), e.array()
+    e.materialize(e.sub(e.add(e.mul(xa, xb), e.ref(xa)), e.scalar(3)))
+    same(llvm_ir.run(e, [a, b, None], n), run_pipeline(rt, e, [a, b, None], n))
+    f = Expr(dtype)
+    ya, yb = f.array(), f.array()
+    f.materialize(f.filter(ya, f.gt(yb, f.scalar(int(a[n // 2])))))
+    same(llvm_ir.run(f, [a, b, None], n), run_pipeline(rt, f, [a, b, None], n))
+    for red in ("sum", "max", "min"):
+        g = Expr(dtype)
+        g.materialize(getattr(g, red)(g.array()))
+        (ref,), (got,) = llvm_ir.run(g, [a], n), run_pipeline(rt, g, [a], n)
+        assert got[0] == ref[0], red
